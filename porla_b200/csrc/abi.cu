@@ -1,0 +1,501 @@
+// extern "C" surface of libmultiexp.so: the 14 cgo symbols of
+// /root/reference/porla/Utils/libmultiexp.h:71-84 (Go bodies: /root/reference/porla/main.go) and the
+// new batched / device-resident entry points declared in include/porla_multiexp.h.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <random>
+#include <vector>
+
+#include "../../include/porla_multiexp.h"
+#include "bn254_pairing.hpp"
+#include "host_bn254.hpp"
+#include "msm.h"
+
+using namespace porla;
+using namespace porla::host;
+
+struct porla_table {
+    PointTable t;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------- process state
+// Mirrors the Go globals of main.go:18-29.
+struct KzgState {
+    Fr tau = Fr::zero(), alpha = Fr::zero();
+    int64_t n_samples = 0;
+    std::vector<G1A> srs_g1;        // host copy (internal form)
+    G2A g2[2];                      // [1]G2, [tau]G2
+    bool have_g2 = false;
+    G1A h_mac = G1A::inf();
+    PointTable srs_table;           // resident in HBM
+    bool have_table = false;
+};
+KzgState g_kzg;
+std::mutex g_io_mu;                 // serialises the staging buffers below
+
+// staging: one device buffer for inputs/outputs of host-buffer calls + a stream
+struct Staging {
+    cudaStream_t stream = nullptr;
+    uint8_t* d_buf = nullptr;
+    size_t cap = 0;
+    uint8_t* h_pinned = nullptr;
+    size_t h_cap = 0;
+    void init() {
+        if (!stream) PORLA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    }
+    uint8_t* dev(size_t bytes) {
+        init();
+        if (bytes > cap) {
+            if (d_buf) {
+                PORLA_CUDA(cudaStreamSynchronize(stream));
+                PORLA_CUDA(cudaFree(d_buf));
+            }
+            cap = bytes + bytes / 4 + 4096;
+            PORLA_CUDA(cudaMalloc(&d_buf, cap));
+        }
+        return d_buf;
+    }
+    uint8_t* pinned(size_t bytes) {
+        if (bytes > h_cap) {
+            if (h_pinned) PORLA_CUDA(cudaFreeHost(h_pinned));
+            h_cap = bytes + 4096;
+            PORLA_CUDA(cudaMallocHost(&h_pinned, h_cap));
+        }
+        return h_pinned;
+    }
+};
+Staging g_stage;
+
+[[noreturn]] void die(const char* msg) {
+    fprintf(stderr, "[libmultiexp/porla_b200] FATAL: %s\n", msg);
+    abort();
+}
+
+// Go's copy(dst, src): min(len(dst), len(src)) bytes
+void go_copy(GoSlice* dst, const uint8_t* src, size_t n) {
+    size_t k = (size_t)dst->len < n ? (size_t)dst->len : n;
+    memcpy(dst->data, src, k);
+}
+
+std::vector<Fr> read_poly(const GoSlice* data_in, int64_t n) {
+    if (data_in->len < n * 32) die("data_in shorter than n_samples*32 bytes (Go would panic: slice bounds out of range)");
+    std::vector<Fr> f((size_t)n);
+    const uint8_t* b = (const uint8_t*)data_in->data;
+    for (int64_t i = 0; i < n; i++) f[(size_t)i] = elem_from_be<Fr>(b + 32 * i, 32);
+    return f;
+}
+
+// Host-buffer MSM core.  Scalars/points are copied to the device, points imported, nbatch MSMs
+// run, results copied back.  Rare compressed-flag BN254 inputs are expanded on the host first.
+void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int64_t n, int64_t nbatch,
+                   int scalar_fmt, int point_fmt, uint8_t* out) {
+    if (nbatch <= 0) return;
+    if (n <= 0) {
+        memset(out, 0, (size_t)nbatch * 64);
+        return;
+    }
+    device_init();
+    std::lock_guard<std::mutex> lock(g_io_mu);
+    const size_t total = (size_t)n * (size_t)nbatch;
+    std::vector<uint8_t> fixed;
+    if (curve == kCurveBn254 && point_fmt == PORLA_POINT_BE64) {
+        // G1Affine.SetBytes: a flag in the top two bits selects a 32-byte compressed encoding
+        for (size_t i = 0; i < total; i++) {
+            if (points[64 * i] & 0xC0) {
+                if (fixed.empty()) fixed.assign(points, points + total * 64);
+                G1A p;
+                if (!g1_unmarshal(points + 64 * i, 64, &p)) p = G1A::inf();
+                g1_marshal(p, fixed.data() + 64 * i);
+            }
+        }
+        if (!fixed.empty()) points = fixed.data();
+    }
+    size_t sc_bytes = total * 32, pt_bytes = total * 64;
+    size_t sc_off = 0, pt_off = (sc_bytes + 255) & ~(size_t)255, out_off = pt_off + ((pt_bytes + 255) & ~(size_t)255);
+    uint8_t* d = g_stage.dev(out_off + (size_t)nbatch * 64);
+    cudaStream_t st = g_stage.stream;
+    PORLA_CUDA(cudaMemcpyAsync(d + sc_off, scalars, sc_bytes, cudaMemcpyHostToDevice, st));
+    PORLA_CUDA(cudaMemcpyAsync(d + pt_off, points, pt_bytes, cudaMemcpyHostToDevice, st));
+    PointTable tab;
+    table_import_device(curve, d + pt_off, point_fmt, (uint32_t)total, &tab, st);
+    MsmOptions opt;
+    opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
+    opt.out_fmt = point_fmt;
+    opt.shared_points = 0;
+    msm_device(curve, tab, d + sc_off, (uint32_t)n, (uint32_t)nbatch, opt, d + out_off, nullptr, st);
+    uint8_t* h = g_stage.pinned((size_t)nbatch * 64);
+    PORLA_CUDA(cudaMemcpyAsync(h, d + out_off, (size_t)nbatch * 64, cudaMemcpyDeviceToHost, st));
+    PORLA_CUDA(cudaStreamSynchronize(st));
+    memcpy(out, h, (size_t)nbatch * 64);
+    table_free(&tab);
+}
+
+void upload_srs();
+
+// nbatch commitments over the resident SRS
+void srs_commit_core(const uint8_t* coeffs_be, int64_t n, int64_t nbatch, uint8_t* out) {
+    if (!g_kzg.have_table) {
+        if (g_kzg.srs_g1.empty()) die("SRS not initialised (call init_SRS or init_SRS_from_data first)");
+        upload_srs();
+    }
+    if (n > (int64_t)g_kzg.srs_table.n) die("polynomial longer than the SRS");
+    device_init();
+    std::lock_guard<std::mutex> lock(g_io_mu);
+    size_t sc_bytes = (size_t)n * nbatch * 32;
+    size_t out_off = (sc_bytes + 255) & ~(size_t)255;
+    uint8_t* d = g_stage.dev(out_off + (size_t)nbatch * 64);
+    cudaStream_t st = g_stage.stream;
+    PORLA_CUDA(cudaMemcpyAsync(d, coeffs_be, sc_bytes, cudaMemcpyHostToDevice, st));
+    MsmOptions opt;
+    opt.scalar_be = 1;
+    opt.out_fmt = PORLA_POINT_BE64;
+    opt.shared_points = 1;
+    msm_device(kCurveBn254, g_kzg.srs_table, d, (uint32_t)n, (uint32_t)nbatch, opt, d + out_off, nullptr, st);
+    uint8_t* h = g_stage.pinned((size_t)nbatch * 64);
+    PORLA_CUDA(cudaMemcpyAsync(h, d + out_off, (size_t)nbatch * 64, cudaMemcpyDeviceToHost, st));
+    PORLA_CUDA(cudaStreamSynchronize(st));
+    memcpy(out, h, (size_t)nbatch * 64);
+}
+
+// SRS bases go to HBM once, at init when a device is present (otherwise on the first commit,
+// which aborts loudly if there is still no GPU).
+void upload_srs() {
+    device_init();
+    std::lock_guard<std::mutex> lock(g_io_mu);
+    g_stage.init();
+    if (g_kzg.srs_table.d_points) table_free(&g_kzg.srs_table);
+    std::vector<uint8_t> bytes(g_kzg.srs_g1.size() * 64);
+    for (size_t i = 0; i < g_kzg.srs_g1.size(); i++) g1_marshal(g_kzg.srs_g1[i], bytes.data() + 64 * i);
+    table_import_host(kCurveBn254, bytes.data(), PORLA_POINT_BE64, (uint32_t)g_kzg.srs_g1.size(), &g_kzg.srs_table,
+                      g_stage.stream);
+    g_kzg.have_table = true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ============================================================================ legacy cgo ABI
+void init_key(GoSlice* tau_key_in, GoSlice* alpha_key_in) {
+    g_kzg.tau = elem_from_be<Fr>((const uint8_t*)tau_key_in->data, (size_t)tau_key_in->len);
+    g_kzg.alpha = elem_from_be<Fr>((const uint8_t*)alpha_key_in->data, (size_t)alpha_key_in->len);
+}
+
+void init_SRS(GoInt SRS_size, GoSlice* out, GoInt64* out_len) {
+    if (SRS_size <= 0) die("init_SRS: SRS_size must be positive");
+    g_kzg.n_samples = SRS_size;
+    // kzg.NewSRS: G1[i] = [tau^i]G1, G2 = {G2, [tau]G2}
+    g_kzg.srs_g1.resize((size_t)SRS_size);
+    G1A g = g1_generator();
+    Fr t = Fr::one();
+    for (GoInt i = 0; i < SRS_size; i++) {
+        g_kzg.srs_g1[(size_t)i] = g1_mul(g, t);
+        t = t * g_kzg.tau;
+    }
+    g_kzg.g2[0] = g2_generator();
+    g_kzg.g2[1] = g2_mul(g_kzg.g2[0], g_kzg.tau);
+    g_kzg.have_g2 = true;
+    // SRS.WriteTo: compressed encoder over &G2[0], &G2[1], G1 (uint32 BE length prefix)
+    std::vector<uint8_t> blob(128 + 4 + (size_t)SRS_size * 32);
+    g2_compress(g_kzg.g2[0], blob.data());
+    g2_compress(g_kzg.g2[1], blob.data() + 64);
+    uint32_t cnt = (uint32_t)SRS_size;
+    blob[128] = (uint8_t)(cnt >> 24);
+    blob[129] = (uint8_t)(cnt >> 16);
+    blob[130] = (uint8_t)(cnt >> 8);
+    blob[131] = (uint8_t)cnt;
+    for (GoInt i = 0; i < SRS_size; i++) g1_compress(g_kzg.srs_g1[(size_t)i], blob.data() + 132 + 32 * i);
+    *out_len = (GoInt64)blob.size();
+    go_copy(out, blob.data(), blob.size());
+    // h_MAC = [rho]G1, rho random (main.go:52-59)
+    std::random_device rd;
+    uint8_t rb[32];
+    for (int i = 0; i < 32; i += 4) {
+        uint32_t v = rd();
+        memcpy(rb + i, &v, 4);
+    }
+    g_kzg.h_mac = g1_mul(g, elem_from_be<Fr>(rb, 32));
+    g_kzg.have_table = false;
+    if (device_available()) upload_srs();
+}
+
+void init_SRS_from_data(GoInt SRS_size, GoSlice* in) {
+    if (SRS_size <= 0) die("init_SRS_from_data: SRS_size must be positive");
+    const uint8_t* b = (const uint8_t*)in->data;
+    if (in->len < 132) die("init_SRS_from_data: blob too short");
+    g_kzg.n_samples = SRS_size;
+    if (!g2_decompress(b, &g_kzg.g2[0]) || !g2_decompress(b + 64, &g_kzg.g2[1])) die("init_SRS_from_data: bad G2 point");
+    g_kzg.have_g2 = true;
+    uint32_t cnt = ((uint32_t)b[128] << 24) | ((uint32_t)b[129] << 16) | ((uint32_t)b[130] << 8) | b[131];
+    if ((GoInt)in->len < 132 + (GoInt)cnt * 32) die("init_SRS_from_data: blob truncated");
+    g_kzg.srs_g1.resize(cnt);
+    for (uint32_t i = 0; i < cnt; i++)
+        if (!g1_unmarshal(b + 132 + 32 * (size_t)i, 32, &g_kzg.srs_g1[i])) die("init_SRS_from_data: bad G1 point");
+    g_kzg.have_table = false;
+    if (device_available()) upload_srs();
+}
+
+void compute_digest(GoSlice* data_in, GoSlice* data_out) {
+    std::vector<Fr> f = read_poly(data_in, g_kzg.n_samples);
+    Fr fx = poly_eval(f, g_kzg.tau) * g_kzg.alpha;
+    G1A base = g_kzg.srs_g1.empty() ? g1_generator() : g_kzg.srs_g1[0];
+    uint8_t buf[64];
+    g1_marshal(g1_mul(base, fx), buf);
+    go_copy(data_out, buf, 64);
+}
+
+void compute_digest_complement(GoSlice* data_in, GoSlice* data_out) {
+    Fr s = elem_from_be<Fr>((const uint8_t*)data_in->data, (size_t)data_in->len);
+    uint8_t buf[64];
+    g1_marshal(g1_mul(g_kzg.h_mac, s), buf);
+    go_copy(data_out, buf, 64);
+}
+
+void compute_digest_from_srs(GoSlice* data_in, GoSlice* data_out) {
+    if (data_in->len < g_kzg.n_samples * 32) die("compute_digest_from_srs: data_in too short");
+    uint8_t buf[64];
+    srs_commit_core((const uint8_t*)data_in->data, g_kzg.n_samples, 1, buf);
+    go_copy(data_out, buf, 64);
+}
+
+void compute_multi_exp(GoSlice* scalars, GoSlice* points, GoInt length, GoSlice* result_out) {
+    if (length < 0 || scalars->len < length * 32 || points->len < length * 64)
+        die("compute_multi_exp: slices shorter than length (Go would panic: slice bounds out of range)");
+    uint8_t buf[64];
+    msm_host_core(kCurveBn254, (const uint8_t*)scalars->data, (const uint8_t*)points->data, length, 1,
+                  PORLA_SCALAR_BE32, PORLA_POINT_BE64, buf);
+    go_copy(result_out, buf, 64);
+}
+
+GoUint8 compare_commitment(GoSlice* commitment_a, GoSlice* commitment_b) {
+    G1A a = G1A::inf(), b = G1A::inf();
+    g1_unmarshal((const uint8_t*)commitment_a->data, (size_t)commitment_a->len, &a);
+    g1_unmarshal((const uint8_t*)commitment_b->data, (size_t)commitment_b->len, &b);
+    if (!(a.x == b.x && a.y == b.y)) {
+        printf("error KZG commitment\n");
+        return 0;
+    }
+    return 1;
+}
+
+void create_proof(GoUint64 random_point, GoSlice* data_in, GoSlice* commitment_out, GoSlice* proof_H,
+                  GoSlice* proof_point, GoSlice* proof_claim) {
+    const int64_t n = g_kzg.n_samples;
+    std::vector<Fr> f = read_poly(data_in, n);
+    Fr z = elem_from_u64<Fr>(random_point);
+    Fr y = poly_eval(f, z);
+    std::vector<Fr> h = poly_quotient(f, z);
+    // both commitments in one launch sequence: MSM 0 = f (n terms), MSM 1 = h padded with a zero
+    std::vector<uint8_t> coeffs((size_t)n * 64, 0);
+    memcpy(coeffs.data(), data_in->data, (size_t)n * 32);
+    for (size_t i = 0; i < h.size(); i++) elem_to_be(h[i], coeffs.data() + (size_t)n * 32 + 32 * i);
+    uint8_t res[128];
+    srs_commit_core(coeffs.data(), n, 2, res);
+    go_copy(commitment_out, res, 64);
+    go_copy(proof_H, res + 64, 64);
+    uint8_t buf[32];
+    elem_to_be(z, buf);
+    go_copy(proof_point, buf, 32);
+    elem_to_be(y, buf);
+    go_copy(proof_claim, buf, 32);
+}
+
+GoUint8 verify_proof(GoSlice* commitment_in, GoSlice* proof_H, GoSlice* proof_point, GoSlice* proof_claim) {
+    G1A c = G1A::inf(), hq = G1A::inf();
+    g1_unmarshal((const uint8_t*)commitment_in->data, (size_t)commitment_in->len, &c);
+    g1_unmarshal((const uint8_t*)proof_H->data, (size_t)proof_H->len, &hq);
+    Fr z = elem_from_be<Fr>((const uint8_t*)proof_point->data, (size_t)proof_point->len);
+    Fr y = elem_from_be<Fr>((const uint8_t*)proof_claim->data, (size_t)proof_claim->len);
+    if (!g_kzg.have_g2) die("verify_proof: SRS not initialised");
+    // e(C - [y]G1, G2) * e(-H, [tau]G2 - [z]G2) == 1
+    G1A yg = g1_mul(g_kzg.srs_g1.empty() ? g1_generator() : g_kzg.srs_g1[0], y);
+    G1A lhs = g1_add(c, yg.neg());
+    G2A zg2 = g2_mul(g_kzg.g2[0], z);
+    G2A rhs2 = g2_add(g_kzg.g2[1], g2_neg(zg2));
+    G1A ps[2] = {lhs, hq.neg()};
+    G2A qs[2] = {g_kzg.g2[0], rhs2};
+    if (!pairing_product_is_one(ps, qs, 2)) {
+        printf("Verifying is wrong\n");
+        return 0;
+    }
+    return 1;
+}
+
+void add_point(GoSlice* point_a, GoSlice* point_b) {
+    G1A a = G1A::inf(), b = G1A::inf();
+    g1_unmarshal((const uint8_t*)point_a->data, (size_t)point_a->len, &a);
+    g1_unmarshal((const uint8_t*)point_b->data, (size_t)point_b->len, &b);
+    uint8_t buf[64];
+    g1_marshal(g1_add(a, b), buf);
+    go_copy(point_a, buf, 64);
+}
+
+void mult_point(GoSlice* point_a, GoSlice* scalar) {
+    G1A p = G1A::inf();
+    g1_unmarshal((const uint8_t*)point_a->data, (size_t)point_a->len, &p);
+    Fr s = elem_from_be<Fr>((const uint8_t*)scalar->data, (size_t)scalar->len);
+    uint8_t buf[64];
+    g1_marshal(g1_mul(p, s), buf);
+    go_copy(point_a, buf, 64);
+}
+
+void neg_point(GoSlice* point) {
+    G1A p = G1A::inf();
+    g1_unmarshal((const uint8_t*)point->data, (size_t)point->len, &p);
+    uint8_t buf[64];
+    g1_marshal(p.neg(), buf);
+    go_copy(point, buf, 64);
+}
+
+void set_inf_point(GoSlice* point) {
+    uint8_t buf[64] = {0};
+    go_copy(point, buf, 64);
+}
+
+// ============================================================================ new entry points
+int porla_device_init(void) { return device_init(); }
+uint64_t porla_launch_count(void) { return launches_issued(); }
+int porla_choose_window(int curve, int64_t n, int64_t nbatch) { return choose_window(curve, (uint32_t)n, (uint32_t)nbatch); }
+
+void compute_multi_exp_batch(GoSlice* scalars, GoSlice* points, GoInt length, GoInt batch, GoSlice* results_out) {
+    if (length < 0 || batch < 0 || scalars->len < length * batch * 32 || points->len < length * batch * 64)
+        die("compute_multi_exp_batch: slices shorter than batch*length");
+    std::vector<uint8_t> buf((size_t)batch * 64);
+    msm_host_core(kCurveBn254, (const uint8_t*)scalars->data, (const uint8_t*)points->data, length, batch,
+                  PORLA_SCALAR_BE32, PORLA_POINT_BE64, buf.data());
+    go_copy(results_out, buf.data(), buf.size());
+}
+
+void compute_digest_from_srs_batch(GoSlice* data_in, GoInt batch, GoSlice* data_out) {
+    if (batch < 0 || data_in->len < g_kzg.n_samples * 32 * batch) die("compute_digest_from_srs_batch: data_in too short");
+    std::vector<uint8_t> buf((size_t)batch * 64);
+    if (batch) srs_commit_core((const uint8_t*)data_in->data, g_kzg.n_samples, batch, buf.data());
+    go_copy(data_out, buf.data(), buf.size());
+}
+
+porla_table* porla_table_create(int curve, const void* points, int64_t n, int point_fmt, int on_device, void* cuda_stream) {
+    device_init();
+    porla_table* t = new porla_table();
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (on_device) table_import_device(curve, (const uint8_t*)points, point_fmt, (uint32_t)n, &t->t, st);
+    else table_import_host(curve, (const uint8_t*)points, point_fmt, (uint32_t)n, &t->t, st);
+    return t;
+}
+
+porla_table* porla_table_create_multiples(int curve, const void* scalars, int64_t n, int scalar_fmt, int on_device,
+                                          void* cuda_stream) {
+    device_init();
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    // generator as a 1-entry table
+    uint8_t gen[64] = {0};
+    if (curve == kCurveBn254) {
+        gen[31] = 1;
+        gen[63] = 2;
+    } else {
+        static const uint8_t sg[64] = {
+            0x79, 0xBE, 0x66, 0x7E, 0xF9, 0xDC, 0xBB, 0xAC, 0x55, 0xA0, 0x62, 0x95, 0xCE, 0x87, 0x0B, 0x07,
+            0x02, 0x9B, 0xFC, 0xDB, 0x2D, 0xCE, 0x28, 0xD9, 0x59, 0xF2, 0x81, 0x5B, 0x16, 0xF8, 0x17, 0x98,
+            0x48, 0x3A, 0xDA, 0x77, 0x26, 0xA3, 0xC4, 0x65, 0x5D, 0xA4, 0xFB, 0xFC, 0x0E, 0x11, 0x08, 0xA8,
+            0xFD, 0x17, 0xB4, 0x48, 0xA6, 0x85, 0x54, 0x19, 0x9C, 0x47, 0xD0, 0x8F, 0xFB, 0x10, 0xD4, 0xB8};
+        memcpy(gen, sg, 64);
+    }
+    PointTable g;
+    table_import_host(curve, gen, PORLA_POINT_BE64, 1, &g, st);
+    const uint8_t* d_sc = (const uint8_t*)scalars;
+    uint8_t* d_tmp = nullptr;
+    if (!on_device) {
+        PORLA_CUDA(cudaMalloc(&d_tmp, (size_t)n * 32));
+        PORLA_CUDA(cudaMemcpyAsync(d_tmp, scalars, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+        d_sc = d_tmp;
+    }
+    porla_table* t = new porla_table();
+    void* d_aff = nullptr;
+    PORLA_CUDA(cudaMalloc(&d_aff, (size_t)(n ? n : 1) * 64));
+    scalar_mul_device(curve, g, d_sc, scalar_fmt == PORLA_SCALAR_BE32, (uint32_t)n, d_aff, st);
+    // re-import through the external format so infinity flags are derived the same way
+    uint8_t* d_ext = nullptr;
+    PORLA_CUDA(cudaMalloc(&d_ext, (size_t)(n ? n : 1) * 64));
+    export_points_device(curve, d_aff, (uint32_t)n, PORLA_POINT_LE64, d_ext, st);
+    table_import_device(curve, d_ext, PORLA_POINT_LE64, (uint32_t)n, &t->t, st);
+    PORLA_CUDA(cudaStreamSynchronize(st));
+    PORLA_CUDA(cudaFree(d_ext));
+    PORLA_CUDA(cudaFree(d_aff));
+    if (d_tmp) PORLA_CUDA(cudaFree(d_tmp));
+    table_free(&g);
+    return t;
+}
+
+int64_t porla_table_len(const porla_table* t) { return t->t.n; }
+int64_t porla_table_num_infinity(const porla_table* t) { return t->t.n_inf; }
+
+void porla_table_export(const porla_table* t, int point_fmt, void* out, int on_device, void* cuda_stream) {
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (on_device) {
+        export_points_device(t->t.curve, t->t.d_points, t->t.n, point_fmt, (uint8_t*)out, st);
+        return;
+    }
+    uint8_t* d = nullptr;
+    PORLA_CUDA(cudaMalloc(&d, (size_t)(t->t.n ? t->t.n : 1) * 64));
+    export_points_device(t->t.curve, t->t.d_points, t->t.n, point_fmt, d, st);
+    PORLA_CUDA(cudaMemcpyAsync(out, d, (size_t)t->t.n * 64, cudaMemcpyDeviceToHost, st));
+    PORLA_CUDA(cudaStreamSynchronize(st));
+    PORLA_CUDA(cudaFree(d));
+}
+
+void porla_table_destroy(porla_table* t) {
+    if (!t) return;
+    table_free(&t->t);
+    delete t;
+}
+
+void porla_msm_device(const porla_table* t, const void* d_scalars, int64_t n, int64_t nbatch, int scalar_fmt,
+                      int shared_points, int window_bits, int out_fmt, void* d_out, void* d_out_xyzz, void* cuda_stream) {
+    int64_t need = shared_points ? n : n * nbatch;
+    if (need > (int64_t)t->t.n) die("porla_msm_device: table shorter than the MSM");
+    MsmOptions opt;
+    opt.window_bits = window_bits;
+    opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
+    opt.out_fmt = out_fmt;
+    opt.shared_points = shared_points;
+    msm_device(t->t.curve, t->t, (const uint8_t*)d_scalars, (uint32_t)n, (uint32_t)nbatch, opt, (uint8_t*)d_out, d_out_xyzz,
+               (cudaStream_t)cuda_stream);
+}
+
+void porla_msm_combine_device(int curve, const void* d_parts, int64_t count, int64_t nbatch, int out_fmt, void* d_out,
+                              void* cuda_stream) {
+    msm_combine_device(curve, d_parts, (uint32_t)count, (uint32_t)nbatch, out_fmt, (uint8_t*)d_out, (cudaStream_t)cuda_stream);
+}
+
+void porla_msm_host(int curve, const void* scalars, const void* points, int64_t n, int64_t nbatch, int scalar_fmt,
+                    int point_fmt, void* out) {
+    msm_host_core(curve, (const uint8_t*)scalars, (const uint8_t*)points, n, nbatch, scalar_fmt, point_fmt, (uint8_t*)out);
+}
+
+void porla_scalar_mul_batch_device(const porla_table* t, const void* d_scalars, int64_t n, int scalar_fmt, int out_fmt,
+                                   void* d_out, void* cuda_stream) {
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    void* d_aff = nullptr;
+    PORLA_CUDA(cudaMallocAsync(&d_aff, (size_t)(n ? n : 1) * 64, st));
+    scalar_mul_device(t->t.curve, t->t, (const uint8_t*)d_scalars, scalar_fmt == PORLA_SCALAR_BE32, (uint32_t)n, d_aff, st);
+    export_points_device(t->t.curve, d_aff, (uint32_t)n, out_fmt, (uint8_t*)d_out, st);
+    PORLA_CUDA(cudaFreeAsync(d_aff, st));
+}
+
+void porla_debug_field_mul(int curve, const void* a, const void* b, int64_t n, void* out) {
+    device_init();
+    std::lock_guard<std::mutex> lock(g_io_mu);
+    size_t bytes = (size_t)n * 32;
+    uint8_t* d = g_stage.dev(3 * bytes + 1024);
+    cudaStream_t st = g_stage.stream;
+    PORLA_CUDA(cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, st));
+    PORLA_CUDA(cudaMemcpyAsync(d + bytes, b, bytes, cudaMemcpyHostToDevice, st));
+    field_mul_device(curve, d, d + bytes, (uint32_t)n, d + 2 * bytes, st);
+    PORLA_CUDA(cudaMemcpyAsync(out, d + 2 * bytes, bytes, cudaMemcpyDeviceToHost, st));
+    PORLA_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // extern "C"

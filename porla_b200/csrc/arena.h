@@ -1,0 +1,44 @@
+// Device scratch arena shared by the per-curve MSM drivers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "msm.h"
+
+namespace porla {
+
+// One growable device block, carved per call.  Grown geometrically, never shrunk; sized for
+// 180 GB parts (a 2^26-point MSM needs ~5 GB of scratch).
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t cap = 0, used = 0;
+    void reset() { used = 0; }
+    void reserve(size_t bytes, cudaStream_t stream) {
+        if (bytes <= cap) return;
+        if (base) {
+            PORLA_CUDA(cudaStreamSynchronize(stream));
+            PORLA_CUDA(cudaDeviceSynchronize());
+            PORLA_CUDA(cudaFree(base));
+        }
+        size_t want = bytes + bytes / 8 + (1u << 20);
+        PORLA_CUDA(cudaMalloc(&base, want));
+        cap = want;
+    }
+    template <class T>
+    T* take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        T* p = reinterpret_cast<T*>(base + used);
+        used += bytes;
+        if (used > cap) {
+            fprintf(stderr, "[libmultiexp/porla_b200] FATAL: arena overflow\n");
+            abort();
+        }
+        return p;
+    }
+    static size_t padded(size_t count, size_t elt) { return (count * elt + 255) & ~(size_t)255; }
+};
+
+}  // namespace porla

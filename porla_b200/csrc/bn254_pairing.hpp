@@ -1,0 +1,353 @@
+// Host-only BN254 G2 arithmetic and optimal-ate pairing check, needed by two O(1) entry points
+// of the legacy C-ABI: init_SRS (the SRS blob carries [1]G2 and [tau]G2, main.go:46-49) and
+// verify_proof (kzg.Verify, main.go:187).  Out of the MSM hot path by construction; written for
+// clarity, not speed (affine G2, schoolbook Fp12, plain square-and-multiply final exponent).
+//
+// Tower: Fp2 = Fp[i]/(i^2+1), Fp12 = Fp2[w]/(w^6 - xi), xi = 9 + i.  Twist E': y^2 = x^3 + 3/xi,
+// untwist (x', y') -> (x' w^2, y' w^3).
+#pragma once
+#include "host_bn254.hpp"
+
+namespace porla {
+namespace host {
+
+struct Fq2 {
+    Fq a0, a1;  // a0 + a1*i
+    static Fq2 zero() { return Fq2{Fq::zero(), Fq::zero()}; }
+    static Fq2 one() { return Fq2{Fq::one(), Fq::zero()}; }
+    bool is_zero() const { return a0.is_zero() && a1.is_zero(); }
+    bool operator==(const Fq2& o) const { return a0 == o.a0 && a1 == o.a1; }
+    Fq2 operator+(const Fq2& o) const { return Fq2{a0 + o.a0, a1 + o.a1}; }
+    Fq2 operator-(const Fq2& o) const { return Fq2{a0 - o.a0, a1 - o.a1}; }
+    Fq2 neg() const { return Fq2{a0.neg(), a1.neg()}; }
+    Fq2 conj() const { return Fq2{a0, a1.neg()}; }
+    Fq2 operator*(const Fq2& o) const {
+        Fq t0 = a0 * o.a0, t1 = a1 * o.a1;
+        Fq t2 = (a0 + a1) * (o.a0 + o.a1);
+        return Fq2{t0 - t1, t2 - t0 - t1};
+    }
+    Fq2 sqr() const { return *this * *this; }
+    Fq2 scale(const Fq& k) const { return Fq2{a0 * k, a1 * k}; }
+    Fq2 inverse() const {
+        Fq n = (a0.sqr() + a1.sqr()).inverse();
+        return Fq2{a0 * n, (a1 * n).neg()};
+    }
+    Fq2 dbl() const { return *this + *this; }
+};
+
+inline Fq2 fq2_pow(const Fq2& a, const uint32_t* e, int nlimbs) {
+    Fq2 r = Fq2::one();
+    for (int i = nlimbs * 32 - 1; i >= 0; i--) {
+        r = r.sqr();
+        if ((e[i >> 5] >> (i & 31)) & 1u) r = r * a;
+    }
+    return r;
+}
+
+inline Fq2 fq2_xi() { return Fq2{elem_from_u64<Fq>(9), elem_from_u64<Fq>(1)}; }
+
+// sqrt in Fq2 via the norm (p = 3 mod 4); false if a is a non-residue
+inline bool fq2_sqrt(const Fq2& a, Fq2* out) {
+    if (a.is_zero()) {
+        *out = a;
+        return true;
+    }
+    Fq half = elem_from_u64<Fq>(2).inverse();
+    if (a.a1.is_zero()) {
+        Fq s;
+        if (fq_sqrt(a.a0, &s)) {
+            *out = Fq2{s, Fq::zero()};
+            return true;
+        }
+        if (fq_sqrt(a.a0.neg(), &s)) {
+            *out = Fq2{Fq::zero(), s};
+            return true;
+        }
+        return false;
+    }
+    Fq n;
+    if (!fq_sqrt(a.a0.sqr() + a.a1.sqr(), &n)) return false;
+    Fq t = (a.a0 + n) * half, x0;
+    if (!fq_sqrt(t, &x0)) {
+        t = (a.a0 - n) * half;
+        if (!fq_sqrt(t, &x0)) return false;
+    }
+    Fq x1 = a.a1 * (x0.dbl()).inverse();
+    Fq2 r{x0, x1};
+    if (!(r.sqr() == a)) return false;
+    *out = r;
+    return true;
+}
+
+// ---------------------------------------------------------------------------- G2 (affine)
+struct G2A {
+    Fq2 x, y;
+    bool inf = true;
+};
+
+inline Fq2 g2_b() {
+    static const Fq2 b = Fq2{elem_from_u64<Fq>(3), Fq::zero()} * fq2_xi().inverse();
+    return b;
+}
+
+inline Fq fq_from_hex_be(const char* hex) {
+    uint8_t b[32];
+    for (int i = 0; i < 32; i++) {
+        auto nib = [](char c) -> int { return c <= '9' ? c - '0' : (c | 32) - 'a' + 10; };
+        b[i] = (uint8_t)((nib(hex[2 * i]) << 4) | nib(hex[2 * i + 1]));
+    }
+    return elem_from_be<Fq>(b, 32);
+}
+
+// the generator gnark-crypto / EIP-197 use (checked on-curve by tests/test_host_abi.py)
+inline G2A g2_generator() {
+    G2A g;
+    g.x = Fq2{fq_from_hex_be("1800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed"),
+              fq_from_hex_be("198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c2")};
+    g.y = Fq2{fq_from_hex_be("12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa"),
+              fq_from_hex_be("090689d0585ff075ec9e99ad690c3395bc4b313370b38ef355acdadcd122975b")};
+    g.inf = false;
+    return g;
+}
+
+inline G2A g2_neg(const G2A& p) {
+    G2A r = p;
+    if (!r.inf) r.y = r.y.neg();
+    return r;
+}
+inline bool g2_on_curve(const G2A& p) { return p.inf || p.y.sqr() == p.x.sqr() * p.x + g2_b(); }
+
+// chord/tangent; *lambda (optional) receives the slope used (for the Miller loop)
+inline G2A g2_add(const G2A& p, const G2A& q, Fq2* lambda = nullptr) {
+    if (p.inf) return q;
+    if (q.inf) return p;
+    Fq2 lam;
+    if (p.x == q.x) {
+        if (!(p.y == q.y) || p.y.is_zero()) return G2A{};
+        Fq2 xx = p.x.sqr();
+        lam = (xx.dbl() + xx) * p.y.dbl().inverse();
+    } else {
+        lam = (q.y - p.y) * (q.x - p.x).inverse();
+    }
+    if (lambda) *lambda = lam;
+    G2A r;
+    r.x = lam.sqr() - p.x - q.x;
+    r.y = lam * (p.x - r.x) - p.y;
+    r.inf = false;
+    return r;
+}
+inline G2A g2_mul(const G2A& p, const Fr& k_internal) {
+    Fr k = k_internal.from_internal();
+    G2A r;
+    for (int i = 255; i >= 0; i--) {
+        r = g2_add(r, r);
+        if ((k.v[i >> 5] >> (i & 31)) & 1u) r = g2_add(r, p);
+    }
+    return r;
+}
+
+// gnark E2 ordering: compare A1 first, then A0
+inline bool fq2_lex_largest(const Fq2& y) { return y.a1.is_zero() ? fq_lex_largest(y.a0) : fq_lex_largest(y.a1); }
+
+// G2Affine.Bytes(): X.A1 || X.A0 big-endian, flags in the top two bits of byte 0
+inline void g2_compress(const G2A& p, uint8_t* out64) {
+    if (p.inf) {
+        memset(out64, 0, 64);
+        out64[0] = kFlagCompressedInf;
+        return;
+    }
+    elem_to_be(p.x.a1, out64);
+    elem_to_be(p.x.a0, out64 + 32);
+    out64[0] |= fq2_lex_largest(p.y) ? kFlagLargest : kFlagSmallest;
+}
+inline bool g2_decompress(const uint8_t* b, G2A* out) {
+    uint8_t flag = b[0] & 0xC0;
+    if (flag == kFlagCompressedInf) {
+        *out = G2A{};
+        return true;
+    }
+    if (flag == kFlagUncompressed) return false;  // 128-byte form never appears in the SRS blob
+    uint8_t xb[32];
+    memcpy(xb, b, 32);
+    xb[0] &= 0x3F;
+    G2A p;
+    p.x = Fq2{elem_from_be<Fq>(b + 32, 32), elem_from_be<Fq>(xb, 32)};
+    if (!fq2_sqrt(p.x.sqr() * p.x + g2_b(), &p.y)) return false;
+    if (fq2_lex_largest(p.y) != (flag == kFlagLargest)) p.y = p.y.neg();
+    p.inf = false;
+    *out = p;
+    return true;
+}
+
+// ---------------------------------------------------------------------------- Fp12
+struct Fq12 {
+    Fq2 c[6];  // sum c[k] w^k, w^6 = xi
+    static Fq12 one() {
+        Fq12 r;
+        for (int k = 0; k < 6; k++) r.c[k] = Fq2::zero();
+        r.c[0] = Fq2::one();
+        return r;
+    }
+    bool is_one() const {
+        if (!(c[0] == Fq2::one())) return false;
+        for (int k = 1; k < 6; k++)
+            if (!c[k].is_zero()) return false;
+        return true;
+    }
+    Fq12 operator*(const Fq12& o) const {
+        Fq2 t[11];
+        for (int k = 0; k < 11; k++) t[k] = Fq2::zero();
+        for (int i = 0; i < 6; i++) {
+            if (c[i].is_zero()) continue;
+            for (int j = 0; j < 6; j++) {
+                if (o.c[j].is_zero()) continue;
+                t[i + j] = t[i + j] + c[i] * o.c[j];
+            }
+        }
+        Fq12 r;
+        Fq2 xi = fq2_xi();
+        for (int k = 0; k < 6; k++) r.c[k] = k < 5 ? t[k] + t[k + 6] * xi : t[k];
+        return r;
+    }
+    Fq12 sqr() const { return *this * *this; }
+    // f^(p^6): w -> -w
+    Fq12 conj6() const {
+        Fq12 r = *this;
+        r.c[1] = r.c[1].neg();
+        r.c[3] = r.c[3].neg();
+        r.c[5] = r.c[5].neg();
+        return r;
+    }
+};
+
+struct PairingConsts {
+    Fq2 g1, g2, g3;   // xi^((p-1)/6), its square and cube (Frobenius of the twist)
+    Fq n[6];          // xi^(k (p^2-1)/6) in Fp, k = 0..5
+    PairingConsts() {
+        static const uint32_t e[8] = {0x2414d4e1u, 0x34b01759u, 0xe6bda1c2u, 0xee9591c2u,
+                                      0xc0403964u, 0xf40d60f3u, 0xd032f006u, 0x0810b7bdu};  // (p-1)/6
+        g1 = fq2_pow(fq2_xi(), e, 8);
+        g2 = g1.sqr();
+        g3 = g2 * g1;
+        Fq nrm = (g1 * g1.conj()).a0;  // xi^((p^2-1)/6)
+        n[0] = Fq::one();
+        for (int k = 1; k < 6; k++) n[k] = n[k - 1] * nrm;
+    }
+};
+inline const PairingConsts& pairing_consts() {
+    static const PairingConsts c;
+    return c;
+}
+
+// f^(p^2): coefficients lie in Fp2 (fixed by p^2), w^k picks up xi^(k (p^2-1)/6)
+inline Fq12 frob2(const Fq12& f) {
+    const PairingConsts& pc = pairing_consts();
+    Fq12 r;
+    for (int k = 0; k < 6; k++) r.c[k] = f.c[k].scale(pc.n[k]);
+    return r;
+}
+
+// inverse through the norm to the quadratic subfield is overkill here; use f^(-1) = conj-chain:
+// for the easy part only f^(p^6 - 1) is needed, so invert by solving with the degree-6 tower:
+// f = a + b w with a,b in Fp6 = Fp2[v], v = w^2.  f^-1 = (a - b w) / (a^2 - b^2 v).
+struct Fq6 {
+    Fq2 c[3];  // sum c[k] v^k, v^3 = xi
+};
+inline Fq6 fq6_mul(const Fq6& x, const Fq6& y) {
+    Fq2 xi = fq2_xi();
+    Fq2 t[5];
+    for (int k = 0; k < 5; k++) t[k] = Fq2::zero();
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) t[i + j] = t[i + j] + x.c[i] * y.c[j];
+    return Fq6{{t[0] + t[3] * xi, t[1] + t[4] * xi, t[2]}};
+}
+inline Fq6 fq6_sub(const Fq6& x, const Fq6& y) { return Fq6{{x.c[0] - y.c[0], x.c[1] - y.c[1], x.c[2] - y.c[2]}}; }
+inline Fq6 fq6_mul_v(const Fq6& x) { return Fq6{{x.c[2] * fq2_xi(), x.c[0], x.c[1]}}; }
+inline Fq6 fq6_inv(const Fq6& x) {
+    Fq2 xi = fq2_xi();
+    Fq2 A = x.c[0].sqr() - x.c[1] * x.c[2] * xi;
+    Fq2 B = x.c[2].sqr() * xi - x.c[0] * x.c[1];
+    Fq2 C = x.c[1].sqr() - x.c[0] * x.c[2];
+    Fq2 F = (x.c[0] * A + (x.c[2] * B + x.c[1] * C) * xi).inverse();
+    return Fq6{{A * F, B * F, C * F}};
+}
+inline Fq12 fq12_inv(const Fq12& f) {
+    Fq6 a{{f.c[0], f.c[2], f.c[4]}}, b{{f.c[1], f.c[3], f.c[5]}};
+    Fq6 d = fq6_inv(fq6_sub(fq6_mul(a, a), fq6_mul_v(fq6_mul(b, b))));
+    Fq6 ra = fq6_mul(a, d), rb = fq6_mul(b, d);
+    Fq12 r;
+    r.c[0] = ra.c[0]; r.c[2] = ra.c[1]; r.c[4] = ra.c[2];
+    r.c[1] = rb.c[0].neg(); r.c[3] = rb.c[1].neg(); r.c[5] = rb.c[2].neg();
+    return r;
+}
+
+// line through the untwisted T with slope lam*w, evaluated at P = (xp, yp) in E(Fp):
+//   l = yp - lam*xp * w + (lam*xT - yT) * w^3
+inline Fq12 line_eval(const Fq2& lam, const G2A& t, const G1A& p) {
+    Fq12 l;
+    for (int k = 0; k < 6; k++) l.c[k] = Fq2::zero();
+    l.c[0] = Fq2{p.y, Fq::zero()};
+    l.c[1] = lam.scale(p.x).neg();
+    l.c[3] = lam * t.x - t.y;
+    return l;
+}
+
+inline Fq12 miller_loop(const G1A& p, const G2A& q) {
+    if (p.is_inf() || q.inf) return Fq12::one();
+    const PairingConsts& pc = pairing_consts();
+    // 6u + 2 = 0x19d797039be763ba8 (65 bits)
+    const uint64_t lo = 0x9d797039be763ba8ull;
+    Fq12 f = Fq12::one();
+    G2A t = q;
+    Fq2 lam;
+    for (int i = 63; i >= 0; i--) {  // bit 64 is the leading one
+        G2A t2 = g2_add(t, t, &lam);
+        f = f.sqr() * line_eval(lam, t, p);
+        t = t2;
+        if ((lo >> i) & 1ull) {
+            G2A t3 = g2_add(t, q, &lam);
+            f = f * line_eval(lam, t, p);
+            t = t3;
+        }
+    }
+    // Q1 = pi(Q), Q2 = -pi^2(Q)
+    G2A q1, q2;
+    q1.x = q.x.conj() * pc.g2;
+    q1.y = q.y.conj() * pc.g3;
+    q1.inf = false;
+    q2.x = q.x.scale(pc.n[2]);
+    q2.y = q.y.scale(pc.n[3]).neg();  // -pi^2(Q); xi^((p^2-1)/2) = n[3] (= -1)
+    q2.inf = false;
+    G2A t3 = g2_add(t, q1, &lam);
+    f = f * line_eval(lam, t, p);
+    t = t3;
+    g2_add(t, q2, &lam);
+    f = f * line_eval(lam, t, p);
+    return f;
+}
+
+inline Fq12 final_exponentiation(const Fq12& f) {
+    // easy part: f^((p^6 - 1)(p^2 + 1))
+    Fq12 a = f.conj6() * fq12_inv(f);
+    Fq12 b = frob2(a) * a;
+    // hard part: (p^4 - p^2 + 1)/r, 761 bits
+    static const uint32_t h[24] = {
+        0xccdf42b1u, 0xe81bb482u, 0xf49c36d4u, 0x5abf5cc4u, 0x1da014fdu, 0xf1154e7eu, 0x87cdbacfu, 0xdcc7b44cu,
+        0x954bcf8au, 0xaaa441e3u, 0xd5095f23u, 0x6b887d56u, 0xf3fd90c6u, 0x79581e16u, 0xd189227du, 0x3b1b1355u,
+        0x61876f6bu, 0x4e529a58u, 0xd5b12278u, 0x6c0eb522u, 0x83177fafu, 0x331ec151u, 0x0b0759adu, 0x01baaa71u};
+    Fq12 r = Fq12::one();
+    for (int i = 760; i >= 0; i--) {
+        r = r.sqr();
+        if ((h[i >> 5] >> (i & 31)) & 1u) r = r * b;
+    }
+    return r;
+}
+
+inline bool pairing_product_is_one(const G1A* ps, const G2A* qs, int n) {
+    Fq12 f = Fq12::one();
+    for (int i = 0; i < n; i++) f = f * miller_loop(ps[i], qs[i]);
+    return final_exponentiation(f).is_one();
+}
+
+}  // namespace host
+}  // namespace porla

@@ -1,0 +1,199 @@
+// Host-side BN254 helpers for the C-ABI: byte codecs (gnark-crypto v0.6.0 layouts, SURVEY.md
+// Appendix B), single-point group operations and Fr polynomial arithmetic.  These back the O(1)
+// entry points of /root/reference/porla/main.go (add_point :196, mult_point :205, neg_point :217,
+// compute_digest :71, kzg.Open inside create_proof :170); the MSMs never come through here.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "ec.cuh"
+
+namespace porla {
+namespace host {
+
+using Fq = Fp<Bn254FpParams>;
+using Fr = Fp<Bn254FrParams>;
+using G1A = Affine<Fq>;
+using G1X = XYZZ<Fq>;
+
+// ---- raw 256-bit <-> big-endian bytes
+inline void be32_to_limbs(const uint8_t* b, uint32_t* l) {
+    for (int i = 0; i < 8; i++) {
+        const uint8_t* p = b + 4 * (7 - i);
+        l[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+    }
+}
+inline void limbs_to_be32(const uint32_t* l, uint8_t* b) {
+    for (int i = 0; i < 8; i++) {
+        uint8_t* p = b + 4 * (7 - i);
+        p[0] = (uint8_t)(l[i] >> 24);
+        p[1] = (uint8_t)(l[i] >> 16);
+        p[2] = (uint8_t)(l[i] >> 8);
+        p[3] = (uint8_t)l[i];
+    }
+}
+
+// canonical (non-Montgomery) limbs of a value < 2^256, reduced below the modulus
+template <class F>
+inline void reduce_canonical(uint32_t* l) {
+    uint32_t m[8], t[8];
+    for (int i = 0; i < 8; i++) m[i] = F::Params::mod(i);
+    for (int k = 0; k < 8; k++) {
+        if (sub256(t, l, m)) break;
+        memcpy(l, t, 32);
+    }
+}
+
+// fp/fr Element.SetBytes: big-endian integer of ANY length reduced mod the modulus; returns the
+// element in internal (Montgomery) form.
+template <class F>
+inline F elem_from_be(const uint8_t* b, size_t len) {
+    if (len <= 32) {
+        uint8_t buf[32] = {0};
+        memcpy(buf + (32 - len), b, len);
+        F x;
+        be32_to_limbs(buf, x.v);
+        reduce_canonical<F>(x.v);
+        return x.to_internal();
+    }
+    // long inputs: Horner in base 2^8
+    F acc = F::zero();
+    F c256 = F::zero();
+    c256.v[0] = 256;
+    c256 = c256.to_internal();
+    for (size_t i = 0; i < len; i++) {
+        F d = F::zero();
+        d.v[0] = b[i];
+        acc = acc * c256 + d.to_internal();
+    }
+    return acc;
+}
+template <class F>
+inline void elem_to_be(const F& x, uint8_t* out32) {
+    F c = x.from_internal();
+    limbs_to_be32(c.v, out32);
+}
+template <class F>
+inline F elem_from_u64(uint64_t v) {
+    F x = F::zero();
+    x.v[0] = (uint32_t)v;
+    x.v[1] = (uint32_t)(v >> 32);
+    return x.to_internal();
+}
+
+template <class F>
+inline F pow_limbs(const F& a, const uint32_t* e) {
+    F r = F::one();
+    for (int i = 255; i >= 0; i--) {
+        r = r.sqr();
+        if ((e[i >> 5] >> (i & 31)) & 1u) r = r * a;
+    }
+    return r;
+}
+
+// sqrt in Fq (p = 3 mod 4): a^((p+1)/4); returns false for non-residues
+inline bool fq_sqrt(const Fq& a, Fq* out) {
+    uint32_t e[8], one[8] = {1, 0, 0, 0, 0, 0, 0, 0}, m[8];
+    for (int i = 0; i < 8; i++) m[i] = Bn254FpParams::mod(i);
+    add256(e, m, one);
+    for (int i = 0; i < 8; i++) e[i] = (e[i] >> 2) | (i < 7 ? (e[i + 1] << 30) : 0u);
+    Fq y = pow_limbs(a, e);
+    if (y.sqr() != a) return false;
+    *out = y;
+    return true;
+}
+
+// lexicographic "largest" test of gnark: y > (p-1)/2 on the canonical integer
+inline bool fq_lex_largest(const Fq& y_internal) {
+    Fq y = y_internal.from_internal();
+    uint32_t half[8], m[8], t[8];
+    for (int i = 0; i < 8; i++) m[i] = Bn254FpParams::mod(i);
+    for (int i = 0; i < 8; i++) half[i] = (m[i] >> 1) | (i < 7 ? (m[i + 1] << 31) : 0u);  // (p-1)/2
+    return sub256(t, half, y.v) != 0;  // half < y
+}
+
+enum : uint8_t { kFlagUncompressed = 0x00, kFlagCompressedInf = 0x40, kFlagSmallest = 0x80, kFlagLargest = 0xC0 };
+
+inline Fq curve_b() { return elem_from_u64<Fq>(3); }
+
+// G1Affine.SetBytes on a 64-byte (uncompressed) or 32-byte (compressed) buffer.
+inline bool g1_unmarshal(const uint8_t* b, size_t len, G1A* out) {
+    if (len < 32) return false;
+    uint8_t flag = b[0] & 0xC0;
+    if (flag == kFlagUncompressed) {
+        if (len < 64) return false;
+        uint8_t xb[32];
+        memcpy(xb, b, 32);
+        out->x = elem_from_be<Fq>(xb, 32);
+        out->y = elem_from_be<Fq>(b + 32, 32);
+        return true;
+    }
+    if (flag == kFlagCompressedInf) {
+        *out = G1A::inf();
+        return true;
+    }
+    uint8_t xb[32];
+    memcpy(xb, b, 32);
+    xb[0] &= 0x3F;
+    Fq x = elem_from_be<Fq>(xb, 32);
+    Fq y;
+    if (!fq_sqrt(x.sqr() * x + curve_b(), &y)) return false;
+    if (fq_lex_largest(y) != (flag == kFlagLargest)) y = y.neg();
+    out->x = x;
+    out->y = y;
+    return true;
+}
+inline void g1_marshal(const G1A& p, uint8_t* out64) {
+    elem_to_be(p.x, out64);
+    elem_to_be(p.y, out64 + 32);
+}
+inline void g1_compress(const G1A& p, uint8_t* out32) {
+    if (p.is_inf()) {
+        memset(out32, 0, 32);
+        out32[0] = kFlagCompressedInf;
+        return;
+    }
+    elem_to_be(p.x, out32);
+    out32[0] |= fq_lex_largest(p.y) ? kFlagLargest : kFlagSmallest;
+}
+
+inline G1A g1_generator() { return G1A{elem_from_u64<Fq>(1), elem_from_u64<Fq>(2)}; }
+
+inline G1A g1_add(const G1A& a, const G1A& b) {
+    G1X r = G1X::from_affine(a);
+    r.madd(b);
+    return r.to_affine();
+}
+// k * p, k an Fr element (internal form)
+inline G1A g1_mul(const G1A& p, const Fr& k_internal) {
+    Fr k = k_internal.from_internal();
+    G1X r = G1X::inf();
+    if (p.is_inf()) return G1A::inf();
+    for (int i = 255; i >= 0; i--) {
+        r = r.dbl();
+        if ((k.v[i >> 5] >> (i & 31)) & 1u) r.madd(p);
+    }
+    return r.to_affine();
+}
+
+// polynomial.Eval: Horner
+inline Fr poly_eval(const std::vector<Fr>& f, const Fr& z) {
+    Fr acc = Fr::zero();
+    for (size_t i = f.size(); i-- > 0;) acc = acc * z + f[i];
+    return acc;
+}
+// kzg.Open's quotient (f - f(z)) / (X - z): synthetic division, degree n-2
+inline std::vector<Fr> poly_quotient(const std::vector<Fr>& f, const Fr& z) {
+    std::vector<Fr> h(f.size() > 0 ? f.size() - 1 : 0);
+    Fr carry = Fr::zero();
+    for (size_t i = f.size(); i-- > 1;) {
+        carry = f[i] + carry * z;
+        h[i - 1] = carry;
+    }
+    return h;
+}
+
+}  // namespace host
+}  // namespace porla

@@ -1,0 +1,152 @@
+// Curve-independent host infrastructure and the curve dispatchers of the device MSM engine.
+// The templated drivers live in msm_impl.cuh (instantiated in msm_bn254.cu / msm_secp.cu).
+#include "msm.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+
+#include "arena.h"
+#include "ec.cuh"
+
+namespace porla {
+
+std::atomic<uint64_t> g_launches{0};
+uint64_t launches_issued() { return g_launches.load(); }
+
+void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e == cudaSuccess) return;
+    fprintf(stderr, "[libmultiexp/porla_b200] FATAL CUDA error %d (%s) at %s:%d in %s\n", (int)e,
+            cudaGetErrorString(e), file, line, what);
+    fprintf(stderr, "[libmultiexp/porla_b200] this library has no CPU fallback; a B200 (sm_100a) is required\n");
+    abort();
+}
+
+static std::once_flag g_dev_once;
+static int g_device = -1;
+
+bool device_available() {
+    int count = 0;
+    return cudaGetDeviceCount(&count) == cudaSuccess && count > 0;
+}
+
+int device_init() {
+    std::call_once(g_dev_once, [] {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            fprintf(stderr,
+                    "[libmultiexp/porla_b200] FATAL: no CUDA device (%s); the MSM path is GPU-only, "
+                    "there is no CPU fallback\n",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+            abort();
+        }
+        int dev = 0;
+        const char* s = getenv("PORLA_DEVICE");
+        if (!s) s = getenv("LOCAL_RANK");
+        if (s) dev = atoi(s) % count;
+        PORLA_CUDA(cudaSetDevice(dev));
+        g_device = dev;
+    });
+    PORLA_CUDA(cudaSetDevice(g_device));
+    return g_device;
+}
+
+// forward declarations of the per-curve drivers (msm_impl.cuh)
+std::mutex g_engine_mu;
+Arena g_arena;
+
+template <class C> void import_impl(const uint8_t*, int, uint32_t, PointTable*, cudaStream_t);
+template <class C> void msm_impl(const PointTable&, const uint8_t*, uint32_t, uint32_t, const MsmOptions&, uint8_t*, void*, cudaStream_t);
+template <class C> void combine_impl(const void*, uint32_t, uint32_t, int, uint8_t*, cudaStream_t);
+template <class C> void scalar_mul_impl(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);
+template <class C> void export_impl(const void*, uint32_t, int, uint8_t*, cudaStream_t);
+template <class C> void field_mul_impl(const void*, const void*, uint32_t, void*, cudaStream_t);
+
+#define DISPATCH(curve, fn, ...)                                  \
+    do {                                                          \
+        if ((curve) == kCurveBn254) fn<Bn254>(__VA_ARGS__);       \
+        else fn<Secp256k1>(__VA_ARGS__);                          \
+    } while (0)
+
+// ---------------------------------------------------------------------------- window choice
+static int scalar_bits(int curve) { return curve == kCurveBn254 ? Bn254::kScalarBits : Secp256k1::kScalarBits; }
+
+int choose_window(int curve, uint32_t n, uint32_t nbatch) {
+    const char* env = getenv("PORLA_WINDOW_BITS");
+    if (env && atoi(env) >= 2 && atoi(env) <= 24) return atoi(env);
+    const int bits = scalar_bits(curve);
+    double best = 1e300;
+    int best_c = 4;
+    for (int c = 3; c <= 22; c++) {
+        int nwin = (bits + 1 + c - 1) / c;
+        double nb = (double)(1u << (c - 1));
+        // one mixed add per (point, window); ~4 mixed-add equivalents per bucket in the reduction
+        double cost = (double)nwin * ((double)n + 4.0 * nb);
+        double total_buckets = (double)nbatch * nwin * nb;
+        if (total_buckets > 3.0e9) continue;           // 32-bit bucket ids
+        if (total_buckets * 128.0 > 48.0e9) continue;  // bucket array budget
+        if (cost < best) {
+            best = cost;
+            best_c = c;
+        }
+    }
+    return best_c;
+}
+
+// ---------------------------------------------------------------------------- dispatchers
+void table_import_device(int curve, const uint8_t* d_bytes, int fmt, uint32_t n, PointTable* out, cudaStream_t stream) {
+    device_init();
+    DISPATCH(curve, import_impl, d_bytes, fmt, n, out, stream);
+}
+
+void table_import_host(int curve, const uint8_t* h_bytes, int fmt, uint32_t n, PointTable* out, cudaStream_t stream) {
+    device_init();
+    uint8_t* d_tmp = nullptr;
+    PORLA_CUDA(cudaMalloc(&d_tmp, (size_t)(n ? n : 1) * 64));
+    if (n) PORLA_CUDA(cudaMemcpyAsync(d_tmp, h_bytes, (size_t)n * 64, cudaMemcpyHostToDevice, stream));
+    table_import_device(curve, d_tmp, fmt, n, out, stream);
+    PORLA_CUDA(cudaFree(d_tmp));
+}
+
+void table_free(PointTable* t) {
+    if (t->d_points) PORLA_CUDA(cudaFree(t->d_points));
+    if (t->d_flags) PORLA_CUDA(cudaFree(t->d_flags));
+    *t = PointTable{};
+}
+
+void msm_device(int curve, const PointTable& table, const uint8_t* d_scalars, uint32_t n, uint32_t nbatch,
+                const MsmOptions& opt, uint8_t* d_out, void* d_out_xyzz, cudaStream_t stream) {
+    device_init();
+    if (nbatch == 0) return;
+    DISPATCH(curve, msm_impl, table, d_scalars, n, nbatch, opt, d_out, d_out_xyzz, stream);
+}
+
+void msm_combine_device(int curve, const void* d_parts, uint32_t count, uint32_t nbatch, int out_fmt, uint8_t* d_out,
+                        cudaStream_t stream) {
+    device_init();
+    if (nbatch == 0) return;
+    DISPATCH(curve, combine_impl, d_parts, count, nbatch, out_fmt, d_out, stream);
+}
+
+void scalar_mul_device(int curve, const PointTable& table, const uint8_t* d_scalars, int scalar_be, uint32_t n,
+                       void* d_out_affine, cudaStream_t stream) {
+    device_init();
+    if (!n) return;
+    DISPATCH(curve, scalar_mul_impl, table, d_scalars, scalar_be, n, d_out_affine, stream);
+}
+
+void export_points_device(int curve, const void* d_affine, uint32_t n, int fmt, uint8_t* d_out, cudaStream_t stream) {
+    device_init();
+    if (!n) return;
+    DISPATCH(curve, export_impl, d_affine, n, fmt, d_out, stream);
+}
+
+void field_mul_device(int curve, const void* d_a, const void* d_b, uint32_t n, void* d_out, cudaStream_t stream) {
+    device_init();
+    if (!n) return;
+    DISPATCH(curve, field_mul_impl, d_a, d_b, n, d_out, stream);
+}
+
+}  // namespace porla

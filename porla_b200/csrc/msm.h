@@ -1,0 +1,70 @@
+// Host-side interface of the device MSM engine (internal to libmultiexp.so; the public C-ABI is
+// include/porla_multiexp.h).  One engine per (process, device, curve); calls are serialised by
+// an internal mutex because Porla invokes the C-ABI from up to 8 pool threads
+// (/root/reference/porla/Server/Server.hpp:1077-1078).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace porla {
+
+enum CurveId : int { kCurveBn254 = 0, kCurveSecp256k1 = 1 };
+
+// Throws nothing; every failure is fatal by design ("no CPU fallback"): prints and aborts.
+void cuda_check(cudaError_t e, const char* what, const char* file, int line);
+#define PORLA_CUDA(x) ::porla::cuda_check((x), #x, __FILE__, __LINE__)
+
+// Selects/initialises the device once (PORLA_DEVICE, else LOCAL_RANK, else 0).  Aborts loudly
+// when no CUDA device is usable.
+int device_init();
+// Non-aborting probe (lets the host-only entry points of the C-ABI work on a machine without a GPU).
+bool device_available();
+
+// Resident point table in internal form (Montgomery for BN254).
+struct PointTable {
+    void* d_points = nullptr;     // Affine<F>[n]
+    uint8_t* d_flags = nullptr;   // 1 = infinity; nullptr when the table has none
+    uint32_t n = 0;
+    uint32_t n_inf = 0;
+    int curve = 0;
+};
+
+// Import `n` external 64-byte points that already live on the device.
+void table_import_device(int curve, const uint8_t* d_bytes, int point_fmt, uint32_t n, PointTable* out,
+                         cudaStream_t stream);
+// Import from host memory (H2D copy + conversion).
+void table_import_host(int curve, const uint8_t* h_bytes, int point_fmt, uint32_t n, PointTable* out,
+                       cudaStream_t stream);
+void table_free(PointTable* t);
+
+struct MsmOptions {
+    int window_bits = 0;      // 0 = choose from n
+    int scalar_be = 1;        // 1: 32-byte big-endian scalars, 0: 8 LE 32-bit limbs
+    int out_fmt = 0;          // PointFormat of the serialised result
+    int shared_points = 1;    // batch: all MSMs over the same table prefix
+};
+
+// nbatch MSMs of n terms each.  d_scalars: nbatch*n*32 bytes on the device.
+// d_out (nullable): nbatch*64 bytes, canonical affine.  d_out_xyzz (nullable): nbatch*128 bytes,
+// un-normalised sums in internal form (for multi-GPU combination).
+void msm_device(int curve, const PointTable& table, const uint8_t* d_scalars, uint32_t n,
+                uint32_t nbatch, const MsmOptions& opt, uint8_t* d_out, void* d_out_xyzz,
+                cudaStream_t stream);
+
+// Sum `count` XYZZ partials per MSM (layout parts[k*nbatch + m]) and serialise nbatch results.
+void msm_combine_device(int curve, const void* d_parts, uint32_t count, uint32_t nbatch, int out_fmt,
+                        uint8_t* d_out, cudaStream_t stream);
+
+// Elementwise batched kernels.
+void scalar_mul_device(int curve, const PointTable& table, const uint8_t* d_scalars, int scalar_be,
+                       uint32_t n, void* d_out_affine, cudaStream_t stream);
+void export_points_device(int curve, const void* d_affine, uint32_t n, int point_fmt, uint8_t* d_out,
+                          cudaStream_t stream);
+void field_mul_device(int curve, const void* d_a, const void* d_b, uint32_t n, void* d_out,
+                      cudaStream_t stream);
+
+int choose_window(int curve, uint32_t n, uint32_t nbatch);
+uint64_t launches_issued();   // number of kernels this library has launched (bench's gpu_launches)
+
+}  // namespace porla

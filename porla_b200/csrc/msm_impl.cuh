@@ -1,0 +1,179 @@
+// Templated host drivers of the kernels in msm_kernels.cuh; instantiated once per curve in
+// msm_bn254.cu / msm_secp.cu so the two curves compile in parallel.
+#pragma once
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <type_traits>
+
+#include "arena.h"
+#include "msm.h"
+#include "msm_kernels.cuh"
+
+namespace porla {
+
+extern std::atomic<uint64_t> g_launches;
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+extern std::mutex g_engine_mu;
+extern Arena g_arena;
+
+template <class C> struct CurveIdOf;
+template <> struct CurveIdOf<Bn254> { static constexpr int value = kCurveBn254; };
+template <> struct CurveIdOf<Secp256k1> { static constexpr int value = kCurveSecp256k1; };
+
+// ---------------------------------------------------------------------------- tables
+template <class C>
+void import_impl(const uint8_t* d_bytes, int fmt, uint32_t n, PointTable* out, cudaStream_t stream) {
+    using F = typename C::F;
+    Affine<F>* pts = nullptr;
+    uint8_t* flags = nullptr;
+    uint32_t* d_count = nullptr;
+    PORLA_CUDA(cudaMalloc(&pts, (size_t)(n ? n : 1) * sizeof(Affine<F>)));
+    PORLA_CUDA(cudaMalloc(&flags, (size_t)(n ? n : 1)));
+    PORLA_CUDA(cudaMalloc(&d_count, 4));
+    PORLA_CUDA(cudaMemsetAsync(d_count, 0, 4, stream));
+    if (n) {
+        int mask = C::F::Params::kMontgomery ? 1 : 0;  // BN254: gnark flag bits in byte 0
+        k_import_points<C><<<(n + 127) / 128, 128, 0, stream>>>(d_bytes, fmt, mask, n, pts, flags, d_count);
+        LAUNCHED();
+        PORLA_CUDA(cudaGetLastError());
+    }
+    uint32_t h_count = 0;
+    PORLA_CUDA(cudaMemcpyAsync(&h_count, d_count, 4, cudaMemcpyDeviceToHost, stream));
+    PORLA_CUDA(cudaStreamSynchronize(stream));
+    PORLA_CUDA(cudaFree(d_count));
+    out->d_points = pts;
+    out->n = n;
+    out->n_inf = h_count;
+    out->curve = CurveIdOf<C>::value;
+    if (h_count == 0) {
+        PORLA_CUDA(cudaFree(flags));
+        out->d_flags = nullptr;
+    } else {
+        out->d_flags = flags;
+    }
+}
+
+// ---------------------------------------------------------------------------- the pipeline
+template <class C>
+void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uint32_t nbatch,
+                     const MsmOptions& opt, uint8_t* d_out, void* d_out_xyzz, cudaStream_t stream) {
+    using F = typename C::F;
+    const int curve = CurveIdOf<C>::value;
+    MsmShape sh;
+    sh.n = n;
+    sh.nbatch = nbatch;
+    sh.shared = opt.shared_points ? 1u : 0u;
+    sh.c = opt.window_bits > 0 ? opt.window_bits : choose_window(curve, n, nbatch);
+    sh.nwin = (C::kScalarBits + 1 + sh.c - 1) / sh.c;
+    sh.nbuckets = 1u << (sh.c - 1);
+
+    const uint64_t slots = (uint64_t)nbatch * sh.nwin;
+    const uint64_t nbt64 = slots * sh.nbuckets;
+    const uint64_t pairs64 = (uint64_t)nbatch * n * sh.nwin;
+    if (nbt64 >= (1ull << 32) || pairs64 >= (1ull << 32) || (uint64_t)nbatch * n >= (1ull << 31)) {
+        fprintf(stderr, "[libmultiexp/porla_b200] FATAL: MSM shape too large for 32-bit indexing\n");
+        abort();
+    }
+    const uint32_t nbt = (uint32_t)nbt64;
+    const uint32_t ntiles = (nbt + kScanTile - 1) / kScanTile;
+
+    // reduction geometry
+    uint32_t chunk = 8;
+    uint32_t threads_per_slot = (sh.nbuckets + chunk - 1) / chunk;
+    uint32_t blocks_per_slot = (threads_per_slot + kRedThreads - 1) / kRedThreads;
+
+    std::lock_guard<std::mutex> lock(g_engine_mu);
+    size_t need = Arena::padded(nbt, 4) * 2 + Arena::padded(ntiles + 1, 4) + 256 +
+                  Arena::padded(pairs64 ? pairs64 : 1, 4) + Arena::padded(nbt, sizeof(XYZZ<F>)) +
+                  Arena::padded(slots * blocks_per_slot, sizeof(XYZZ<F>));
+    g_arena.reserve(need, stream);
+    g_arena.reset();
+    uint32_t* counters = g_arena.take<uint32_t>(nbt);
+    uint32_t* offsets = g_arena.take<uint32_t>(nbt);
+    uint32_t* tile_sums = g_arena.take<uint32_t>(ntiles + 1);
+    uint32_t* grand = g_arena.take<uint32_t>(1);
+    uint32_t* sorted = g_arena.take<uint32_t>(pairs64 ? pairs64 : 1);
+    XYZZ<F>* buckets = g_arena.take<XYZZ<F>>(nbt);
+    XYZZ<F>* partials = g_arena.take<XYZZ<F>>(slots * blocks_per_slot);
+
+    const Affine<F>* points = reinterpret_cast<const Affine<F>*>(table.d_points);
+    const uint64_t total_scalars = (uint64_t)n * nbatch;
+
+    PORLA_CUDA(cudaMemsetAsync(counters, 0, (size_t)nbt * 4, stream));
+    if (total_scalars) {
+        uint32_t grid = (uint32_t)((total_scalars + 255) / 256);
+        if (grid > 148u * 32u) grid = 148u * 32u;
+        k_digits<C, false><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, counters, nullptr);
+        LAUNCHED();
+        k_scan_tiles<<<ntiles, kScanThreads, 0, stream>>>(counters, offsets, nbt, tile_sums);
+        LAUNCHED();
+        k_scan_sums<<<1, kScanThreads, 0, stream>>>(tile_sums, ntiles, grand);
+        LAUNCHED();
+        k_scan_add<<<ntiles, kScanThreads, 0, stream>>>(offsets, counters, nbt, tile_sums);
+        LAUNCHED();
+        k_digits<C, true><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, counters, sorted);
+        LAUNCHED();
+    } else {
+        PORLA_CUDA(cudaMemsetAsync(offsets, 0, (size_t)nbt * 4, stream));
+    }
+    k_accumulate<C><<<(nbt + kAccThreads - 1) / kAccThreads, kAccThreads, 0, stream>>>(
+        points, sorted, offsets, counters, nullptr, nbt, buckets);
+    LAUNCHED();
+    dim3 rgrid(blocks_per_slot, (uint32_t)slots);
+    k_reduce<C><<<rgrid, kRedThreads, 0, stream>>>(buckets, sh.nbuckets, chunk, threads_per_slot, partials);
+    LAUNCHED();
+    k_finalize<C><<<nbatch, 64, sh.nwin * sizeof(XYZZ<F>), stream>>>(
+        partials, blocks_per_slot, sh.nwin, sh.c, opt.out_fmt, d_out, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
+    LAUNCHED();
+    PORLA_CUDA(cudaGetLastError());
+}
+
+
+template <class C>
+void combine_impl(const void* d_parts, uint32_t count, uint32_t nbatch, int out_fmt, uint8_t* d_out, cudaStream_t stream) {
+    using F = typename C::F;
+    k_combine<C><<<(nbatch + 63) / 64, 64, 0, stream>>>(reinterpret_cast<const XYZZ<F>*>(d_parts), count, nbatch, out_fmt, d_out);
+    LAUNCHED();
+    PORLA_CUDA(cudaGetLastError());
+}
+
+template <class C>
+void scalar_mul_impl(const PointTable& table, const uint8_t* d_scalars, int scalar_be, uint32_t n, void* d_out_affine,
+                     cudaStream_t stream) {
+    using F = typename C::F;
+    k_scalar_mul<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<F>*>(table.d_points), table.n, d_scalars,
+                                                        scalar_be, n, reinterpret_cast<Affine<F>*>(d_out_affine));
+    LAUNCHED();
+    PORLA_CUDA(cudaGetLastError());
+}
+
+template <class C>
+void export_impl(const void* d_affine, uint32_t n, int fmt, uint8_t* d_out, cudaStream_t stream) {
+    using F = typename C::F;
+    k_export_points<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<F>*>(d_affine), n, fmt, d_out);
+    LAUNCHED();
+    PORLA_CUDA(cudaGetLastError());
+}
+
+template <class C>
+void field_mul_impl(const void* d_a, const void* d_b, uint32_t n, void* d_out, cudaStream_t stream) {
+    using F = typename C::F;
+    k_field_mul<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const F*>(d_a), reinterpret_cast<const F*>(d_b), n,
+                                                       reinterpret_cast<F*>(d_out));
+    LAUNCHED();
+    PORLA_CUDA(cudaGetLastError());
+}
+
+#define PORLA_INSTANTIATE_CURVE(C)                                                                                     \
+    template void import_impl<C>(const uint8_t*, int, uint32_t, PointTable*, cudaStream_t);                            \
+    template void msm_impl<C>(const PointTable&, const uint8_t*, uint32_t, uint32_t, const MsmOptions&, uint8_t*,      \
+                              void*, cudaStream_t);                                                                    \
+    template void combine_impl<C>(const void*, uint32_t, uint32_t, int, uint8_t*, cudaStream_t);                       \
+    template void scalar_mul_impl<C>(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);           \
+    template void export_impl<C>(const void*, uint32_t, int, uint8_t*, cudaStream_t);                                  \
+    template void field_mul_impl<C>(const void*, const void*, uint32_t, void*, cudaStream_t);
+
+}  // namespace porla

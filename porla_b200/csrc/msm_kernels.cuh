@@ -1,0 +1,462 @@
+// Pippenger (bucket-method) multi-scalar multiplication kernels for sm_100a, templated on curve.
+//
+// Replaces, on the device:
+//   * gnark-crypto's G1Affine.MultiExp reached from /root/reference/porla/main.go:136 (and
+//     kzg.Commit, main.go:114,164), and
+//   * secp256k1_ecmult_pippenger_wnaf, /root/reference/porla/Utils/secp256k1_lib/ecmult_impl.h:492-567.
+//
+// Pipeline (one or many MSMs per launch sequence; "window slot" = (msm, window)):
+//   k_digits<COUNT>   signed c-bit recoding of every scalar, histogram of bucket sizes
+//   k_scan_*          exclusive prefix sum -> bucket offsets
+//   k_digits<SCATTER> recode again, scatter (point index | sign) into bucket-sorted order
+//   k_accumulate      one thread per bucket: XYZZ += affine over the bucket's slice
+//   k_reduce          per window slot: chunked running-sum reduction -> a few partials
+//   k_finalize        per MSM: sum partials, Horner over windows, to affine, serialise
+//
+// Data layout in HBM: points are 64-byte affine records (x,y as 8 LE 32-bit limbs in the
+// field's internal form, infinity = all zero) read with 128-bit loads; buckets are 128-byte
+// XYZZ records; the sorted index array is 4 B per (point, window) pair.
+#pragma once
+#include "ec.cuh"
+
+namespace porla {
+
+enum ScalarFormat : int { kScalarBE32 = 0, kScalarLE32 = 1 };
+enum PointFormat : int { kPointBE64 = 0, kPointLE64 = 1 };
+
+struct MsmShape {
+    uint32_t n;          // scalars per MSM
+    uint32_t nbatch;     // MSMs in this launch
+    uint32_t shared;     // 1: every MSM uses points[0..n), 0: MSM m uses points[m*n .. (m+1)*n)
+    int c;               // window bits
+    int nwin;            // windows per scalar
+    uint32_t nbuckets;   // buckets per window = 2^(c-1)
+};
+
+// ---------------------------------------------------------------------------- small helpers
+template <class T>
+PORLA_D T ld16(const T* p) {  // 16-byte aligned record, 128-bit loads
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldg(s + i);
+    return r;
+}
+template <class T>
+PORLA_D void st16(T* p, const T& v) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+
+PORLA_D uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// 32 bytes -> 8 little-endian limbs
+PORLA_D void load_u256(const uint8_t* base, size_t idx, int big_endian, uint32_t* s) {
+    const uint4* p = reinterpret_cast<const uint4*>(base + idx * 32);
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    if (big_endian) {
+        s[7] = bswap32(a.x); s[6] = bswap32(a.y); s[5] = bswap32(a.z); s[4] = bswap32(a.w);
+        s[3] = bswap32(b.x); s[2] = bswap32(b.y); s[1] = bswap32(b.z); s[0] = bswap32(b.w);
+    } else {
+        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+        s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    }
+}
+PORLA_D void store_u256(uint8_t* base, size_t idx, int big_endian, const uint32_t* s) {
+    uint4* p = reinterpret_cast<uint4*>(base + idx * 32);
+    uint4 a, b;
+    if (big_endian) {
+        a.x = bswap32(s[7]); a.y = bswap32(s[6]); a.z = bswap32(s[5]); a.w = bswap32(s[4]);
+        b.x = bswap32(s[3]); b.y = bswap32(s[2]); b.z = bswap32(s[1]); b.w = bswap32(s[0]);
+    } else {
+        a.x = s[0]; a.y = s[1]; a.z = s[2]; a.w = s[3];
+        b.x = s[4]; b.y = s[5]; b.z = s[6]; b.w = s[7];
+    }
+    p[0] = a;
+    p[1] = b;
+}
+
+// s mod order (fr.Element.SetBytes semantics, main.go:127; secp256k1: scalars are "not reduced"
+// by convert_ZZ_to_scalar, utils.h:180-192, the reference then works mod n).
+template <class C>
+PORLA_D void reduce_scalar(uint32_t* s) {
+    uint32_t m[8], t[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = C::order(i);
+    // 2^256 / r < 6 for BN254, < 2 for secp256k1
+    for (int k = 0; k < 6; k++) {
+        uint32_t borrow = sub256(t, s, m);
+        if (borrow) break;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = t[i];
+    }
+}
+
+// ---------------------------------------------------------------------------- import / export
+// External bytes -> internal affine records.  BN254: gnark Marshal layout X||Y big-endian with
+// the two flag bits of byte 0 masked (fp.Element.SetBytes reduces mod p); 64 zero bytes is
+// infinity.  flags[i] = 1 marks infinity so the recoder can drop the pair.
+template <class C>
+__global__ void k_import_points(const uint8_t* __restrict__ in, int fmt, int mask_top2, uint32_t n,
+                                Affine<typename C::F>* __restrict__ out, uint8_t* __restrict__ flags,
+                                uint32_t* __restrict__ inf_count) {
+    using F = typename C::F;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x, y;
+    load_u256(in, 2 * (size_t)i, fmt == kPointBE64, x.v);
+    load_u256(in, 2 * (size_t)i + 1, fmt == kPointBE64, y.v);
+    if (mask_top2) x.v[7] &= 0x3fffffffu;
+    // reduce below p (inputs are < 2^256; p > 2^253 so a few subtractions suffice)
+    for (int k = 0; k < 6; k++) {
+        F t;
+        uint32_t m[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) m[j] = F::Params::mod(j);
+        if (sub256(t.v, x.v, m)) break;
+        x = t;
+    }
+    for (int k = 0; k < 6; k++) {
+        F t;
+        uint32_t m[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) m[j] = F::Params::mod(j);
+        if (sub256(t.v, y.v, m)) break;
+        y = t;
+    }
+    bool inf = x.is_zero() && y.is_zero();
+    Affine<F> p{x.to_internal(), y.to_internal()};
+    st16(out + i, p);
+    if (flags) flags[i] = inf ? 1 : 0;
+    if (inf && inf_count) atomicAdd(inf_count, 1u);
+}
+
+// internal affine -> external bytes (inverse of the above)
+template <class C>
+__global__ void k_export_points(const Affine<typename C::F>* __restrict__ in, uint32_t n, int fmt,
+                                uint8_t* __restrict__ out) {
+    using F = typename C::F;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = ld16(in + i);
+    F x = p.x.from_internal(), y = p.y.from_internal();
+    store_u256(out, 2 * (size_t)i, fmt == kPointBE64, x.v);
+    store_u256(out, 2 * (size_t)i + 1, fmt == kPointBE64, y.v);
+}
+
+// ---------------------------------------------------------------------------- recoding
+// Signed c-bit digits: d_w in [-2^(c-1), 2^(c-1)], bucket id |d_w| - 1; nwin*c > bits of the
+// order, so the top digit never overflows.
+template <class C, bool SCATTER>
+__global__ void k_digits(const uint8_t* __restrict__ scalars, int big_endian,
+                         const uint8_t* __restrict__ inf_flags, MsmShape sh,
+                         uint32_t* __restrict__ counters, uint32_t* __restrict__ sorted) {
+    const uint64_t total = (uint64_t)sh.n * sh.nbatch;
+    const uint32_t half = 1u << (sh.c - 1);
+    const uint32_t mask = (1u << sh.c) - 1u;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t m = (uint32_t)(idx / sh.n);
+        uint32_t i = (uint32_t)(idx - (uint64_t)m * sh.n);
+        uint32_t pidx = sh.shared ? i : (uint32_t)idx;
+        if (inf_flags && inf_flags[pidx]) continue;
+        uint32_t s[9];
+        load_u256(scalars, idx, big_endian, s);
+        s[8] = 0;
+        reduce_scalar<C>(s);
+        uint32_t carry = 0;
+        uint32_t slot_base = m * (uint32_t)sh.nwin * sh.nbuckets;
+        for (int w = 0; w < sh.nwin; w++) {
+            uint32_t pos = (uint32_t)w * sh.c;
+            uint32_t word = pos >> 5, sft = pos & 31;
+            uint32_t lo = word < 8 ? s[word] : 0u;
+            uint32_t hi = word < 7 ? s[word + 1] : 0u;
+            uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry;
+            uint32_t neg = d > half;
+            carry = neg;
+            uint32_t mag = neg ? ((1u << sh.c) - d) : d;
+            if (mag != 0) {
+                uint32_t b = slot_base + (uint32_t)w * sh.nbuckets + (mag - 1);
+                if (!SCATTER) {
+                    atomicAdd(counters + b, 1u);
+                } else {
+                    uint32_t at = atomicAdd(counters + b, 1u);
+                    sorted[at] = pidx | (neg << 31);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- prefix sum
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// block-wide exclusive scan of one value per thread; returns the exclusive prefix, total in *sum
+PORLA_D uint32_t block_exclusive_scan(uint32_t v, uint32_t* sum) {
+    __shared__ uint32_t warp_tot[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t t = lane < (int)(blockDim.x >> 5) ? warp_tot[lane] : 0u;
+        uint32_t ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += u;
+        }
+        warp_tot[lane] = ti - t;  // exclusive warp offsets
+        if (lane == 31) *sum = ti;
+    }
+    __syncthreads();
+    uint32_t r = warp_tot[wid] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+static __global__ void __launch_bounds__(kScanThreads)
+k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+             uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t total;
+    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems], s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        v[k] = base + k < n ? in[base + k] : 0u;
+        s += v[k];
+    }
+    uint32_t ex = block_exclusive_scan(s, &total);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the tile sums in place; writes the grand total to *grand
+static __global__ void __launch_bounds__(kScanThreads)
+k_scan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles, uint32_t* __restrict__ grand) {
+    __shared__ uint32_t total;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < ntiles; base += kScanThreads) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0u;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < ntiles) tile_sums[i] = carry + ex;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand = carry;
+}
+
+// out[i] += tile offset; also mirrors the result into `copy` (the scatter cursors)
+static __global__ void __launch_bounds__(kScanThreads)
+k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ copy, uint32_t n,
+           const uint32_t* __restrict__ tile_sums) {
+    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    uint32_t off = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++)
+        if (base + k < n) {
+            uint32_t v = out[base + k] + off;
+            out[base + k] = v;
+            copy[base + k] = v;
+        }
+}
+
+// ---------------------------------------------------------------------------- accumulation
+// One thread per bucket.  `begin[b]` is the bucket's first slot in `sorted`, `end[b]` one past its
+// last (the scatter cursors after the scatter pass).  Entries are (point index | sign << 31).
+constexpr int kAccThreads = 128;
+
+template <class C>
+PORLA_D Affine<typename C::F> load_signed_point(const Affine<typename C::F>* __restrict__ points,
+                                                uint32_t e) {
+    Affine<typename C::F> p = ld16(points + (e & 0x7fffffffu));
+    if (e >> 31) p.y = p.y.neg();
+    return p;
+}
+
+template <class C>
+__global__ void __launch_bounds__(kAccThreads)
+k_accumulate(const Affine<typename C::F>* __restrict__ points, const uint32_t* __restrict__ sorted,
+             const uint32_t* __restrict__ begin, const uint32_t* __restrict__ end,
+             const uint32_t* __restrict__ order, uint32_t total_buckets,
+             XYZZ<typename C::F>* __restrict__ buckets) {
+    using F = typename C::F;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_buckets) return;
+    uint32_t b = order ? order[t] : t;
+    uint32_t j = begin[b], e = end[b];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (j < e) {
+        Affine<F> p = load_signed_point<C>(points, sorted[j]);
+        acc = XYZZ<F>{p.x, p.y, F::one(), F::one()};
+        for (++j; j < e; ++j) {
+            Affine<F> q = load_signed_point<C>(points, sorted[j]);
+            if (acc.is_inf()) acc = XYZZ<F>{q.x, q.y, F::one(), F::one()};
+            else acc.madd_finite(q);
+        }
+    }
+    st16(buckets + b, acc);
+}
+
+// ---------------------------------------------------------------------------- bucket reduction
+// Window slot s owns buckets[s*nb .. (s+1)*nb); bucket k has weight k+1.  Thread t of the slot
+// takes the chunk [t*chunk, (t+1)*chunk): running sums give sum_k (k-lo+1) B_k and S = sum_k B_k;
+// adding lo*S (small double-and-add) yields the chunk's weighted sum.  A shared-memory tree then
+// leaves one partial per block:  partials[s * blocks_per_slot + blockIdx.x].
+constexpr int kRedThreads = 64;
+
+template <class C>
+__global__ void __launch_bounds__(kRedThreads)
+k_reduce(const XYZZ<typename C::F>* __restrict__ buckets, uint32_t nb, uint32_t chunk,
+         uint32_t threads_per_slot, XYZZ<typename C::F>* __restrict__ partials) {
+    using F = typename C::F;
+    __shared__ XYZZ<F> sh[kRedThreads];
+    const uint32_t slot = blockIdx.y;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (t < threads_per_slot) {
+        const XYZZ<F>* base = buckets + (size_t)slot * nb;
+        uint32_t lo = t * chunk;
+        uint32_t hi = lo + chunk < nb ? lo + chunk : nb;
+        XYZZ<F> run = XYZZ<F>::inf();
+        for (uint32_t k = hi; k-- > lo;) {
+            XYZZ<F> bk = ld16(base + k);
+            run.add(bk);
+            acc.add(run);
+        }
+        if (lo != 0) {
+            XYZZ<F> w = mul_small(run, lo);
+            acc.add(w);
+        }
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            XYZZ<F> a = sh[threadIdx.x];
+            a.add(sh[threadIdx.x + o]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st16(partials + (size_t)slot * gridDim.x + blockIdx.x, sh[0]);
+}
+
+// ---------------------------------------------------------------------------- finalisation
+// One block per MSM.  Thread w sums the partials of window w; thread 0 then runs Horner over the
+// windows (c doublings each; doubling infinity is free so leading empty windows cost nothing),
+// normalises to affine and serialises.  out_fmt: kPointBE64 / kPointLE64 external bytes
+// (canonical, not Montgomery); out_xyzz (optional) receives the un-normalised sum for multi-GPU
+// combination.
+template <class C>
+__global__ void k_finalize(const XYZZ<typename C::F>* __restrict__ partials, uint32_t blocks_per_slot,
+                           int nwin, int c, int out_fmt, uint8_t* __restrict__ out,
+                           XYZZ<typename C::F>* __restrict__ out_xyzz) {
+    using F = typename C::F;
+    extern __shared__ uint4 sh_raw[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(sh_raw);
+    const uint32_t m = blockIdx.x;
+    for (int w = threadIdx.x; w < nwin; w += blockDim.x) {
+        const XYZZ<F>* p = partials + ((size_t)m * nwin + w) * blocks_per_slot;
+        XYZZ<F> s = ld16(p);
+        for (uint32_t k = 1; k < blocks_per_slot; k++) s.add(ld16(p + k));
+        sh[w] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    XYZZ<F> r = XYZZ<F>::inf();
+    for (int w = nwin - 1; w >= 0; w--) {
+        if (!r.is_inf())
+            for (int k = 0; k < c; k++) r = r.dbl();
+        r.add(sh[w]);
+    }
+    if (out_xyzz) st16(out_xyzz + m, r);
+    if (out) {
+        Affine<F> a = r.to_affine();
+        F x = a.x.from_internal(), y = a.y.from_internal();
+        store_u256(out, 2 * (size_t)m, out_fmt == kPointBE64, x.v);
+        store_u256(out, 2 * (size_t)m + 1, out_fmt == kPointBE64, y.v);
+    }
+}
+
+// Sum `count` XYZZ partial results per MSM (multi-GPU combine) and serialise.
+template <class C>
+__global__ void k_combine(const XYZZ<typename C::F>* __restrict__ parts, uint32_t count,
+                          uint32_t nbatch, int out_fmt, uint8_t* __restrict__ out) {
+    using F = typename C::F;
+    uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nbatch) return;
+    XYZZ<F> r = XYZZ<F>::inf();
+    for (uint32_t k = 0; k < count; k++) r.add(ld16(parts + (size_t)k * nbatch + m));
+    Affine<F> a = r.to_affine();
+    F x = a.x.from_internal(), y = a.y.from_internal();
+    store_u256(out, 2 * (size_t)m, out_fmt == kPointBE64, x.v);
+    store_u256(out, 2 * (size_t)m + 1, out_fmt == kPointBE64, y.v);
+}
+
+// ---------------------------------------------------------------------------- elementwise ops
+// Batched single-point kernels (the "FFT in the exponent" butterflies issue
+// these through mult_point/add_point/neg_point, main.go:196-222) and test hooks.
+// out[i] = k_i * P_i, scalars 32-byte records, plain double-and-add.
+template <class C>
+__global__ void __launch_bounds__(128)
+k_scalar_mul(const Affine<typename C::F>* __restrict__ points, uint32_t npoints,
+             const uint8_t* __restrict__ scalars, int big_endian, uint32_t n,
+             Affine<typename C::F>* __restrict__ out) {
+    using F = typename C::F;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    load_u256(scalars, i, big_endian, s);
+    reduce_scalar<C>(s);
+    Affine<F> p = ld16(points + (npoints == 1 ? 0 : i));
+    XYZZ<F> r = XYZZ<F>::inf();
+    if (!p.is_inf()) {
+        int top = 255;
+        while (top >= 0 && !((s[top >> 5] >> (top & 31)) & 1u)) top--;
+        for (int b = top; b >= 0; b--) {
+            r = r.dbl();
+            if ((s[b >> 5] >> (b & 31)) & 1u) r.madd(p);
+        }
+    }
+    st16(out + i, r.to_affine());
+}
+
+// out[i] = a[i] + b[i]
+template <class C>
+__global__ void k_point_add(const Affine<typename C::F>* __restrict__ a,
+                            const Affine<typename C::F>* __restrict__ b, uint32_t n,
+                            Affine<typename C::F>* __restrict__ out) {
+    using F = typename C::F;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> r = XYZZ<F>::from_affine(ld16(a + i));
+    r.madd(ld16(b + i));
+    st16(out + i, r.to_affine());
+}
+
+// out[i] = a[i] * b[i] on raw field elements (internal form) -- unit-test hook for the PTX path
+template <class C>
+__global__ void k_field_mul(const typename C::F* __restrict__ a, const typename C::F* __restrict__ b,
+                            uint32_t n, typename C::F* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = a[i] * b[i];
+}
+
+}  // namespace porla
