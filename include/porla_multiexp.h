@@ -143,8 +143,14 @@ int porla_secp256k1_ecmult_multi_var(const porla_secp256k1_callback* error_callb
 /* 33-byte SEC1 compressed form of a gej/ge result (eckey_impl.h:36-52); returns 0 for infinity. */
 int porla_secp256k1_gej_serialize(const porla_secp256k1_gej* a, unsigned char out33[33]);
 
+/* Integer-multiply roofline probe: sustained 32x32->64 multiply-accumulates per second of the
+ * device.  variant 0: mad.wide.u32 (IMAD.WIDE.U32); 1: mad.lo.cc/madc.hi.cc carry chains as the
+ * field code issues them; 2: 32-bit mad.lo.  Runs at least min_seconds. */
+double porla_measure_pint(int variant, double min_seconds);
+
 /* ---- test hooks (host buffers; GPU kernels underneath) */
-/* out[i] = a[i]*b[i] in the curve's base field, canonical 8x32 LE limbs in and out. */
+/* out[i] = a[i] (*) b[i], the device field product on raw 8x32 LE limbs: a*b mod p for secp256k1,
+ * the Montgomery product a*b*2^-256 mod p for BN254. */
 void porla_debug_field_mul(int curve, const void* a, const void* b, int64_t n, void* out);
 /* out[i] = a[i] + b[i] on external 64-byte points (host-side group law, the code behind add_point). */
 void porla_debug_point_add_host(int curve, const void* a, const void* b, int64_t n, int point_fmt, void* out);

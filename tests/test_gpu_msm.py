@@ -1,0 +1,177 @@
+"""Parity of the CUDA path against the oracle, through the C-ABI (libmultiexp.so).
+
+BN254: the oracle is oracle/curves_py.py (independent big-int restatement; gnark-crypto is not
+available, so "parity vs restatement").  secp256k1: oracle/curves_py.py here, and the vendored
+reference C (oracle/_ref) in tests/test_gpu_secp_ref.py.
+"""
+import ctypes as C
+import random
+
+import pytest
+
+import porla_b200 as pb
+from oracle import curves_py as O
+
+pytestmark = pytest.mark.gpu
+
+BN, SE = O.BN254, O.SECP256K1
+
+
+def be(x):
+    return x.to_bytes(32, "big")
+
+
+def enc_points(pts):
+    return b"".join(bytes(64) if P is None else be(P[0]) + be(P[1]) for P in pts)
+
+
+def rand_points(c, n, seed):
+    rnd = random.Random(seed)
+    G = (c.gx, c.gy)
+    base = [O.hash_point(c, i) for i in range(min(n, 24))]
+    out = []
+    for i in range(n):
+        if i < len(base):
+            out.append(base[i])
+        else:  # cheap: sums of earlier points stay on the curve
+            out.append(O.add(c, out[rnd.randrange(i)], out[rnd.randrange(i)]))
+    return out
+
+
+@pytest.mark.parametrize("curve,c", [(pb.CURVE_BN254, BN), (pb.CURVE_SECP256K1, SE)])
+def test_field_mul_matches_bigint(curve, c):
+    rnd = random.Random(1)
+    n = 4096
+    a = [rnd.randrange(c.p) for _ in range(n)]
+    b = [rnd.randrange(c.p) for _ in range(n)]
+    a[0], b[0] = c.p - 1, c.p - 1
+    a[1], b[1] = 0, 5
+    a[2], b[2] = 1, c.p - 1
+    le = lambda v: v.to_bytes(32, "little")
+    ab, bb, ob = bytearray(b"".join(map(le, a))), bytearray(b"".join(map(le, b))), bytearray(32 * n)
+    pb.load().porla_debug_field_mul(curve, (C.c_ubyte * len(ab)).from_buffer(ab), (C.c_ubyte * len(bb)).from_buffer(bb), n,
+                                    (C.c_ubyte * len(ob)).from_buffer(ob))
+    rinv = pow(1 << 256, -1, c.p) if c is BN else 1
+    for i in range(n):
+        got = int.from_bytes(ob[32 * i:32 * i + 32], "little")
+        assert got == a[i] * b[i] * rinv % c.p, i
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 128, 766, 1500])
+def test_compute_multi_exp_matches_oracle(n):
+    rnd = random.Random(n)
+    pts = rand_points(BN, n, n)
+    sc = [rnd.randrange(1 << 256) for _ in range(n)]          # >= r values are reduced (fr.SetBytes)
+    got = pb.bn254_multi_exp(enc_points(pts), b"".join(map(be, sc)), n)
+    assert got == O.bn254_marshal(O.msm(BN, sc, pts))
+
+
+def test_compute_multi_exp_zero_length():
+    assert pb.bn254_multi_exp(b"", b"", 0) == bytes(64)
+
+
+def test_porla_audit_shape_31bit_scalars_with_infinities():
+    # Server.hpp:900-901: 31-bit coefficients, many alignment MACs still infinity
+    n = 766
+    rnd = random.Random(7)
+    pts = rand_points(BN, n, 3)
+    for i in range(0, n, 5):
+        pts[i] = None
+    sc = [rnd.randrange(1 << 31) for _ in range(n)]
+    scb = b"".join(pb.bn254_scalar_set_int(s) for s in sc)
+    got = pb.bn254_multi_exp(enc_points(pts), scb, n)
+    assert got == O.bn254_marshal(O.msm(BN, sc, pts))
+
+
+def test_edge_cases_cancel_duplicate_zero():
+    rnd = random.Random(11)
+    P, Q = O.hash_point(BN, 100), O.hash_point(BN, 101)
+    cases = [
+        ([5, 5], [P, O.neg(BN, P)]),                 # cancels to infinity
+        ([3, 4, 9], [P, P, P]),                      # same point in several buckets
+        ([7, 7, 7, 7], [P, P, Q, Q]),                # P + P inside one bucket -> doubling branch
+        ([0, 0, 0], [P, Q, P]),                      # all-zero scalars
+        ([BN.n, BN.n + 1], [P, Q]),                  # reduction: r -> 0, r+1 -> 1
+        ([BN.n - 1, 1], [P, P]),                     # (r-1)P + P = infinity
+        ([1 << 255, (1 << 256) - 1], [P, Q]),
+        ([12345], [None]),
+    ]
+    for sc, pts in cases:
+        got = pb.bn254_multi_exp(enc_points(pts), b"".join(map(be, sc)), len(sc))
+        assert got == O.bn254_marshal(O.msm_naive(BN, sc, pts)), (sc,)
+    # constant scalar, many points (one giant bucket per window)
+    n = 300
+    pts = rand_points(BN, n, 5)
+    k = rnd.randrange(BN.n)
+    got = pb.bn254_multi_exp(enc_points(pts), be(k) * n, n)
+    assert got == O.bn254_marshal(O.msm(BN, [k] * n, pts))
+
+
+def test_batch_multi_exp():
+    batch, n = 5, 40
+    rnd = random.Random(3)
+    pts = rand_points(BN, batch * n, 9)
+    sc = [rnd.randrange(BN.n) for _ in range(batch * n)]
+    got = pb.bn254_multi_exp_batch(enc_points(pts), b"".join(map(be, sc)), n, batch)
+    for m in range(batch):
+        exp = O.bn254_marshal(O.msm(BN, sc[m * n:(m + 1) * n], pts[m * n:(m + 1) * n]))
+        assert got[64 * m:64 * m + 64] == exp, m
+
+
+@pytest.mark.parametrize("window", [0, 4, 9, 13, 16])
+def test_window_sizes_agree(window, monkeypatch):
+    n = 600
+    rnd = random.Random(2)
+    pts = rand_points(BN, n, 21)
+    sc = [rnd.randrange(BN.n) for _ in range(n)]
+    if window:
+        monkeypatch.setenv("PORLA_WINDOW_BITS", str(window))
+    got = pb.bn254_multi_exp(enc_points(pts), b"".join(map(be, sc)), n)
+    assert got == O.bn254_marshal(O.msm(BN, sc, pts))
+
+
+def test_multiples_table_and_closed_form():
+    # table[i] = k_i G; MSM(s, table) = (sum s_i k_i) G  -- size-independent checksum
+    import torch
+    n = 1 << 14
+    rnd = random.Random(4)
+    ks = [rnd.randrange(BN.n) for _ in range(n)]
+    ss = [rnd.randrange(BN.n) for _ in range(n)]
+    tab = pb.Table.multiples_of_generator(pb.CURVE_BN254, b"".join(k.to_bytes(32, "little") for k in ks), n, pb.SCALAR_LE32)
+    ext = tab.export()
+    G = (1, 2)
+    for i in (0, 1, n // 2, n - 1):
+        assert ext[64 * i:64 * i + 64] == O.bn254_marshal(O.mul(BN, ks[i], G))
+    d_sc = torch.frombuffer(bytearray(b"".join(map(be, ss))), dtype=torch.uint8).cuda()
+    d_out = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    tab.msm_device(d_sc.data_ptr(), n, d_out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    expect = O.mul(BN, sum(s * k for s, k in zip(ss, ks)) % BN.n, G)
+    assert bytes(d_out.cpu().numpy()) == O.bn254_marshal(expect)
+    tab.destroy()
+
+
+@pytest.mark.parametrize("n", [1, 5, 96, 700])
+def test_secp256k1_msm_host(n):
+    rnd = random.Random(n + 1)
+    pts = rand_points(SE, n, n + 5)
+    sc = [rnd.randrange(1 << 256) for _ in range(n)]
+    got = pb.msm_host(pb.CURVE_SECP256K1, b"".join(s.to_bytes(32, "little") for s in sc), enc_points(pts), n,
+                      scalar_fmt=pb.SCALAR_LE32, point_fmt=pb.POINT_BE64)
+    exp = O.msm(SE, sc, pts)
+    assert got == (bytes(64) if exp is None else be(exp[0]) + be(exp[1]))
+
+
+def test_secp256k1_adapter_callback():
+    n = 40
+    rnd = random.Random(8)
+    pts = rand_points(SE, n, 77)
+    pts[3] = None
+    sc = [rnd.randrange(SE.n) for _ in range(n)]
+    sc[5] = 0
+    ok, res = pb.secp256k1_ecmult_multi_var(sc, pts, g_scalar=0)
+    assert ok == 1 and res == O.msm(SE, sc, pts)
+    ok, res = pb.secp256k1_ecmult_multi_var(sc, pts, g_scalar=12345)
+    assert res == O.add(SE, O.msm(SE, sc, pts), O.mul(SE, 12345, (SE.gx, SE.gy)))
+    ok, res = pb.secp256k1_ecmult_multi_var([], [], g_scalar=None)
+    assert ok == 1 and res is None
