@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- G1 MSM points/second on N B200s (BASELINE.json metric), and the CPU reference arm.
+
+A "step" is one multi-scalar multiplication over synthetic inputs: every rank owns 2^LOG2N BN254 G1
+points resident in HBM (a contiguous range of one N*2^LOG2N-point MSM) plus a
+rotating set of scalar vectors.  Each step: the Pippenger pipeline on each rank -> one 128-byte
+XYZZ partial per rank -> NCCL all-gather (the only exchange step) -> final add + normalisation.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log2n 20] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM;
+`e2e` = the same metric through the legacy C-ABI call `compute_multi_exp` with HOST buffers
+(H2D of scalars+points, import, MSM, D2H inside the timed region).  `--impl reference` times the
+CPU path of the reference's algorithm on the host cores (oracle port: gnark-crypto itself is not
+available offline).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "G1 MSM points/sec"
+MAC32_PER_POINT = 21760           # 16 windows x 10 field mults x 136 MAC32 (BN254)
+BYTES_PER_POINT = 96              # 64 B affine point + 32 B scalar, read once
+SCALAR_SETS = 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--log2n", type=int, default=int(os.environ.get("PORLA_BENCH_LOG2N", "20")))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample-log2n", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", default=os.environ.get("PORLA_BENCH_SWEEP", "16,24"),
+                    help="extra sizes (log2) timed at N=1 and reported under 'sweep'")
+    return ap.parse_args()
+
+
+def workload_name(log2n, world):
+    return ("single BN254 G1 MSM, 2^%d uniform 256-bit scalars (reduced mod r) x 2^%d random points per GPU"
+            " (BASELINE.json configs[1]%s)" % (log2n, log2n, "" if world == 1 else ", range-sharded over %d GPUs, configs[4]" % world))
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+def cpu_port_rate(log2n: int, threads: int, steps: int = 1, warmup: int = 0):
+    """points/s of the C restatement (oracle/bn254_oracle.c) on a 2^log2n sample of the workload."""
+    from oracle import loader, curves_py as O
+    import hashlib
+    n = 1 << log2n
+    G = O.bn254_marshal((1, 2))
+    step = O.bn254_marshal(O.mul(O.BN254, 0x9E3779B97F4A7C15F39CC0605CEDC834, (1, 2)))
+    points = loader.bn254_point_chain(G, step, n)
+    scalars = b"".join(hashlib.sha256(b"porla-sc" + i.to_bytes(8, "little")).digest() for i in range(n))
+    best = None
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        loader.bn254_msm(scalars, points, n, threads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            best = dt if best is None else min(best, dt)
+    return n / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    log2s = min(args.log2n, args.cpu_sample_log2n + 2)
+    steps = max(1, min(args.steps, 3))
+    rate, sec = cpu_port_rate(log2s, threads, steps=steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 / u64x4 Montgomery (integer)", "data": "synthetic",
+        "config": {"workload": workload_name(args.log2n, 1),
+                   "note": "CPU arm: C restatement of gnark-crypto v0.6.0 MultiExp (oracle/bn254_oracle.c), NOT gnark-crypto "
+                           "itself (Go toolchain/module unavailable offline); window-parallel workers as gnark does"},
+        "cpu_baseline": {"value": rate, "unit": "points/s", "cores": threads, "kind": "port",
+                         "sample": "one 2^%d-point MSM per step (bounded sample of the 2^%d workload)" % (log2s, args.log2n)},
+        "e2e": {"value": rate, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(len(s) > col and s[col].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(self.samples[0][1])),
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import porla_b200 as pb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("PORLA_DEVICE", str(local))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = pb.load()
+    lib.porla_device_init()
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make_inputs(log2n):
+        n = 1 << log2n
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + 7919 * rank + log2n)
+        ks = torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device=dev, generator=g)
+        table = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks.data_ptr(), n, pb.SCALAR_LE32, on_device=True, stream=stream)
+        torch.cuda.synchronize()
+        scalars = [torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device=dev, generator=g) for _ in range(SCALAR_SETS)]
+        return n, table, scalars, ks
+
+    xyzz = torch.zeros(128, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(128 * world, dtype=torch.uint8, device=dev)
+    out = torch.zeros(64, dtype=torch.uint8, device=dev)
+
+    def step(table, scalars, n, i):
+        sc = scalars[i % SCALAR_SETS]
+        if world == 1:
+            table.msm_device(sc.data_ptr(), n, out.data_ptr(), scalar_fmt=pb.SCALAR_LE32, stream=stream)
+        else:
+            table.msm_device(sc.data_ptr(), n, 0, scalar_fmt=pb.SCALAR_LE32, d_out_xyzz=xyzz.data_ptr(), stream=stream)
+            dist.all_gather_into_tensor(gathered, xyzz)
+            if rank == 0:
+                lib.porla_msm_combine_device(pb.CURVE_BN254, C.c_void_p(gathered.data_ptr()), world, 1, pb.POINT_BE64,
+                                             C.c_void_p(out.data_ptr()), C.c_void_p(stream))
+
+    def timed(table, scalars, n, steps, warmup):
+        for i in range(warmup):
+            step(table, scalars, n, i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.porla_launch_count()
+        e0.record()
+        for i in range(steps):
+            step(table, scalars, n, warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.porla_launch_count() - l0
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, launches
+
+    n, table, scalars, ks = make_inputs(args.log2n)
+
+    # ---- headline: device-resident throughput
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_step, launches = timed(table, scalars, n, args.steps, max(args.warmup, 3))
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    value = world * n / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the launch stream
+    p_int = lib.porla_measure_pint(1, 0.25) if rank == 0 else 0.0
+    lib.porla_stage_timing_enable(1)
+    stage = (C.c_float * 8)()
+    acc_ms, stage_sum = [], None
+    for i in range(max(3, min(args.steps, 10))):
+        step(table, scalars, n, i)
+        torch.cuda.synchronize()
+        k = lib.porla_stage_timing_read(stage)
+        vals = [stage[j] for j in range(k)]
+        acc_ms.append(vals[3])
+        stage_sum = vals if stage_sum is None else [a + b for a, b in zip(stage_sum, vals)]
+    lib.porla_stage_timing_enable(0)
+    stages = {nm: v / len(acc_ms) for nm, v in zip(["count", "scan", "scatter", "accumulate", "reduce", "finalize"], stage_sum)}
+    acc_avg = sum(acc_ms) / len(acc_ms)
+
+    # ---- e2e through the legacy C-ABI with host buffers (pinned)
+    e2e = None
+    if True:
+        import numpy as np
+        pts_host = torch.empty(n * 64, dtype=torch.uint8).pin_memory()
+        lib.porla_table_export(C.c_void_p(table.handle), pb.POINT_BE64, C.c_void_p(pts_host.data_ptr()), 0, None)
+        # big-endian 32-byte scalars as bn254_scalar (utils.h:307-318)
+        sc_le = scalars[0].cpu().numpy().view(np.uint8).reshape(n, 32)
+        sc_host = torch.from_numpy(np.ascontiguousarray(sc_le[:, ::-1])).pin_memory()
+        res = (C.c_ubyte * 64)()
+        gs_sc = pb.GoSlice(sc_host.data_ptr(), n * 32, n * 32)
+        gs_pt = pb.GoSlice(pts_host.data_ptr(), n * 64, n * 64)
+        gs_out = pb.GoSlice(C.cast(res, C.c_void_p), 64, 64)
+        e2e_steps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            lib.compute_multi_exp(C.byref(gs_sc), C.byref(gs_pt), n, C.byref(gs_out))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            lib.compute_multi_exp(C.byref(gs_sc), C.byref(gs_pt), n, C.byref(gs_out))
+            if world > 1:
+                part = torch.frombuffer(bytearray(bytes(res)), dtype=torch.uint8).to(dev)
+                allp = torch.zeros(64 * world, dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(allp, part)
+                if rank == 0:
+                    acc = bytearray(allp[:64].cpu().numpy().tobytes())
+                    for r in range(1, world):
+                        pb.bn254_add(acc, allp[64 * r:64 * r + 64].cpu().numpy().tobytes())
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": world * n / dt, "unit": "points/s", "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": 64,
+               "ms_per_step": dt * 1e3, "api": "compute_multi_exp(GoSlice*, GoSlice*, GoInt, GoSlice*) with pinned host buffers"}
+        # the device result of the same scalars must equal the C-ABI result (cheap self-check)
+        step(table, scalars, n, 0)
+        torch.cuda.synchronize()
+        if world == 1 and bytes(out.cpu().numpy().tobytes()) != bytes(res):
+            raise SystemExit("bench self-check failed: device MSM and compute_multi_exp disagree")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- sweep at other sizes (N = 1 only; reported, not the headline)
+    sweep = {}
+    if world == 1 and args.sweep:
+        for lg in [int(x) for x in args.sweep.split(",") if x]:
+            if lg == args.log2n:
+                continue
+            n2, t2, s2, _ = make_inputs(lg)
+            ms2, _ = timed(t2, s2, n2, max(3, min(args.steps, 5)), 3)
+            sweep["2^%d" % lg] = {"points_per_s": n2 / (ms2 * 1e-3), "ms_per_step": ms2,
+                                  "whole_msm_frac_of_imad_peak": n2 * MAC32_PER_POINT / (ms2 * 1e-3) / p_int}
+            t2.destroy()
+
+    # ---- CPU baseline beside it (bounded sample, host cores of this box)
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        lgs = min(args.log2n, args.cpu_sample_log2n)
+        rate, sec = cpu_port_rate(lgs, threads)
+        cpu = {"value": rate, "unit": "points/s", "cores": threads, "kind": "port",
+               "sample": "one 2^%d-point BN254 MSM (%.2f s) with the C restatement of gnark-crypto MultiExp, "
+                         "window-parallel over %d threads" % (lgs, sec, threads)}
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    macs = n * MAC32_PER_POINT
+    line = {
+        "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 (8x32-bit limb Montgomery, IMAD carry chains)", "data": "synthetic",
+        "config": {"workload": workload_name(args.log2n, world), "points_per_gpu": n, "window_bits": lib.porla_choose_window(0, n, 1),
+                   "l2": "each step uses one of %d resident scalar vectors in rotation; per-step working set (table %d MiB + "
+                         "scalars %d MiB + sorted pairs + buckets) exceeds the 126 MB L2" % (SCALAR_SETS, n * 64 >> 20, n * 32 >> 20),
+                   "parallelism": "point-range sharding, 1 process/GPU, 128 B all-gather" if world > 1 else "single GPU"},
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary() if sampler else None,
+        "roofline": {
+            "bound": "imad", "kernel": "k_accumulate<Bn254>",
+            "achieved": macs / (acc_avg * 1e-3) / 1e12, "peak": p_int / 1e12, "unit": "TMAC32/s",
+            "frac": macs / (acc_avg * 1e-3) / p_int,
+            "peak_source": "measured live: porla_measure_pint (mad.lo.cc/madc.hi.cc chains, all SMs); integer pipe is not in MEASURED_PEAKS.json",
+            "whole_msm_frac": macs / (ms_step * 1e-3) / p_int if world == 1 else None,
+            "traffic": None,
+            "hbm": {"algorithmic_gbs": n * BYTES_PER_POINT / (ms_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            "stage_ms": stages,
+        },
+        "cpu_baseline": cpu,
+        "sweep": sweep,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -119,6 +119,10 @@ void porla_msm_combine_device(int curve, const void* d_parts, int64_t count, int
 void porla_msm_host(int curve, const void* scalars, const void* points, int64_t n, int64_t nbatch,
                     int scalar_fmt, int point_fmt, void* out);
 int porla_choose_window(int curve, int64_t n, int64_t nbatch);
+/* Per-stage CUDA-event timing of the most recent porla_msm_device call: ms_out[0..5] = count,
+ * scan, scatter, accumulate, reduce, finalize.  Returns the number of stages (0 when disabled). */
+void porla_stage_timing_enable(int on);
+int porla_stage_timing_read(float* ms_out);
 
 /* Batched single-scalar multiplication out[i] = k_i * table[i] (table of length 1: fixed base). */
 void porla_scalar_mul_batch_device(const porla_table* t, const void* d_scalars, int64_t n,

@@ -359,6 +359,8 @@ void set_inf_point(GoSlice* point) {
 // ============================================================================ new entry points
 int porla_device_init(void) { return device_init(); }
 uint64_t porla_launch_count(void) { return launches_issued(); }
+void porla_stage_timing_enable(int on) { stage_timing_enable(on); }
+int porla_stage_timing_read(float* ms_out) { return stage_timing_read(ms_out); }
 int porla_choose_window(int curve, int64_t n, int64_t nbatch) { return choose_window(curve, (uint32_t)n, (uint32_t)nbatch); }
 
 void compute_multi_exp_batch(GoSlice* scalars, GoSlice* points, GoInt length, GoInt batch, GoSlice* results_out) {

@@ -41,4 +41,21 @@ struct Arena {
     static size_t padded(size_t count, size_t elt) { return (count * elt + 255) & ~(size_t)255; }
 };
 
+// Optional per-stage CUDA-event timing of the most recent MSM (bench.py's live roofline figure).
+enum { kStageCount = 0, kStageScan, kStageScatter, kStageAccumulate, kStageReduce, kStageFinalize, kNumStages };
+struct StageTimer {
+    bool enabled = false;
+    cudaEvent_t ev[kNumStages + 1] = {};
+    bool created = false;
+    void mark(int i, cudaStream_t s) {
+        if (!enabled) return;
+        if (!created) {
+            for (auto& e : ev) PORLA_CUDA(cudaEventCreate(&e));
+            created = true;
+        }
+        PORLA_CUDA(cudaEventRecord(ev[i], s));
+    }
+};
+extern StageTimer g_stage_timer;
+
 }  // namespace porla

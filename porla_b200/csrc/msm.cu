@@ -56,6 +56,20 @@ int device_init() {
 // forward declarations of the per-curve drivers (msm_impl.cuh)
 std::mutex g_engine_mu;
 Arena g_arena;
+StageTimer g_stage_timer;
+
+void stage_timing_enable(int on) { g_stage_timer.enabled = on != 0; }
+int stage_timing_read(float* ms_out) {
+    if (!g_stage_timer.enabled || !g_stage_timer.created) return 0;
+    PORLA_CUDA(cudaEventSynchronize(g_stage_timer.ev[kNumStages]));
+    for (int i = 0; i < kNumStages; i++) {
+        float ms = 0;
+        // a stage that was skipped (empty MSM) keeps a stale event: report what CUDA gives
+        if (cudaEventElapsedTime(&ms, g_stage_timer.ev[i], g_stage_timer.ev[i + 1]) != cudaSuccess) ms = 0;
+        ms_out[i] = ms;
+    }
+    return kNumStages;
+}
 
 template <class C> void import_impl(const uint8_t*, int, uint32_t, PointTable*, cudaStream_t);
 template <class C> void msm_impl(const PointTable&, const uint8_t*, uint32_t, uint32_t, const MsmOptions&, uint8_t*, void*, cudaStream_t);

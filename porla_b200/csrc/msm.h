@@ -64,6 +64,11 @@ void export_points_device(int curve, const void* d_affine, uint32_t n, int point
 void field_mul_device(int curve, const void* d_a, const void* d_b, uint32_t n, void* d_out,
                       cudaStream_t stream);
 
+// Per-stage CUDA-event timing of the most recent msm_device call (count, scan, scatter, accumulate,
+// reduce, finalize), in ms.  Returns the number of stages written (0 when disabled).
+void stage_timing_enable(int on);
+int stage_timing_read(float* ms_out);
+
 int choose_window(int curve, uint32_t n, uint32_t nbatch);
 uint64_t launches_issued();   // number of kernels this library has launched (bench's gpu_launches)
 

@@ -19,6 +19,7 @@ extern std::atomic<uint64_t> g_launches;
 extern std::mutex g_engine_mu;
 extern Arena g_arena;
 
+
 template <class C> struct CurveIdOf;
 template <> struct CurveIdOf<Bn254> { static constexpr int value = kCurveBn254; };
 template <> struct CurveIdOf<Secp256k1> { static constexpr int value = kCurveSecp256k1; };
@@ -102,29 +103,35 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     const Affine<F>* points = reinterpret_cast<const Affine<F>*>(table.d_points);
     const uint64_t total_scalars = (uint64_t)n * nbatch;
 
+    g_stage_timer.mark(kStageCount, stream);
     PORLA_CUDA(cudaMemsetAsync(counters, 0, (size_t)nbt * 4, stream));
     if (total_scalars) {
         uint32_t grid = (uint32_t)((total_scalars + 255) / 256);
         if (grid > 148u * 32u) grid = 148u * 32u;
         k_digits<C, false><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, counters, nullptr);
         LAUNCHED();
+        g_stage_timer.mark(kStageScan, stream);
         k_scan_tiles<<<ntiles, kScanThreads, 0, stream>>>(counters, offsets, nbt, tile_sums);
         LAUNCHED();
         k_scan_sums<<<1, kScanThreads, 0, stream>>>(tile_sums, ntiles, grand);
         LAUNCHED();
         k_scan_add<<<ntiles, kScanThreads, 0, stream>>>(offsets, counters, nbt, tile_sums);
         LAUNCHED();
+        g_stage_timer.mark(kStageScatter, stream);
         k_digits<C, true><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, counters, sorted);
         LAUNCHED();
     } else {
         PORLA_CUDA(cudaMemsetAsync(offsets, 0, (size_t)nbt * 4, stream));
     }
+    g_stage_timer.mark(kStageAccumulate, stream);
     k_accumulate<C><<<(nbt + kAccThreads - 1) / kAccThreads, kAccThreads, 0, stream>>>(
         points, sorted, offsets, counters, nullptr, nbt, buckets);
     LAUNCHED();
+    g_stage_timer.mark(kStageReduce, stream);
     dim3 rgrid(blocks_per_slot, (uint32_t)slots);
     k_reduce<C><<<rgrid, kRedThreads, 0, stream>>>(buckets, sh.nbuckets, chunk, threads_per_slot, partials);
     LAUNCHED();
+    g_stage_timer.mark(kStageFinalize, stream);
     k_finalize<C><<<nbatch, 64, sh.nwin * sizeof(XYZZ<F>), stream>>>(
         partials, blocks_per_slot, sh.nwin, sh.c, opt.out_fmt, d_out, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
     LAUNCHED();

@@ -29,6 +29,7 @@ NEW_SYMBOLS = [
     "porla_msm_device", "porla_msm_combine_device", "porla_msm_host", "porla_choose_window",
     "porla_scalar_mul_batch_device", "porla_secp256k1_ecmult_multi_var",
     "porla_secp256k1_gej_serialize", "porla_debug_field_mul", "porla_debug_point_add_host", "porla_measure_pint",
+    "porla_stage_timing_enable", "porla_stage_timing_read",
 ]
 
 
@@ -103,6 +104,8 @@ def load() -> C.CDLL:
         "porla_secp256k1_ecmult_multi_var": (I, [P, P, C.POINTER(SecpGej), C.POINTER(SecpScalar), SECP_CB, P, C.c_size_t]),
         "porla_secp256k1_gej_serialize": (I, [C.POINTER(SecpGej), C.c_char_p]),
         "porla_measure_pint": (C.c_double, [I, C.c_double]),
+        "porla_stage_timing_enable": (None, [I]),
+        "porla_stage_timing_read": (I, [C.POINTER(C.c_float)]),
         "porla_debug_field_mul": (None, [I, P, P, C.c_int64, P]),
         "porla_debug_point_add_host": (None, [I, P, P, C.c_int64, I, P]),
     }
