@@ -81,30 +81,47 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     const uint32_t nbt = (uint32_t)nbt64;
     const uint32_t ntiles = (nbt + kScanTile - 1) / kScanTile;
 
-    // reduction geometry
-    uint32_t chunk = 8;
+    // reduction geometry: enough threads to fill the machine, chunks as long as that allows
+    uint32_t chunk = 64;
+    while (chunk > 4 && (uint64_t)nbt / chunk < 148ull * 512ull) chunk >>= 1;
     uint32_t threads_per_slot = (sh.nbuckets + chunk - 1) / chunk;
     uint32_t blocks_per_slot = (threads_per_slot + kRedThreads - 1) / kRedThreads;
 
+    // accumulation geometry: slice length L (pairs per thread)
+    const uint64_t pairs_cap = pairs64 ? pairs64 : 1;
+    uint32_t L = 64;
+    while (L > 4 && pairs_cap / L < 148ull * 512ull * 4ull) L >>= 1;
+    const uint32_t nslices_cap = (uint32_t)((pairs_cap + L - 1) / L);
+    const uint32_t long_cap = (uint32_t)(pairs_cap / ((uint64_t)L * kStitchSerial)) + 2;
+
     std::lock_guard<std::mutex> lock(g_engine_mu);
-    size_t need = Arena::padded(nbt, 4) * 2 + Arena::padded(ntiles + 1, 4) + 256 +
-                  Arena::padded(pairs64 ? pairs64 : 1, 4) + Arena::padded(nbt, sizeof(XYZZ<F>)) +
-                  Arena::padded(slots * blocks_per_slot, sizeof(XYZZ<F>));
+    size_t need = Arena::padded(nbt, 4) * 2 + Arena::padded(ntiles + 1, 4) + 512 +
+                  Arena::padded(pairs_cap, 8) + Arena::padded(nbt, sizeof(XYZZ<F>)) +
+                  2 * Arena::padded(nslices_cap, sizeof(XYZZ<F>)) + Arena::padded(long_cap, 8) +
+                  Arena::padded(slots * blocks_per_slot, sizeof(XYZZ<F>)) + Arena::padded(slots, sizeof(XYZZ<F>));
     g_arena.reserve(need, stream);
     g_arena.reset();
     uint32_t* counters = g_arena.take<uint32_t>(nbt);
     uint32_t* offsets = g_arena.take<uint32_t>(nbt);
     uint32_t* tile_sums = g_arena.take<uint32_t>(ntiles + 1);
-    uint32_t* grand = g_arena.take<uint32_t>(1);
-    uint32_t* sorted = g_arena.take<uint32_t>(pairs64 ? pairs64 : 1);
+    uint32_t* grand = g_arena.take<uint32_t>(1);       // total number of (point, window) pairs
+    uint32_t* long_count = g_arena.take<uint32_t>(1);
+    uint2* sorted = g_arena.take<uint2>(pairs_cap);
     XYZZ<F>* buckets = g_arena.take<XYZZ<F>>(nbt);
+    XYZZ<F>* part_head = g_arena.take<XYZZ<F>>(nslices_cap);
+    XYZZ<F>* part_tail = g_arena.take<XYZZ<F>>(nslices_cap);
+    uint2* long_runs = g_arena.take<uint2>(long_cap);
     XYZZ<F>* partials = g_arena.take<XYZZ<F>>(slots * blocks_per_slot);
+    XYZZ<F>* wsum = g_arena.take<XYZZ<F>>(slots);
 
     const Affine<F>* points = reinterpret_cast<const Affine<F>*>(table.d_points);
     const uint64_t total_scalars = (uint64_t)n * nbatch;
 
     g_stage_timer.mark(kStageCount, stream);
     PORLA_CUDA(cudaMemsetAsync(counters, 0, (size_t)nbt * 4, stream));
+    PORLA_CUDA(cudaMemsetAsync(grand, 0, 4, stream));
+    PORLA_CUDA(cudaMemsetAsync(long_count, 0, 4, stream));
+    PORLA_CUDA(cudaMemsetAsync(buckets, 0, (size_t)nbt * sizeof(XYZZ<F>), stream));  // empty bucket = infinity
     if (total_scalars) {
         uint32_t grid = (uint32_t)((total_scalars + 255) / 256);
         if (grid > 148u * 32u) grid = 148u * 32u;
@@ -120,24 +137,37 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         g_stage_timer.mark(kStageScatter, stream);
         k_digits<C, true><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, counters, sorted);
         LAUNCHED();
+        g_stage_timer.mark(kStageAccumulate, stream);
+        k_accumulate<C><<<(nslices_cap + kAccThreads - 1) / kAccThreads, kAccThreads, 0, stream>>>(
+            points, sorted, grand, L, buckets, part_head, part_tail);
+        LAUNCHED();
+        k_stitch<C><<<(nslices_cap + 63) / 64, 64, 0, stream>>>(sorted, grand, L, buckets, part_head, part_tail, long_count,
+                                                               long_runs);
+        LAUNCHED();
+        k_stitch_long<C><<<148, kLongThreads, 0, stream>>>(sorted, grand, L, buckets, part_head, long_count, long_runs);
+        LAUNCHED();
     } else {
-        PORLA_CUDA(cudaMemsetAsync(offsets, 0, (size_t)nbt * 4, stream));
+        g_stage_timer.mark(kStageScan, stream);
+        g_stage_timer.mark(kStageScatter, stream);
+        g_stage_timer.mark(kStageAccumulate, stream);
     }
-    g_stage_timer.mark(kStageAccumulate, stream);
-    k_accumulate<C><<<(nbt + kAccThreads - 1) / kAccThreads, kAccThreads, 0, stream>>>(
-        points, sorted, offsets, counters, nullptr, nbt, buckets);
-    LAUNCHED();
     g_stage_timer.mark(kStageReduce, stream);
     dim3 rgrid(blocks_per_slot, (uint32_t)slots);
     k_reduce<C><<<rgrid, kRedThreads, 0, stream>>>(buckets, sh.nbuckets, chunk, threads_per_slot, partials);
     LAUNCHED();
+    const XYZZ<F>* window_sums = partials;
+    if (blocks_per_slot > 1) {
+        k_window_sums<C><<<(uint32_t)slots, kRedThreads, 0, stream>>>(partials, blocks_per_slot, wsum);
+        LAUNCHED();
+        window_sums = wsum;
+    }
     g_stage_timer.mark(kStageFinalize, stream);
     k_finalize<C><<<nbatch, 64, sh.nwin * sizeof(XYZZ<F>), stream>>>(
-        partials, blocks_per_slot, sh.nwin, sh.c, opt.out_fmt, d_out, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
+        window_sums, 1, sh.nwin, sh.c, opt.out_fmt, d_out, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
     LAUNCHED();
+    g_stage_timer.mark(kNumStages, stream);
     PORLA_CUDA(cudaGetLastError());
 }
-
 
 template <class C>
 void combine_impl(const void* d_parts, uint32_t count, uint32_t nbatch, int out_fmt, uint8_t* d_out, cudaStream_t stream) {

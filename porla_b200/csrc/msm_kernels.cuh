@@ -153,7 +153,7 @@ __global__ void k_export_points(const Affine<typename C::F>* __restrict__ in, ui
 template <class C, bool SCATTER>
 __global__ void k_digits(const uint8_t* __restrict__ scalars, int big_endian,
                          const uint8_t* __restrict__ inf_flags, MsmShape sh,
-                         uint32_t* __restrict__ counters, uint32_t* __restrict__ sorted) {
+                         uint32_t* __restrict__ counters, uint2* __restrict__ sorted) {
     const uint64_t total = (uint64_t)sh.n * sh.nbatch;
     const uint32_t half = 1u << (sh.c - 1);
     const uint32_t mask = (1u << sh.c) - 1u;
@@ -184,7 +184,7 @@ __global__ void k_digits(const uint8_t* __restrict__ scalars, int big_endian,
                     atomicAdd(counters + b, 1u);
                 } else {
                     uint32_t at = atomicAdd(counters + b, 1u);
-                    sorted[at] = pidx | (neg << 31);
+                    sorted[at] = make_uint2(b, pidx | (neg << 31));
                 }
             }
         }
@@ -277,8 +277,13 @@ k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ copy, uint32_t n,
 }
 
 // ---------------------------------------------------------------------------- accumulation
-// One thread per bucket.  `begin[b]` is the bucket's first slot in `sorted`, `end[b]` one past its
-// last (the scatter cursors after the scatter pass).  Entries are (point index | sign << 31).
+// Load-balanced segmented accumulation.  `sorted` holds the M (bucket id, point index | sign << 31)
+// pairs grouped by bucket.  Thread t owns the fixed-length slice [t*L, (t+1)*L) regardless of where
+// bucket boundaries fall, so every thread performs the same number of mixed additions whatever
+// the digit distribution (31-bit audit coefficients, the short top window, repeated scalars).
+// A bucket that lies wholly inside one slice is written straight to buckets[]; a bucket cut by a
+// slice boundary leaves a partial sum: part_head[t] (the bucket continues from slice t-1) or
+// part_tail[t] (it continues into slice t+1).  k_stitch then adds the partials of each cut bucket.
 constexpr int kAccThreads = 128;
 
 template <class C>
@@ -291,26 +296,137 @@ PORLA_D Affine<typename C::F> load_signed_point(const Affine<typename C::F>* __r
 
 template <class C>
 __global__ void __launch_bounds__(kAccThreads)
-k_accumulate(const Affine<typename C::F>* __restrict__ points, const uint32_t* __restrict__ sorted,
-             const uint32_t* __restrict__ begin, const uint32_t* __restrict__ end,
-             const uint32_t* __restrict__ order, uint32_t total_buckets,
-             XYZZ<typename C::F>* __restrict__ buckets) {
+k_accumulate(const Affine<typename C::F>* __restrict__ points, const uint2* __restrict__ sorted,
+             const uint32_t* __restrict__ total_pairs, uint32_t L,
+             XYZZ<typename C::F>* __restrict__ buckets, XYZZ<typename C::F>* __restrict__ part_head,
+             XYZZ<typename C::F>* __restrict__ part_tail) {
     using F = typename C::F;
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total_buckets) return;
-    uint32_t b = order ? order[t] : t;
-    uint32_t j = begin[b], e = end[b];
-    XYZZ<F> acc = XYZZ<F>::inf();
-    if (j < e) {
-        Affine<F> p = load_signed_point<C>(points, sorted[j]);
-        acc = XYZZ<F>{p.x, p.y, F::one(), F::one()};
-        for (++j; j < e; ++j) {
-            Affine<F> q = load_signed_point<C>(points, sorted[j]);
-            if (acc.is_inf()) acc = XYZZ<F>{q.x, q.y, F::one(), F::one()};
-            else acc.madd_finite(q);
+    const uint32_t M = *total_pairs;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t start64 = (uint64_t)t * L;
+    if (start64 >= M) return;
+    const uint32_t start = (uint32_t)start64;
+    const uint32_t end = (M - start > L) ? start + L : M;
+    const uint32_t prev_key = start > 0 ? __ldg(&sorted[start - 1].x) : 0xffffffffu;
+    const uint32_t next_key = end < M ? __ldg(&sorted[end].x) : 0xffffffffu;
+
+    uint2 e = __ldg(&sorted[start]);
+    uint32_t key = e.x;
+    bool first = true;  // still inside the first bucket of this slice
+    Affine<F> p = load_signed_point<C>(points, e.y);
+    XYZZ<F> acc{p.x, p.y, F::one(), F::one()};
+    for (uint32_t pos = start + 1; pos < end; ++pos) {
+        e = __ldg(&sorted[pos]);
+        Affine<F> q = load_signed_point<C>(points, e.y);
+        if (e.x != key) {
+            if (first && prev_key == key) st16(part_head + t, acc);
+            else st16(buckets + key, acc);
+            first = false;
+            key = e.x;
+            acc = XYZZ<F>{q.x, q.y, F::one(), F::one()};
+        } else if (acc.is_inf()) {
+            acc = XYZZ<F>{q.x, q.y, F::one(), F::one()};
+        } else {
+            acc.madd_finite(q);
         }
     }
-    st16(buckets + b, acc);
+    if (first && prev_key == key) st16(part_head + t, acc);        // continues from the left (maybe also to the right)
+    else if (next_key == key) st16(part_tail + t, acc);            // starts here, continues to the right
+    else st16(buckets + key, acc);
+}
+
+// One thread per slice boundary owner: slice t owns the cut bucket that STARTS inside it and runs on
+// into slice t+1; it adds part_tail[t] and the part_head[] of every following slice the bucket
+// covers.  Buckets longer than L * kStitchSerial pairs are finished by k_stitch_long (a block each).
+constexpr uint32_t kStitchSerial = 48;
+
+template <class C>
+__global__ void __launch_bounds__(64)
+k_stitch(const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_pairs, uint32_t L,
+         XYZZ<typename C::F>* __restrict__ buckets, const XYZZ<typename C::F>* __restrict__ part_head,
+         const XYZZ<typename C::F>* __restrict__ part_tail, uint32_t* __restrict__ long_count,
+         uint2* __restrict__ long_runs) {
+    using F = typename C::F;
+    const uint32_t M = *total_pairs;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t start64 = (uint64_t)t * L;
+    if (start64 >= M) return;
+    const uint32_t start = (uint32_t)start64;
+    if (M - start <= L) return;                       // last slice: nothing to its right
+    const uint32_t end = start + L;
+    const uint32_t key = __ldg(&sorted[end - 1].x);
+    if (__ldg(&sorted[end].x) != key) return;         // no bucket is cut at this boundary
+    if (__ldg(&sorted[start].x) == key && start > 0 && __ldg(&sorted[start - 1].x) == key) return;  // not the owner
+    // how many following slices does the bucket touch?  (binary search would also do; runs are short)
+    const uint32_t nslices = (uint32_t)(((uint64_t)M + L - 1) / L);
+    uint32_t u = t + 1, cnt = 0;
+    XYZZ<F> acc = ld16(part_tail + t);
+    for (;;) {
+        if (cnt == kStitchSerial) {                   // hand the rest to the cooperative kernel
+            st16(buckets + key, acc);
+            uint32_t slot = atomicAdd(long_count, 1u);
+            long_runs[slot] = make_uint2(key, u);
+            return;
+        }
+        acc.add(ld16(part_head + u));
+        cnt++;
+        // does slice u lie wholly inside the bucket and continue?
+        uint32_t uend = (u + 1 < nslices) ? (u + 1) * L : M;
+        if (u + 1 < nslices && __ldg(&sorted[uend - 1].x) == key && __ldg(&sorted[uend].x) == key) u++;
+        else break;
+    }
+    st16(buckets + key, acc);
+}
+
+// Cooperative tail for very long buckets (skewed inputs such as a constant scalar): block b takes
+// long_runs[b] = (bucket, first unprocessed slice u0); its threads add part_head[u0 + j], j strided,
+// then a shared-memory tree; the result is added to what k_stitch already stored.
+constexpr int kLongThreads = 128;
+
+template <class C>
+__global__ void __launch_bounds__(kLongThreads)
+k_stitch_long(const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_pairs, uint32_t L,
+              XYZZ<typename C::F>* __restrict__ buckets, const XYZZ<typename C::F>* __restrict__ part_head,
+              const uint32_t* __restrict__ long_count, const uint2* __restrict__ long_runs) {
+    using F = typename C::F;
+    __shared__ XYZZ<F> sh[kLongThreads];
+    __shared__ uint32_t s_last;
+    const uint32_t M = *total_pairs;
+    const uint32_t nruns = *long_count;
+    const uint32_t nslices = (uint32_t)(((uint64_t)M + L - 1) / L);
+    for (uint32_t r = blockIdx.x; r < nruns; r += gridDim.x) {
+        const uint32_t key = long_runs[r].x, u0 = long_runs[r].y;
+        if (threadIdx.x == 0) {
+            // last slice touched by the bucket: binary search for the last pair with this key
+            uint32_t lo = u0 * L, hi = M;  // sorted[lo].x == key (slice u0 starts inside the bucket)
+            while (hi - lo > 1) {
+                uint32_t mid = lo + (hi - lo) / 2;
+                if (__ldg(&sorted[mid].x) == key) lo = mid;
+                else hi = mid;
+            }
+            s_last = lo / L;
+        }
+        __syncthreads();
+        const uint32_t last = s_last < nslices ? s_last : nslices - 1;
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t u = u0 + threadIdx.x; u <= last; u += kLongThreads) acc.add(ld16(part_head + u));
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = kLongThreads / 2; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) {
+                XYZZ<F> a = sh[threadIdx.x];
+                a.add(sh[threadIdx.x + o]);
+                sh[threadIdx.x] = a;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            XYZZ<F> a = ld16(buckets + key);
+            a.add(sh[0]);
+            st16(buckets + key, a);
+        }
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------- bucket reduction
@@ -355,6 +471,31 @@ k_reduce(const XYZZ<typename C::F>* __restrict__ buckets, uint32_t nb, uint32_t 
         __syncthreads();
     }
     if (threadIdx.x == 0) st16(partials + (size_t)slot * gridDim.x + blockIdx.x, sh[0]);
+}
+
+// ---------------------------------------------------------------------------- window sums
+// Sums the per-block partials of one window slot with a block-wide tree (replaces a serial loop
+// in the finaliser): wsum[slot] = sum_k partials[slot*count + k].
+template <class C>
+__global__ void __launch_bounds__(kRedThreads)
+k_window_sums(const XYZZ<typename C::F>* __restrict__ partials, uint32_t count,
+              XYZZ<typename C::F>* __restrict__ wsum) {
+    using F = typename C::F;
+    __shared__ XYZZ<F> sh[kRedThreads];
+    const XYZZ<F>* p = partials + (size_t)blockIdx.x * count;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = threadIdx.x; k < count; k += kRedThreads) acc.add(ld16(p + k));
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            XYZZ<F> a = sh[threadIdx.x];
+            a.add(sh[threadIdx.x + o]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st16(wsum + blockIdx.x, sh[0]);
 }
 
 // ---------------------------------------------------------------------------- finalisation
