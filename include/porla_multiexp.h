@@ -111,6 +111,12 @@ void porla_table_destroy(porla_table* t);
 void porla_msm_device(const porla_table* t, const void* d_scalars, int64_t n, int64_t nbatch,
                       int scalar_fmt, int shared_points, int window_bits, int out_fmt, void* d_out,
                       void* d_out_xyzz, void* cuda_stream);
+/* One MSM over table[0..n) with device-resident scalars and the 64-byte result delivered to HOST
+ * memory (synchronous).  The data-parallel stages run on the GPU; the serial tail -- Horner over
+ * the <= 64 per-window sums and the affine normalisation -- runs on the calling host thread
+ * (set PORLA_DEVICE_FINALIZE=1 to keep it on the device). */
+void porla_msm_resident(const porla_table* t, const void* d_scalars, int64_t n, int scalar_fmt,
+                        int window_bits, int out_fmt, void* h_out64, void* cuda_stream);
 /* Multi-GPU combine: parts[k*nbatch + m] (k < count) are XYZZ partials gathered from the ranks. */
 void porla_msm_combine_device(int curve, const void* d_parts, int64_t count, int64_t nbatch,
                               int out_fmt, void* d_out, void* cuda_stream);

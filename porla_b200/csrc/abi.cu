@@ -89,6 +89,38 @@ std::vector<Fr> read_poly(const GoSlice* data_in, int64_t n) {
     return f;
 }
 
+// Runs nbatch MSMs and brings the nbatch*64-byte results to host memory.  Few MSMs: the device
+// stops at the per-window sums and the serial tail (Horner + normalisation) runs on the host, which
+// is ~15x faster than one GPU thread; many MSMs: the device finaliser runs them in parallel.
+// d_scratch_out must hold max(nbatch*64, nbatch*nwin*128) bytes.  Caller holds g_io_mu.
+constexpr int64_t kHostFinalizeMaxBatch = 4;
+size_t result_scratch_bytes(int curve, int64_t n, int64_t nbatch) {
+    MsmPlan p = msm_plan(curve, (uint32_t)n, (uint32_t)nbatch, 0);
+    size_t a = (size_t)nbatch * 64, b = (size_t)nbatch * p.nwin * 128;
+    return a > b ? a : b;
+}
+void run_and_fetch(int curve, const PointTable& tab, const uint8_t* d_scalars, int64_t n, int64_t nbatch, MsmOptions opt,
+                   uint8_t* d_scratch_out, uint8_t* out, cudaStream_t st) {
+    const char* force_dev = getenv("PORLA_DEVICE_FINALIZE");
+    if (nbatch <= kHostFinalizeMaxBatch && !(force_dev && force_dev[0] == '1')) {
+        MsmPlan p = msm_plan(curve, (uint32_t)n, (uint32_t)nbatch, opt.window_bits);
+        opt.window_bits = p.c;
+        opt.d_window_sums = d_scratch_out;
+        size_t bytes = (size_t)nbatch * p.nwin * 128;
+        msm_device(curve, tab, d_scalars, (uint32_t)n, (uint32_t)nbatch, opt, nullptr, nullptr, st);
+        uint8_t* h = g_stage.pinned(bytes);
+        PORLA_CUDA(cudaMemcpyAsync(h, d_scratch_out, bytes, cudaMemcpyDeviceToHost, st));
+        PORLA_CUDA(cudaStreamSynchronize(st));
+        for (int64_t m = 0; m < nbatch; m++) finalize_host(curve, h + (size_t)m * p.nwin * 128, p.nwin, p.c, opt.out_fmt, out + 64 * m);
+        return;
+    }
+    msm_device(curve, tab, d_scalars, (uint32_t)n, (uint32_t)nbatch, opt, d_scratch_out, nullptr, st);
+    uint8_t* h = g_stage.pinned((size_t)nbatch * 64);
+    PORLA_CUDA(cudaMemcpyAsync(h, d_scratch_out, (size_t)nbatch * 64, cudaMemcpyDeviceToHost, st));
+    PORLA_CUDA(cudaStreamSynchronize(st));
+    memcpy(out, h, (size_t)nbatch * 64);
+}
+
 // Host-buffer MSM core.  Scalars/points are copied to the device, points imported, nbatch MSMs
 // run, results copied back.  Rare compressed-flag BN254 inputs are expanded on the host first.
 void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int64_t n, int64_t nbatch,
@@ -116,7 +148,7 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
     }
     size_t sc_bytes = total * 32, pt_bytes = total * 64;
     size_t sc_off = 0, pt_off = (sc_bytes + 255) & ~(size_t)255, out_off = pt_off + ((pt_bytes + 255) & ~(size_t)255);
-    uint8_t* d = g_stage.dev(out_off + (size_t)nbatch * 64);
+    uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(curve, n, nbatch));
     cudaStream_t st = g_stage.stream;
     PORLA_CUDA(cudaMemcpyAsync(d + sc_off, scalars, sc_bytes, cudaMemcpyHostToDevice, st));
     PORLA_CUDA(cudaMemcpyAsync(d + pt_off, points, pt_bytes, cudaMemcpyHostToDevice, st));
@@ -126,11 +158,7 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.out_fmt = point_fmt;
     opt.shared_points = 0;
-    msm_device(curve, tab, d + sc_off, (uint32_t)n, (uint32_t)nbatch, opt, d + out_off, nullptr, st);
-    uint8_t* h = g_stage.pinned((size_t)nbatch * 64);
-    PORLA_CUDA(cudaMemcpyAsync(h, d + out_off, (size_t)nbatch * 64, cudaMemcpyDeviceToHost, st));
-    PORLA_CUDA(cudaStreamSynchronize(st));
-    memcpy(out, h, (size_t)nbatch * 64);
+    run_and_fetch(curve, tab, d + sc_off, n, nbatch, opt, d + out_off, out, st);
     table_free(&tab);
 }
 
@@ -147,18 +175,14 @@ void srs_commit_core(const uint8_t* coeffs_be, int64_t n, int64_t nbatch, uint8_
     std::lock_guard<std::mutex> lock(g_io_mu);
     size_t sc_bytes = (size_t)n * nbatch * 32;
     size_t out_off = (sc_bytes + 255) & ~(size_t)255;
-    uint8_t* d = g_stage.dev(out_off + (size_t)nbatch * 64);
+    uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(kCurveBn254, n, nbatch));
     cudaStream_t st = g_stage.stream;
     PORLA_CUDA(cudaMemcpyAsync(d, coeffs_be, sc_bytes, cudaMemcpyHostToDevice, st));
     MsmOptions opt;
     opt.scalar_be = 1;
     opt.out_fmt = PORLA_POINT_BE64;
     opt.shared_points = 1;
-    msm_device(kCurveBn254, g_kzg.srs_table, d, (uint32_t)n, (uint32_t)nbatch, opt, d + out_off, nullptr, st);
-    uint8_t* h = g_stage.pinned((size_t)nbatch * 64);
-    PORLA_CUDA(cudaMemcpyAsync(h, d + out_off, (size_t)nbatch * 64, cudaMemcpyDeviceToHost, st));
-    PORLA_CUDA(cudaStreamSynchronize(st));
-    memcpy(out, h, (size_t)nbatch * 64);
+    run_and_fetch(kCurveBn254, g_kzg.srs_table, d, n, nbatch, opt, d + out_off, out, st);
 }
 
 // SRS bases go to HBM once, at init when a device is present (otherwise on the first commit,
@@ -465,6 +489,25 @@ void porla_msm_device(const porla_table* t, const void* d_scalars, int64_t n, in
     opt.shared_points = shared_points;
     msm_device(t->t.curve, t->t, (const uint8_t*)d_scalars, (uint32_t)n, (uint32_t)nbatch, opt, (uint8_t*)d_out, d_out_xyzz,
                (cudaStream_t)cuda_stream);
+}
+
+void porla_msm_resident(const porla_table* t, const void* d_scalars, int64_t n, int scalar_fmt, int window_bits, int out_fmt,
+                        void* h_out64, void* cuda_stream) {
+    if (n > (int64_t)t->t.n) die("porla_msm_resident: table shorter than the MSM");
+    if (n <= 0) {
+        memset(h_out64, 0, 64);
+        return;
+    }
+    std::lock_guard<std::mutex> lock(g_io_mu);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    MsmOptions opt;
+    opt.window_bits = window_bits;
+    opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
+    opt.out_fmt = out_fmt;
+    opt.shared_points = 1;
+    static uint8_t* d_ws = nullptr;  // 64 windows x 128 B is the most any plan needs... sized generously
+    if (!d_ws) PORLA_CUDA(cudaMalloc(&d_ws, 128 * 128));
+    run_and_fetch(t->t.curve, t->t, (const uint8_t*)d_scalars, n, 1, opt, d_ws, (uint8_t*)h_out64, st);
 }
 
 void porla_msm_combine_device(int curve, const void* d_parts, int64_t count, int64_t nbatch, int out_fmt, void* d_out,

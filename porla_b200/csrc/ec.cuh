@@ -152,9 +152,12 @@ PORLA_HD XYZZ<F> mul_small(const XYZZ<F>& p, uint32_t k) {
 // Curve tags ------------------------------------------------------------------------------
 using Bn254Fp = Fp<Bn254FpParams>;
 using SecpFp = Fp<Secp256k1FpParams>;
+using Bn254FpCompact = Fp<Bn254FpParams, true>;
+using SecpFpCompact = Fp<Secp256k1FpParams, true>;
 
 struct Bn254 {
     using F = Bn254Fp;
+    using FC = Bn254FpCompact;  // same layout, non-inlined multiplier (cold kernels)
     static constexpr int kScalarBits = 254;
     // r (scalar field order), little-endian 32-bit limbs
     PORLA_HD static constexpr uint32_t order(int i) {
@@ -167,6 +170,7 @@ struct Bn254 {
 
 struct Secp256k1 {
     using F = SecpFp;
+    using FC = SecpFpCompact;
     static constexpr int kScalarBits = 256;
     PORLA_HD static constexpr uint32_t order(int i) {
         constexpr uint32_t m[8] = {0xd0364141u, 0xbfd25e8cu, 0xaf48a03bu, 0xbaaedce6u,

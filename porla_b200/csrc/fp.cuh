@@ -151,7 +151,18 @@ PORLA_HD uint32_t sub256(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 // ------------------------------------------------------------------------------------------
 // Field element
 // ------------------------------------------------------------------------------------------
+// kCompact = true routes every device-side product through ONE non-inlined copy of the multiplier
+// (8 + 8 registers in, 8 out).  The bucket-accumulation kernel wants everything inlined; the cold
+// kernels (bucket reduction, stitching, window combine) inline a dozen XYZZ additions and become
+// instruction-fetch bound (ncu: stall_no_instruction dominates) unless the code is kept small.
+template <class P, bool kCompact>
+struct Fp;
+#ifdef __CUDACC__
 template <class P>
+__device__ __noinline__ Fp<P, true> fp_mul_outlined(Fp<P, true> a, Fp<P, true> b);
+#endif
+
+template <class P, bool kCompact = false>
 struct alignas(16) Fp {
     uint32_t v[8];
     using Params = P;
@@ -438,7 +449,7 @@ struct alignas(16) Fp {
     PORLA_HD friend Fp operator*(const Fp& a, const Fp& b) { return mul(a, b); }
     PORLA_HD Fp sqr() const { return mul(*this, *this); }
 
-    PORLA_HD static Fp mul(const Fp& a, const Fp& b) {
+    PORLA_HD static Fp mul_inlined(const Fp& a, const Fp& b) {
         if (P::kMontgomery) {
 #ifdef __CUDA_ARCH__
             return mul_mont_device(a, b);
@@ -448,6 +459,12 @@ struct alignas(16) Fp {
         } else {
             return mul_special_portable(a, b);
         }
+    }
+    PORLA_HD static Fp mul(const Fp& a, const Fp& b) {
+#ifdef __CUDA_ARCH__
+        if constexpr (kCompact) return fp_mul_outlined<P>(a, b);
+#endif
+        return mul_inlined(a, b);
     }
 
     // to/from the internal representation (Montgomery for BN254, identity for secp256k1)
@@ -479,5 +496,12 @@ struct alignas(16) Fp {
         return r;
     }
 };
+
+#ifdef __CUDACC__
+template <class P>
+__device__ __noinline__ Fp<P, true> fp_mul_outlined(Fp<P, true> a, Fp<P, true> b) {
+    return Fp<P, true>::mul_inlined(a, b);
+}
+#endif
 
 }  // namespace porla

@@ -6,9 +6,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <cstring>
 
 #include "arena.h"
 #include "ec.cuh"
+#include "host_fp64.hpp"
 
 namespace porla {
 
@@ -107,6 +109,43 @@ int choose_window(int curve, uint32_t n, uint32_t nbatch) {
         }
     }
     return best_c;
+}
+
+MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits) {
+    MsmPlan p;
+    p.c = window_bits > 0 ? window_bits : choose_window(curve, n, nbatch);
+    p.nwin = (scalar_bits(curve) + 1 + p.c - 1) / p.c;
+    return p;
+}
+
+// ---------------------------------------------------------------------------- host finaliser
+template <class F64>
+static void finalize_host_impl(const void* h_window_sums, int nwin, int c, int out_fmt, uint8_t* out64) {
+    static_assert(sizeof(XYZZ<F64>) == 128, "device and host XYZZ layouts must coincide");
+    const XYZZ<F64>* ws = reinterpret_cast<const XYZZ<F64>*>(h_window_sums);
+    XYZZ<F64> r = XYZZ<F64>::inf();
+    for (int w = nwin - 1; w >= 0; w--) {
+        if (!r.is_inf())
+            for (int k = 0; k < c; k++) r = r.dbl();
+        XYZZ<F64> s;
+        memcpy(&s, ws + w, sizeof(s));
+        r.add(s);
+    }
+    Affine<F64> a = r.to_affine();
+    F64 xy[2] = {a.x.from_internal(), a.y.from_internal()};
+    for (int k = 0; k < 2; k++) {
+        if (out_fmt == 0) {  // big-endian
+            for (int i = 0; i < 4; i++)
+                for (int j = 0; j < 8; j++) out64[32 * k + 8 * (3 - i) + j] = (uint8_t)(xy[k].v[i] >> (8 * (7 - j)));
+        } else {
+            memcpy(out64 + 32 * k, xy[k].v, 32);
+        }
+    }
+}
+
+void finalize_host(int curve, const void* h_window_sums, int nwin, int c, int out_fmt, uint8_t* out64) {
+    if (curve == kCurveBn254) finalize_host_impl<host::Fp64<host::Bn254Fq64Params>>(h_window_sums, nwin, c, out_fmt, out64);
+    else finalize_host_impl<host::Fp64<host::SecpFq64Params>>(h_window_sums, nwin, c, out_fmt, out64);
 }
 
 // ---------------------------------------------------------------------------- dispatchers

@@ -43,7 +43,20 @@ struct MsmOptions {
     int scalar_be = 1;        // 1: 32-byte big-endian scalars, 0: 8 LE 32-bit limbs
     int out_fmt = 0;          // PointFormat of the serialised result
     int shared_points = 1;    // batch: all MSMs over the same table prefix
+    // When set, receives the nbatch*nwin per-window sums (XYZZ, 128 B each, window-major per MSM)
+    // and the device finaliser is skipped: the caller combines them with finalize_host().
+    void* d_window_sums = nullptr;
 };
+
+struct MsmPlan {
+    int c;      // window bits
+    int nwin;   // windows per scalar
+};
+MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits);
+
+// Host-side tail of one MSM: Horner over the window sums (c doublings per window), affine
+// normalisation, serialisation.  h_window_sums: nwin XYZZ records as produced on the device.
+void finalize_host(int curve, const void* h_window_sums, int nwin, int c, int out_fmt, uint8_t* out64);
 
 // nbatch MSMs of n terms each.  d_scalars: nbatch*n*32 bytes on the device.
 // d_out (nullable): nbatch*64 bytes, canonical affine.  d_out_xyzz (nullable): nbatch*128 bytes,

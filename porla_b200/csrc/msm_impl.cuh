@@ -82,8 +82,10 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     const uint32_t ntiles = (nbt + kScanTile - 1) / kScanTile;
 
     // reduction geometry: enough threads to fill the machine, chunks as long as that allows
+    // (each thread pays a fixed ~20-operation weighting step, so chunks below 16 buckets waste work)
     uint32_t chunk = 64;
-    while (chunk > 4 && (uint64_t)nbt / chunk < 148ull * 512ull) chunk >>= 1;
+    while (chunk > 16 && (uint64_t)nbt / chunk < 148ull * 256ull) chunk >>= 1;
+    while (chunk > 4 && sh.nbuckets / chunk < 4) chunk >>= 1;
     uint32_t threads_per_slot = (sh.nbuckets + chunk - 1) / chunk;
     uint32_t blocks_per_slot = (threads_per_slot + kRedThreads - 1) / kRedThreads;
 
@@ -115,6 +117,10 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     XYZZ<F>* wsum = g_arena.take<XYZZ<F>>(slots);
 
     const Affine<F>* points = reinterpret_cast<const Affine<F>*>(table.d_points);
+    // the cold kernels see the same records through the compact (outlined-multiply) field type
+    using FC = typename C::FC;
+    using XC = XYZZ<FC>;
+    static_assert(sizeof(XC) == sizeof(XYZZ<F>), "layouts must coincide");
     const uint64_t total_scalars = (uint64_t)n * nbatch;
 
     g_stage_timer.mark(kStageCount, stream);
@@ -141,10 +147,11 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         k_accumulate<C><<<(nslices_cap + kAccThreads - 1) / kAccThreads, kAccThreads, 0, stream>>>(
             points, sorted, grand, L, buckets, part_head, part_tail);
         LAUNCHED();
-        k_stitch<C><<<(nslices_cap + 63) / 64, 64, 0, stream>>>(sorted, grand, L, buckets, part_head, part_tail, long_count,
-                                                               long_runs);
+        k_stitch<C><<<(nslices_cap + 63) / 64, 64, 0, stream>>>(sorted, grand, L, (XC*)buckets, (const XC*)part_head,
+                                                               (const XC*)part_tail, long_count, long_runs);
         LAUNCHED();
-        k_stitch_long<C><<<148, kLongThreads, 0, stream>>>(sorted, grand, L, buckets, part_head, long_count, long_runs);
+        k_stitch_long<C><<<148, kLongThreads, 0, stream>>>(sorted, grand, L, (XC*)buckets, (const XC*)part_head, long_count,
+                                                          long_runs);
         LAUNCHED();
     } else {
         g_stage_timer.mark(kStageScan, stream);
@@ -153,25 +160,29 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     }
     g_stage_timer.mark(kStageReduce, stream);
     dim3 rgrid(blocks_per_slot, (uint32_t)slots);
-    k_reduce<C><<<rgrid, kRedThreads, 0, stream>>>(buckets, sh.nbuckets, chunk, threads_per_slot, partials);
+    k_reduce<C><<<rgrid, kRedThreads, 0, stream>>>((const XC*)buckets, sh.nbuckets, chunk, threads_per_slot, (XC*)partials);
     LAUNCHED();
     const XYZZ<F>* window_sums = partials;
     if (blocks_per_slot > 1) {
-        k_window_sums<C><<<(uint32_t)slots, kRedThreads, 0, stream>>>(partials, blocks_per_slot, wsum);
+        k_window_sums<C><<<(uint32_t)slots, kRedThreads, 0, stream>>>((const XC*)partials, blocks_per_slot, (XC*)wsum);
         LAUNCHED();
         window_sums = wsum;
     }
     g_stage_timer.mark(kStageFinalize, stream);
-    k_finalize<C><<<nbatch, 64, sh.nwin * sizeof(XYZZ<F>), stream>>>(
-        window_sums, 1, sh.nwin, sh.c, opt.out_fmt, d_out, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
-    LAUNCHED();
+    if (opt.d_window_sums) {
+        PORLA_CUDA(cudaMemcpyAsync(opt.d_window_sums, window_sums, slots * sizeof(XYZZ<F>), cudaMemcpyDeviceToDevice, stream));
+    } else {
+        k_finalize<C><<<nbatch, 64, sh.nwin * sizeof(XYZZ<F>), stream>>>(
+            (const XC*)window_sums, 1, sh.nwin, sh.c, opt.out_fmt, d_out, reinterpret_cast<XC*>(d_out_xyzz));
+        LAUNCHED();
+    }
     g_stage_timer.mark(kNumStages, stream);
     PORLA_CUDA(cudaGetLastError());
 }
 
 template <class C>
 void combine_impl(const void* d_parts, uint32_t count, uint32_t nbatch, int out_fmt, uint8_t* d_out, cudaStream_t stream) {
-    using F = typename C::F;
+    using F = typename C::FC;
     k_combine<C><<<(nbatch + 63) / 64, 64, 0, stream>>>(reinterpret_cast<const XYZZ<F>*>(d_parts), count, nbatch, out_fmt, d_out);
     LAUNCHED();
     PORLA_CUDA(cudaGetLastError());
@@ -180,7 +191,7 @@ void combine_impl(const void* d_parts, uint32_t count, uint32_t nbatch, int out_
 template <class C>
 void scalar_mul_impl(const PointTable& table, const uint8_t* d_scalars, int scalar_be, uint32_t n, void* d_out_affine,
                      cudaStream_t stream) {
-    using F = typename C::F;
+    using F = typename C::FC;
     k_scalar_mul<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<F>*>(table.d_points), table.n, d_scalars,
                                                         scalar_be, n, reinterpret_cast<Affine<F>*>(d_out_affine));
     LAUNCHED();

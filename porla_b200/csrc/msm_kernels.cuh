@@ -151,12 +151,14 @@ __global__ void k_export_points(const Affine<typename C::F>* __restrict__ in, ui
 // Signed c-bit digits: d_w in [-2^(c-1), 2^(c-1)], bucket id |d_w| - 1; nwin*c > bits of the
 // order, so the top digit never overflows.
 template <class C, bool SCATTER>
-__global__ void k_digits(const uint8_t* __restrict__ scalars, int big_endian,
-                         const uint8_t* __restrict__ inf_flags, MsmShape sh,
-                         uint32_t* __restrict__ counters, uint2* __restrict__ sorted) {
+__global__ void __launch_bounds__(256)
+k_digits(const uint8_t* __restrict__ scalars, int big_endian,
+         const uint8_t* __restrict__ inf_flags, MsmShape sh,
+         uint32_t* __restrict__ counters, uint2* __restrict__ sorted) {
     const uint64_t total = (uint64_t)sh.n * sh.nbatch;
     const uint32_t half = 1u << (sh.c - 1);
     const uint32_t mask = (1u << sh.c) - 1u;
+    constexpr int kBatch = 8;  // independent atomics kept in flight per thread
     for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t m = (uint32_t)(idx / sh.n);
@@ -168,24 +170,41 @@ __global__ void k_digits(const uint8_t* __restrict__ scalars, int big_endian,
         s[8] = 0;
         reduce_scalar<C>(s);
         uint32_t carry = 0;
-        uint32_t slot_base = m * (uint32_t)sh.nwin * sh.nbuckets;
-        for (int w = 0; w < sh.nwin; w++) {
-            uint32_t pos = (uint32_t)w * sh.c;
-            uint32_t word = pos >> 5, sft = pos & 31;
-            uint32_t lo = word < 8 ? s[word] : 0u;
-            uint32_t hi = word < 7 ? s[word + 1] : 0u;
-            uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry;
-            uint32_t neg = d > half;
-            carry = neg;
-            uint32_t mag = neg ? ((1u << sh.c) - d) : d;
-            if (mag != 0) {
-                uint32_t b = slot_base + (uint32_t)w * sh.nbuckets + (mag - 1);
-                if (!SCATTER) {
-                    atomicAdd(counters + b, 1u);
-                } else {
-                    uint32_t at = atomicAdd(counters + b, 1u);
-                    sorted[at] = make_uint2(b, pidx | (neg << 31));
+        const uint32_t slot_base = m * (uint32_t)sh.nwin * sh.nbuckets;
+        for (int w0 = 0; w0 < sh.nwin; w0 += kBatch) {
+            uint32_t bucket[kBatch], val[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; k++) {
+                int w = w0 + k;
+                bucket[k] = 0xffffffffu;
+                val[k] = 0;
+                if (w < sh.nwin) {
+                    uint32_t pos = (uint32_t)w * sh.c;
+                    uint32_t word = pos >> 5, sft = pos & 31;
+                    uint32_t lo = s[word < 8 ? word : 8];
+                    uint32_t hi = s[word < 7 ? word + 1 : 8];
+                    uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry;
+                    uint32_t neg = d > half;
+                    carry = neg;
+                    uint32_t mag = neg ? ((1u << sh.c) - d) : d;
+                    if (mag != 0) {
+                        bucket[k] = slot_base + (uint32_t)w * sh.nbuckets + (mag - 1);
+                        val[k] = pidx | (neg << 31);
+                    }
                 }
+            }
+            if (!SCATTER) {
+#pragma unroll
+                for (int k = 0; k < kBatch; k++)
+                    if (bucket[k] != 0xffffffffu) atomicAdd(counters + bucket[k], 1u);
+            } else {
+                uint32_t at[kBatch];
+#pragma unroll
+                for (int k = 0; k < kBatch; k++)
+                    at[k] = bucket[k] != 0xffffffffu ? atomicAdd(counters + bucket[k], 1u) : 0u;
+#pragma unroll
+                for (int k = 0; k < kBatch; k++)
+                    if (bucket[k] != 0xffffffffu) sorted[at[k]] = make_uint2(bucket[k], val[k]);
             }
         }
     }
@@ -343,10 +362,10 @@ constexpr uint32_t kStitchSerial = 48;
 template <class C>
 __global__ void __launch_bounds__(64)
 k_stitch(const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_pairs, uint32_t L,
-         XYZZ<typename C::F>* __restrict__ buckets, const XYZZ<typename C::F>* __restrict__ part_head,
-         const XYZZ<typename C::F>* __restrict__ part_tail, uint32_t* __restrict__ long_count,
+         XYZZ<typename C::FC>* __restrict__ buckets, const XYZZ<typename C::FC>* __restrict__ part_head,
+         const XYZZ<typename C::FC>* __restrict__ part_tail, uint32_t* __restrict__ long_count,
          uint2* __restrict__ long_runs) {
-    using F = typename C::F;
+    using F = typename C::FC;
     const uint32_t M = *total_pairs;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t start64 = (uint64_t)t * L;
@@ -386,9 +405,9 @@ constexpr int kLongThreads = 128;
 template <class C>
 __global__ void __launch_bounds__(kLongThreads)
 k_stitch_long(const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_pairs, uint32_t L,
-              XYZZ<typename C::F>* __restrict__ buckets, const XYZZ<typename C::F>* __restrict__ part_head,
+              XYZZ<typename C::FC>* __restrict__ buckets, const XYZZ<typename C::FC>* __restrict__ part_head,
               const uint32_t* __restrict__ long_count, const uint2* __restrict__ long_runs) {
-    using F = typename C::F;
+    using F = typename C::FC;
     __shared__ XYZZ<F> sh[kLongThreads];
     __shared__ uint32_t s_last;
     const uint32_t M = *total_pairs;
@@ -438,9 +457,9 @@ constexpr int kRedThreads = 64;
 
 template <class C>
 __global__ void __launch_bounds__(kRedThreads)
-k_reduce(const XYZZ<typename C::F>* __restrict__ buckets, uint32_t nb, uint32_t chunk,
-         uint32_t threads_per_slot, XYZZ<typename C::F>* __restrict__ partials) {
-    using F = typename C::F;
+k_reduce(const XYZZ<typename C::FC>* __restrict__ buckets, uint32_t nb, uint32_t chunk,
+         uint32_t threads_per_slot, XYZZ<typename C::FC>* __restrict__ partials) {
+    using F = typename C::FC;
     __shared__ XYZZ<F> sh[kRedThreads];
     const uint32_t slot = blockIdx.y;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -478,9 +497,9 @@ k_reduce(const XYZZ<typename C::F>* __restrict__ buckets, uint32_t nb, uint32_t 
 // in the finaliser): wsum[slot] = sum_k partials[slot*count + k].
 template <class C>
 __global__ void __launch_bounds__(kRedThreads)
-k_window_sums(const XYZZ<typename C::F>* __restrict__ partials, uint32_t count,
-              XYZZ<typename C::F>* __restrict__ wsum) {
-    using F = typename C::F;
+k_window_sums(const XYZZ<typename C::FC>* __restrict__ partials, uint32_t count,
+              XYZZ<typename C::FC>* __restrict__ wsum) {
+    using F = typename C::FC;
     __shared__ XYZZ<F> sh[kRedThreads];
     const XYZZ<F>* p = partials + (size_t)blockIdx.x * count;
     XYZZ<F> acc = XYZZ<F>::inf();
@@ -505,10 +524,10 @@ k_window_sums(const XYZZ<typename C::F>* __restrict__ partials, uint32_t count,
 // (canonical, not Montgomery); out_xyzz (optional) receives the un-normalised sum for multi-GPU
 // combination.
 template <class C>
-__global__ void k_finalize(const XYZZ<typename C::F>* __restrict__ partials, uint32_t blocks_per_slot,
+__global__ void k_finalize(const XYZZ<typename C::FC>* __restrict__ partials, uint32_t blocks_per_slot,
                            int nwin, int c, int out_fmt, uint8_t* __restrict__ out,
-                           XYZZ<typename C::F>* __restrict__ out_xyzz) {
-    using F = typename C::F;
+                           XYZZ<typename C::FC>* __restrict__ out_xyzz) {
+    using F = typename C::FC;
     extern __shared__ uint4 sh_raw[];
     XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(sh_raw);
     const uint32_t m = blockIdx.x;
@@ -537,9 +556,9 @@ __global__ void k_finalize(const XYZZ<typename C::F>* __restrict__ partials, uin
 
 // Sum `count` XYZZ partial results per MSM (multi-GPU combine) and serialise.
 template <class C>
-__global__ void k_combine(const XYZZ<typename C::F>* __restrict__ parts, uint32_t count,
+__global__ void k_combine(const XYZZ<typename C::FC>* __restrict__ parts, uint32_t count,
                           uint32_t nbatch, int out_fmt, uint8_t* __restrict__ out) {
-    using F = typename C::F;
+    using F = typename C::FC;
     uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nbatch) return;
     XYZZ<F> r = XYZZ<F>::inf();
@@ -556,10 +575,10 @@ __global__ void k_combine(const XYZZ<typename C::F>* __restrict__ parts, uint32_
 // out[i] = k_i * P_i, scalars 32-byte records, plain double-and-add.
 template <class C>
 __global__ void __launch_bounds__(128)
-k_scalar_mul(const Affine<typename C::F>* __restrict__ points, uint32_t npoints,
+k_scalar_mul(const Affine<typename C::FC>* __restrict__ points, uint32_t npoints,
              const uint8_t* __restrict__ scalars, int big_endian, uint32_t n,
-             Affine<typename C::F>* __restrict__ out) {
-    using F = typename C::F;
+             Affine<typename C::FC>* __restrict__ out) {
+    using F = typename C::FC;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -580,10 +599,10 @@ k_scalar_mul(const Affine<typename C::F>* __restrict__ points, uint32_t npoints,
 
 // out[i] = a[i] + b[i]
 template <class C>
-__global__ void k_point_add(const Affine<typename C::F>* __restrict__ a,
-                            const Affine<typename C::F>* __restrict__ b, uint32_t n,
-                            Affine<typename C::F>* __restrict__ out) {
-    using F = typename C::F;
+__global__ void k_point_add(const Affine<typename C::FC>* __restrict__ a,
+                            const Affine<typename C::FC>* __restrict__ b, uint32_t n,
+                            Affine<typename C::FC>* __restrict__ out) {
+    using F = typename C::FC;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     XYZZ<F> r = XYZZ<F>::from_affine(ld16(a + i));

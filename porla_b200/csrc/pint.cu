@@ -3,7 +3,10 @@
 // every SM busy, timed with CUDA events.  Three instruction mixes:
 //   0  mad.wide.u32, 8 independent 64-bit accumulators/thread        (IMAD.WIDE.U32)
 //   1  mad.lo.cc / madc.hi.cc carry chains, the mix the field code uses (IMAD.WIDE.U32.X + carry preds)
-//   2  mad.lo.u32 (plain 32-bit IMAD), for comparison
+//   2  mad.lo.u32 (plain 32-bit IMAD, a 32x32->32 multiply-add), for comparison only
+// Measured on B200: variants 0/1 ~ 9.2e12 /s (32 lanes/clk/SM: IMAD.WIDE issues at half the rate of
+// the 32-bit IMAD), variant 2 ~ 1.84e13 /s (64 lanes/clk/SM).  The roofline unit "MAC32" is a full
+// 32x32->64 multiply-accumulate, i.e. variant 1.
 #include <cstdio>
 
 #include "../../include/porla_multiexp.h"
@@ -106,7 +109,9 @@ extern "C" double porla_measure_pint(int variant, double min_seconds) {
     };
     launch(3);
     PORLA_CUDA(cudaDeviceSynchronize());
-    double macs_per_launch = (double)blocks * threads * (double)kIters * 8.0;
+    // per thread: variants 0 and 2 issue 8 multiply-adds per iteration for kIters iterations;
+    // variant 1 issues 2 rows x 4 wide products per iteration for kIters/2 iterations
+    double macs_per_launch = (double)blocks * threads * (double)kIters * (variant == 1 ? 4.0 : 8.0);
     int reps = 8;
     double best = 0;
     for (int round = 0; round < 6; round++) {

@@ -26,7 +26,7 @@ NEW_SYMBOLS = [
     "porla_device_init", "porla_launch_count", "compute_multi_exp_batch",
     "compute_digest_from_srs_batch", "porla_table_create", "porla_table_create_multiples",
     "porla_table_len", "porla_table_num_infinity", "porla_table_export", "porla_table_destroy",
-    "porla_msm_device", "porla_msm_combine_device", "porla_msm_host", "porla_choose_window",
+    "porla_msm_device", "porla_msm_resident", "porla_msm_combine_device", "porla_msm_host", "porla_choose_window",
     "porla_scalar_mul_batch_device", "porla_secp256k1_ecmult_multi_var",
     "porla_secp256k1_gej_serialize", "porla_debug_field_mul", "porla_debug_point_add_host", "porla_measure_pint",
     "porla_stage_timing_enable", "porla_stage_timing_read",
@@ -97,6 +97,7 @@ def load() -> C.CDLL:
         "porla_table_export": (None, [P, I, P, I, P]),
         "porla_table_destroy": (None, [P]),
         "porla_msm_device": (None, [P, P, C.c_int64, C.c_int64, I, I, I, I, P, P, P]),
+        "porla_msm_resident": (None, [P, P, C.c_int64, I, I, I, P, P]),
         "porla_msm_combine_device": (None, [I, P, C.c_int64, C.c_int64, I, P, P]),
         "porla_msm_host": (None, [I, P, P, C.c_int64, C.c_int64, I, I, P]),
         "porla_choose_window": (I, [I, C.c_int64, C.c_int64]),
@@ -279,6 +280,14 @@ class Table:
         load().porla_msm_device(C.c_void_p(self.handle), C.c_void_p(d_scalars), n, nbatch, scalar_fmt, int(shared_points),
                                 window_bits, out_fmt, C.c_void_p(d_out) if d_out else None,
                                 C.c_void_p(d_out_xyzz) if d_out_xyzz else None, C.c_void_p(stream))
+
+    def msm_resident(self, d_scalars: int, n: int, scalar_fmt: int = SCALAR_BE32, window_bits: int = 0,
+                     out_fmt: int = POINT_BE64, stream: int = 0) -> bytes:
+        """Synchronous MSM with device-resident scalars; the 64-byte result comes back to the host."""
+        out = (C.c_ubyte * 64)()
+        load().porla_msm_resident(C.c_void_p(self.handle), C.c_void_p(d_scalars), n, scalar_fmt, window_bits, out_fmt,
+                                  C.cast(out, C.c_void_p), C.c_void_p(stream))
+        return bytes(out)
 
     def destroy(self) -> None:
         if self.handle:
