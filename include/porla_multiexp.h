@@ -117,6 +117,15 @@ void porla_msm_device(const porla_table* t, const void* d_scalars, int64_t n, in
  * (set PORLA_DEVICE_FINALIZE=1 to keep it on the device). */
 void porla_msm_resident(const porla_table* t, const void* d_scalars, int64_t n, int scalar_fmt,
                         int window_bits, int out_fmt, void* h_out64, void* cuda_stream);
+/* Building blocks of a range-sharded MSM (one process per GPU): every rank runs
+ * the pipeline over its point range up to the per-window sums (nwin XYZZ records of 128 B, about
+ * 2 KiB), the ranks all-gather them, and one host combines: add the parts window by window, Horner
+ * over the windows, normalise.  All ranks must use the same window size (porla_msm_plan). */
+void porla_msm_plan(int curve, int64_t n, int64_t nbatch, int window_bits, int* c_out, int* nwin_out);
+void porla_msm_window_sums_device(const porla_table* t, const void* d_scalars, int64_t n, int scalar_fmt,
+                                  int window_bits, void* d_window_sums, void* cuda_stream);
+void porla_msm_finalize_host(int curve, const void* h_window_sums, int64_t nparts, int nwin, int c,
+                             int out_fmt, void* out64);
 /* Multi-GPU combine: parts[k*nbatch + m] (k < count) are XYZZ partials gathered from the ranks. */
 void porla_msm_combine_device(int curve, const void* d_parts, int64_t count, int64_t nbatch,
                               int out_fmt, void* d_out, void* cuda_stream);

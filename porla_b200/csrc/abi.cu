@@ -510,6 +510,27 @@ void porla_msm_resident(const porla_table* t, const void* d_scalars, int64_t n, 
     run_and_fetch(t->t.curve, t->t, (const uint8_t*)d_scalars, n, 1, opt, d_ws, (uint8_t*)h_out64, st);
 }
 
+void porla_msm_plan(int curve, int64_t n, int64_t nbatch, int window_bits, int* c_out, int* nwin_out) {
+    MsmPlan p = msm_plan(curve, (uint32_t)n, (uint32_t)nbatch, window_bits);
+    *c_out = p.c;
+    *nwin_out = p.nwin;
+}
+
+void porla_msm_window_sums_device(const porla_table* t, const void* d_scalars, int64_t n, int scalar_fmt, int window_bits,
+                                  void* d_window_sums, void* cuda_stream) {
+    if (n > (int64_t)t->t.n) die("porla_msm_window_sums_device: table shorter than the MSM");
+    MsmOptions opt;
+    opt.window_bits = msm_plan(t->t.curve, (uint32_t)n, 1, window_bits).c;
+    opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
+    opt.shared_points = 1;
+    opt.d_window_sums = d_window_sums;
+    msm_device(t->t.curve, t->t, (const uint8_t*)d_scalars, (uint32_t)n, 1, opt, nullptr, nullptr, (cudaStream_t)cuda_stream);
+}
+
+void porla_msm_finalize_host(int curve, const void* h_window_sums, int64_t nparts, int nwin, int c, int out_fmt, void* out64) {
+    finalize_host_parts(curve, h_window_sums, (int)nparts, nwin, c, out_fmt, (uint8_t*)out64);
+}
+
 void porla_msm_combine_device(int curve, const void* d_parts, int64_t count, int64_t nbatch, int out_fmt, void* d_out,
                               void* cuda_stream) {
     msm_combine_device(curve, d_parts, (uint32_t)count, (uint32_t)nbatch, out_fmt, (uint8_t*)d_out, (cudaStream_t)cuda_stream);

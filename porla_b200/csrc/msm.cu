@@ -120,16 +120,18 @@ MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits) {
 
 // ---------------------------------------------------------------------------- host finaliser
 template <class F64>
-static void finalize_host_impl(const void* h_window_sums, int nwin, int c, int out_fmt, uint8_t* out64) {
+static void finalize_host_impl(const void* h_window_sums, int nparts, int nwin, int c, int out_fmt, uint8_t* out64) {
     static_assert(sizeof(XYZZ<F64>) == 128, "device and host XYZZ layouts must coincide");
     const XYZZ<F64>* ws = reinterpret_cast<const XYZZ<F64>*>(h_window_sums);
     XYZZ<F64> r = XYZZ<F64>::inf();
     for (int w = nwin - 1; w >= 0; w--) {
         if (!r.is_inf())
             for (int k = 0; k < c; k++) r = r.dbl();
-        XYZZ<F64> s;
-        memcpy(&s, ws + w, sizeof(s));
-        r.add(s);
+        for (int part = 0; part < nparts; part++) {  // multi-GPU: one set of window sums per rank
+            XYZZ<F64> s;
+            memcpy(&s, ws + (size_t)part * nwin + w, sizeof(s));
+            r.add(s);
+        }
     }
     Affine<F64> a = r.to_affine();
     F64 xy[2] = {a.x.from_internal(), a.y.from_internal()};
@@ -143,9 +145,14 @@ static void finalize_host_impl(const void* h_window_sums, int nwin, int c, int o
     }
 }
 
+void finalize_host_parts(int curve, const void* h_window_sums, int nparts, int nwin, int c, int out_fmt, uint8_t* out64) {
+    if (curve == kCurveBn254)
+        finalize_host_impl<host::Fp64<host::Bn254Fq64Params>>(h_window_sums, nparts, nwin, c, out_fmt, out64);
+    else
+        finalize_host_impl<host::Fp64<host::SecpFq64Params>>(h_window_sums, nparts, nwin, c, out_fmt, out64);
+}
 void finalize_host(int curve, const void* h_window_sums, int nwin, int c, int out_fmt, uint8_t* out64) {
-    if (curve == kCurveBn254) finalize_host_impl<host::Fp64<host::Bn254Fq64Params>>(h_window_sums, nwin, c, out_fmt, out64);
-    else finalize_host_impl<host::Fp64<host::SecpFq64Params>>(h_window_sums, nwin, c, out_fmt, out64);
+    finalize_host_parts(curve, h_window_sums, 1, nwin, c, out_fmt, out64);
 }
 
 // ---------------------------------------------------------------------------- dispatchers

@@ -57,6 +57,9 @@ MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits);
 // Host-side tail of one MSM: Horner over the window sums (c doublings per window), affine
 // normalisation, serialisation.  h_window_sums: nwin XYZZ records as produced on the device.
 void finalize_host(int curve, const void* h_window_sums, int nwin, int c, int out_fmt, uint8_t* out64);
+// Same for an MSM sharded over `nparts` devices: h_window_sums holds nparts consecutive sets of
+// nwin window sums (all computed with the same window size); they are added window by window.
+void finalize_host_parts(int curve, const void* h_window_sums, int nparts, int nwin, int c, int out_fmt, uint8_t* out64);
 
 // nbatch MSMs of n terms each.  d_scalars: nbatch*n*32 bytes on the device.
 // d_out (nullable): nbatch*64 bytes, canonical affine.  d_out_xyzz (nullable): nbatch*128 bytes,

@@ -26,7 +26,8 @@ NEW_SYMBOLS = [
     "porla_device_init", "porla_launch_count", "compute_multi_exp_batch",
     "compute_digest_from_srs_batch", "porla_table_create", "porla_table_create_multiples",
     "porla_table_len", "porla_table_num_infinity", "porla_table_export", "porla_table_destroy",
-    "porla_msm_device", "porla_msm_resident", "porla_msm_combine_device", "porla_msm_host", "porla_choose_window",
+    "porla_msm_device", "porla_msm_resident", "porla_msm_plan", "porla_msm_window_sums_device",
+    "porla_msm_finalize_host", "porla_msm_combine_device", "porla_msm_host", "porla_choose_window",
     "porla_scalar_mul_batch_device", "porla_secp256k1_ecmult_multi_var",
     "porla_secp256k1_gej_serialize", "porla_debug_field_mul", "porla_debug_point_add_host", "porla_measure_pint",
     "porla_stage_timing_enable", "porla_stage_timing_read",
@@ -98,6 +99,9 @@ def load() -> C.CDLL:
         "porla_table_destroy": (None, [P]),
         "porla_msm_device": (None, [P, P, C.c_int64, C.c_int64, I, I, I, I, P, P, P]),
         "porla_msm_resident": (None, [P, P, C.c_int64, I, I, I, P, P]),
+        "porla_msm_plan": (None, [I, C.c_int64, C.c_int64, I, C.POINTER(I), C.POINTER(I)]),
+        "porla_msm_window_sums_device": (None, [P, P, C.c_int64, I, I, P, P]),
+        "porla_msm_finalize_host": (None, [I, P, C.c_int64, I, I, I, P]),
         "porla_msm_combine_device": (None, [I, P, C.c_int64, C.c_int64, I, P, P]),
         "porla_msm_host": (None, [I, P, P, C.c_int64, C.c_int64, I, I, P]),
         "porla_choose_window": (I, [I, C.c_int64, C.c_int64]),
