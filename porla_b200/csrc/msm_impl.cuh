@@ -131,7 +131,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     if (total_scalars) {
         uint32_t grid = (uint32_t)((total_scalars + 255) / 256);
         if (grid > 148u * 32u) grid = 148u * 32u;
-        k_digits<C, false><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, counters, nullptr);
+        k_digits<C, false><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, 0, sh.nwin, counters, nullptr);
         LAUNCHED();
         g_stage_timer.mark(kStageScan, stream);
         k_scan_tiles<<<ntiles, kScanThreads, 0, stream>>>(counters, offsets, nbt, tile_sums);
@@ -141,8 +141,19 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         k_scan_add<<<ntiles, kScanThreads, 0, stream>>>(offsets, counters, nbt, tile_sums);
         LAUNCHED();
         g_stage_timer.mark(kStageScatter, stream);
-        k_digits<C, true><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, counters, sorted);
-        LAUNCHED();
+        // windows per scatter launch: keep the written region of `sorted` (8 B per pair) around 64 MB
+        int wgroup = sh.nwin;
+        if (nbatch == 1) {
+            uint64_t per_window = (uint64_t)n * 8;
+            wgroup = (int)((64ull << 20) / (per_window ? per_window : 1));
+            if (wgroup < 1) wgroup = 1;
+            if (wgroup > sh.nwin) wgroup = sh.nwin;
+        }
+        for (int w0 = 0; w0 < sh.nwin; w0 += wgroup) {
+            int w1 = w0 + wgroup < sh.nwin ? w0 + wgroup : sh.nwin;
+            k_digits<C, true><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, w0, w1, counters, sorted);
+            LAUNCHED();
+        }
         g_stage_timer.mark(kStageAccumulate, stream);
         k_accumulate<C><<<(nslices_cap + kAccThreads - 1) / kAccThreads, kAccThreads, 0, stream>>>(
             points, sorted, grand, L, buckets, part_head, part_tail);

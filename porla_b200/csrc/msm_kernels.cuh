@@ -153,8 +153,11 @@ __global__ void k_export_points(const Affine<typename C::F>* __restrict__ in, ui
 template <class C, bool SCATTER>
 __global__ void __launch_bounds__(256)
 k_digits(const uint8_t* __restrict__ scalars, int big_endian,
-         const uint8_t* __restrict__ inf_flags, MsmShape sh,
+         const uint8_t* __restrict__ inf_flags, MsmShape sh, int w_begin, int w_end,
          uint32_t* __restrict__ counters, uint2* __restrict__ sorted) {
+    // Only windows [w_begin, w_end) are emitted: the host scatters a few windows per launch so that
+    // the region of `sorted` being written (n * 8 B per window) stays L2-resident and the 8-byte
+    // stores merge into full sectors before they reach HBM.
     const uint64_t total = (uint64_t)sh.n * sh.nbatch;
     const uint32_t half = 1u << (sh.c - 1);
     const uint32_t mask = (1u << sh.c) - 1u;
@@ -171,7 +174,7 @@ k_digits(const uint8_t* __restrict__ scalars, int big_endian,
         reduce_scalar<C>(s);
         uint32_t carry = 0;
         const uint32_t slot_base = m * (uint32_t)sh.nwin * sh.nbuckets;
-        for (int w0 = 0; w0 < sh.nwin; w0 += kBatch) {
+        for (int w0 = 0; w0 < w_end; w0 += kBatch) {
             uint32_t bucket[kBatch], val[kBatch];
 #pragma unroll
             for (int k = 0; k < kBatch; k++) {
@@ -187,7 +190,7 @@ k_digits(const uint8_t* __restrict__ scalars, int big_endian,
                     uint32_t neg = d > half;
                     carry = neg;
                     uint32_t mag = neg ? ((1u << sh.c) - d) : d;
-                    if (mag != 0) {
+                    if (mag != 0 && w >= w_begin && w < w_end) {
                         bucket[k] = slot_base + (uint32_t)w * sh.nbuckets + (mag - 1);
                         val[k] = pidx | (neg << 31);
                     }
