@@ -170,7 +170,11 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         g_stage_timer.mark(kStageAccumulate, stream);
     }
     g_stage_timer.mark(kStageReduce, stream);
-    dim3 rgrid(blocks_per_slot, (uint32_t)slots);
+    if (slots * blocks_per_slot >= (1ull << 31)) {
+        fprintf(stderr, "[libmultiexp/porla_b200] FATAL: too many window slots for one launch\n");
+        abort();
+    }
+    const uint32_t rgrid = (uint32_t)(slots * blocks_per_slot);
     k_reduce<C><<<rgrid, kRedThreads, 0, stream>>>((const XC*)buckets, sh.nbuckets, chunk, threads_per_slot, (XC*)partials);
     LAUNCHED();
     const XYZZ<F>* window_sums = partials;

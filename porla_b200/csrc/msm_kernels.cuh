@@ -464,8 +464,11 @@ k_reduce(const XYZZ<typename C::FC>* __restrict__ buckets, uint32_t nb, uint32_t
          uint32_t threads_per_slot, XYZZ<typename C::FC>* __restrict__ partials) {
     using F = typename C::FC;
     __shared__ XYZZ<F> sh[kRedThreads];
-    const uint32_t slot = blockIdx.y;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    // 1-D grid (slot-major): gridDim.y would cap the number of window slots at 65535
+    const uint32_t blocks_per_slot = (threads_per_slot + kRedThreads - 1) / kRedThreads;
+    const uint32_t slot = blockIdx.x / blocks_per_slot;
+    const uint32_t blk = blockIdx.x - slot * blocks_per_slot;
+    const uint32_t t = blk * blockDim.x + threadIdx.x;
     XYZZ<F> acc = XYZZ<F>::inf();
     if (t < threads_per_slot) {
         const XYZZ<F>* base = buckets + (size_t)slot * nb;
@@ -492,7 +495,7 @@ k_reduce(const XYZZ<typename C::FC>* __restrict__ buckets, uint32_t nb, uint32_t
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) st16(partials + (size_t)slot * gridDim.x + blockIdx.x, sh[0]);
+    if (threadIdx.x == 0) st16(partials + (size_t)slot * blocks_per_slot + blk, sh[0]);
 }
 
 // ---------------------------------------------------------------------------- window sums
