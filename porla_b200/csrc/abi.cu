@@ -121,8 +121,8 @@ void run_and_fetch(int curve, const PointTable& tab, const uint8_t* d_scalars, i
     memcpy(out, h, (size_t)nbatch * 64);
 }
 
-// Host-buffer MSM core.  Scalars/points are copied to the device, points imported, nbatch MSMs
-// run, results copied back.  Rare compressed-flag BN254 inputs are expanded on the host first.
+// Host-buffer MSM core.  Scalars/points are copied to the device, points imported (the import
+// kernel also decodes gnark's compressed-flag encodings), nbatch MSMs run, results copied back.
 void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int64_t n, int64_t nbatch,
                    int scalar_fmt, int point_fmt, uint8_t* out) {
     if (nbatch <= 0) return;
@@ -133,33 +133,22 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
     device_init();
     std::lock_guard<std::mutex> lock(g_io_mu);
     const size_t total = (size_t)n * (size_t)nbatch;
-    std::vector<uint8_t> fixed;
-    if (curve == kCurveBn254 && point_fmt == PORLA_POINT_BE64) {
-        // G1Affine.SetBytes: a flag in the top two bits selects a 32-byte compressed encoding
-        for (size_t i = 0; i < total; i++) {
-            if (points[64 * i] & 0xC0) {
-                if (fixed.empty()) fixed.assign(points, points + total * 64);
-                G1A p;
-                if (!g1_unmarshal(points + 64 * i, 64, &p)) p = G1A::inf();
-                g1_marshal(p, fixed.data() + 64 * i);
-            }
-        }
-        if (!fixed.empty()) points = fixed.data();
-    }
+    // staging layout: scalars | raw points | imported table | infinity flags | result scratch
+    auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t sc_bytes = total * 32, pt_bytes = total * 64;
-    size_t sc_off = 0, pt_off = (sc_bytes + 255) & ~(size_t)255, out_off = pt_off + ((pt_bytes + 255) & ~(size_t)255);
+    size_t sc_off = 0, pt_off = pad(sc_bytes), tab_off = pt_off + pad(pt_bytes), fl_off = tab_off + pad(pt_bytes),
+           out_off = fl_off + pad(total);
     uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(curve, n, nbatch));
     cudaStream_t st = g_stage.stream;
     PORLA_CUDA(cudaMemcpyAsync(d + sc_off, scalars, sc_bytes, cudaMemcpyHostToDevice, st));
     PORLA_CUDA(cudaMemcpyAsync(d + pt_off, points, pt_bytes, cudaMemcpyHostToDevice, st));
     PointTable tab;
-    table_import_device(curve, d + pt_off, point_fmt, (uint32_t)total, &tab, st);
+    table_import_into(curve, d + pt_off, point_fmt, (uint32_t)total, d + tab_off, d + fl_off, &tab, st);
     MsmOptions opt;
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.out_fmt = point_fmt;
     opt.shared_points = 0;
     run_and_fetch(curve, tab, d + sc_off, n, nbatch, opt, d + out_off, out, st);
-    table_free(&tab);
 }
 
 void upload_srs();

@@ -74,6 +74,7 @@ int stage_timing_read(float* ms_out) {
 }
 
 template <class C> void import_impl(const uint8_t*, int, uint32_t, PointTable*, cudaStream_t);
+template <class C> void import_into_impl(const uint8_t*, int, uint32_t, void*, uint8_t*, cudaStream_t);
 template <class C> void msm_impl(const PointTable&, const uint8_t*, uint32_t, uint32_t, const MsmOptions&, uint8_t*, void*, cudaStream_t);
 template <class C> void combine_impl(const void*, uint32_t, uint32_t, int, uint8_t*, cudaStream_t);
 template <class C> void scalar_mul_impl(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);
@@ -168,6 +169,17 @@ void table_import_host(int curve, const uint8_t* h_bytes, int fmt, uint32_t n, P
     if (n) PORLA_CUDA(cudaMemcpyAsync(d_tmp, h_bytes, (size_t)n * 64, cudaMemcpyHostToDevice, stream));
     table_import_device(curve, d_tmp, fmt, n, out, stream);
     PORLA_CUDA(cudaFree(d_tmp));
+}
+
+void table_import_into(int curve, const uint8_t* d_bytes, int fmt, uint32_t n, void* d_points_out, uint8_t* d_flags_out,
+                       PointTable* out, cudaStream_t stream) {
+    device_init();
+    DISPATCH(curve, import_into_impl, d_bytes, fmt, n, d_points_out, d_flags_out, stream);
+    out->d_points = d_points_out;
+    out->d_flags = d_flags_out;
+    out->n = n;
+    out->n_inf = 0;  // unknown (not counted on this path); the flags are always consulted
+    out->curve = curve;
 }
 
 void table_free(PointTable* t) {

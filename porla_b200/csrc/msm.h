@@ -37,6 +37,10 @@ void table_import_device(int curve, const uint8_t* d_bytes, int point_fmt, uint3
 void table_import_host(int curve, const uint8_t* h_bytes, int point_fmt, uint32_t n, PointTable* out,
                        cudaStream_t stream);
 void table_free(PointTable* t);
+// Import into caller-provided device buffers (n*64 B points, n B flags): no allocation, no sync.
+// The returned table borrows the buffers (do not table_free it).
+void table_import_into(int curve, const uint8_t* d_bytes, int point_fmt, uint32_t n, void* d_points_out,
+                       uint8_t* d_flags_out, PointTable* out, cudaStream_t stream);
 
 struct MsmOptions {
     int window_bits = 0;      // 0 = choose from n

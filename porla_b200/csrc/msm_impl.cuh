@@ -26,6 +26,18 @@ template <> struct CurveIdOf<Secp256k1> { static constexpr int value = kCurveSec
 
 // ---------------------------------------------------------------------------- tables
 template <class C>
+void import_into_impl(const uint8_t* d_bytes, int fmt, uint32_t n, void* d_points_out, uint8_t* d_flags_out,
+                      cudaStream_t stream) {
+    using F = typename C::F;
+    if (!n) return;
+    int mask = C::F::Params::kMontgomery ? 1 : 0;
+    k_import_points<C><<<(n + 127) / 128, 128, 0, stream>>>(d_bytes, fmt, mask, n, reinterpret_cast<Affine<F>*>(d_points_out),
+                                                           d_flags_out, nullptr);
+    LAUNCHED();
+    PORLA_CUDA(cudaGetLastError());
+}
+
+template <class C>
 void import_impl(const uint8_t* d_bytes, int fmt, uint32_t n, PointTable* out, cudaStream_t stream) {
     using F = typename C::F;
     Affine<F>* pts = nullptr;
@@ -232,6 +244,7 @@ void field_mul_impl(const void* d_a, const void* d_b, uint32_t n, void* d_out, c
 
 #define PORLA_INSTANTIATE_CURVE(C)                                                                                     \
     template void import_impl<C>(const uint8_t*, int, uint32_t, PointTable*, cudaStream_t);                            \
+    template void import_into_impl<C>(const uint8_t*, int, uint32_t, void*, uint8_t*, cudaStream_t);                   \
     template void msm_impl<C>(const PointTable&, const uint8_t*, uint32_t, uint32_t, const MsmOptions&, uint8_t*,      \
                               void*, cudaStream_t);                                                                    \
     template void combine_impl<C>(const void*, uint32_t, uint32_t, int, uint8_t*, cudaStream_t);                       \

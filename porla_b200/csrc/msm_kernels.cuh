@@ -109,23 +109,55 @@ __global__ void k_import_points(const uint8_t* __restrict__ in, int fmt, int mas
     F x, y;
     load_u256(in, 2 * (size_t)i, fmt == kPointBE64, x.v);
     load_u256(in, 2 * (size_t)i + 1, fmt == kPointBE64, y.v);
+    // gnark G1Affine.SetBytes: the top two bits of byte 0 select the encoding
+    //   00 uncompressed X||Y, 01 compressed infinity, 10/11 compressed (y smallest/largest)
+    uint32_t flag = mask_top2 ? (x.v[7] >> 30) : 0u;
     if (mask_top2) x.v[7] &= 0x3fffffffu;
+    uint32_t m[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) m[j] = F::Params::mod(j);
     // reduce below p (inputs are < 2^256; p > 2^253 so a few subtractions suffice)
     for (int k = 0; k < 6; k++) {
         F t;
-        uint32_t m[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) m[j] = F::Params::mod(j);
         if (sub256(t.v, x.v, m)) break;
         x = t;
     }
     for (int k = 0; k < 6; k++) {
         F t;
-        uint32_t m[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) m[j] = F::Params::mod(j);
         if (sub256(t.v, y.v, m)) break;
         y = t;
+    }
+    if (flag == 1u) {
+        x = F::zero();
+        y = F::zero();
+    } else if (flag >= 2u) {
+        // compressed point (never produced by Porla for MSM inputs; handled for SetBytes parity):
+        // y = sqrt(x^3 + b) = (x^3 + b)^((p+1)/4), p = 3 mod 4; pick the root by the flag
+        F xi = x.to_internal();
+        F bb = F::zero();
+        bb.v[0] = C::kB;
+        F rhs = xi.sqr() * xi + bb.to_internal();
+        uint32_t e[8], one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+        add256(e, m, one);
+#pragma unroll
+        for (int j = 0; j < 8; j++) e[j] = (e[j] >> 2) | (j < 7 ? (e[j + 1] << 30) : 0u);
+        F r = F::one();
+        for (int b = 255; b >= 0; b--) {
+            r = r.sqr();
+            if ((e[b >> 5] >> (b & 31)) & 1u) r = r * rhs;
+        }
+        if (r.sqr() != rhs) {
+            x = F::zero();
+            y = F::zero();
+        } else {
+            F yc = r.from_internal();
+            uint32_t half[8], t[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) half[j] = (m[j] >> 1) | (j < 7 ? (m[j + 1] << 31) : 0u);
+            bool largest = sub256(t, half, yc.v) != 0;  // y > (p-1)/2
+            if (largest != (flag == 3u)) sub256(yc.v, m, yc.v);
+            y = yc;
+        }
     }
     bool inf = x.is_zero() && y.is_zero();
     Affine<F> p{x.to_internal(), y.to_internal()};

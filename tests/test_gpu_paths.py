@@ -212,3 +212,18 @@ def test_batched_commitments_config3_miniature_and_kzg_roundtrip():
     assert h_ == loader.bn254_msm(b"".join(map(be, hq)), srs_bytes[:64 * (n - 1)], n - 1, 2)
     assert k.verify_proof(c_, h_, z_, y_)
     assert not k.verify_proof(c_, h_, z_, be((y + 1) % BN.n))
+
+
+def test_compressed_flag_inputs_follow_setbytes():
+    """G1Affine.SetBytes semantics on MSM inputs (main.go:130): flag 01 = infinity, 10/11 = compressed
+    x with the y root chosen by the flag; only the first 32 bytes are read for those."""
+    pts = bn254_points(4)
+    raw = bytearray(enc_points(pts))
+    raw[64 * 1:64 * 1 + 32] = O.bn254_compress(pts[1])      # compressed form of the same point
+    raw[64 * 1 + 32:64 * 2] = b"\xAA" * 32                  # ignored tail
+    raw[64 * 2:64 * 3] = bytes([0x40]) + bytes(63)          # compressed infinity
+    raw[64 * 3:64 * 3 + 32] = O.bn254_compress(O.neg(BN, pts[3]))
+    sc = [5, 7, 11, 13]
+    got = pb.bn254_multi_exp(bytes(raw), b"".join(map(be, sc)), 4)
+    want = O.msm_naive(BN, sc, [pts[0], pts[1], None, O.neg(BN, pts[3])])
+    assert got == O.bn254_marshal(want)
