@@ -98,6 +98,12 @@ porla_table* porla_table_create(int curve, const void* points, int64_t n, int po
  * has a closed form. */
 porla_table* porla_table_create_multiples(int curve, const void* scalars, int64_t n, int scalar_fmt,
                                           int on_device, void* cuda_stream);
+/* Fixed-base expansion of a resident table: stores 2^(c*w) * P_i for every window w (nwin * n * 64 B
+ * of HBM, one-time ~254 doublings per point).  MSMs over the table (shared_points, window_bits 0 or
+ * equal to the returned c) then use ONE bucket set for all windows: no per-window bucket reduction
+ * and no doublings in the window combine.  window_bits 0 = choose for MSMs of n_hint terms, batch_hint
+ * per launch.  Meant for the SRS / generator tables; arbitrary per-call points use the general path. */
+int porla_table_precompute(porla_table* t, int window_bits, int64_t n_hint, int64_t batch_hint, void* cuda_stream);
 int64_t porla_table_len(const porla_table* t);
 int64_t porla_table_num_infinity(const porla_table* t);
 void porla_table_export(const porla_table* t, int point_fmt, void* out, int on_device, void* cuda_stream);

@@ -95,7 +95,7 @@ std::vector<Fr> read_poly(const GoSlice* data_in, int64_t n) {
 // d_scratch_out must hold max(nbatch*64, nbatch*nwin*128) bytes.  Caller holds g_io_mu.
 constexpr int64_t kHostFinalizeMaxBatch = 4;
 size_t result_scratch_bytes(int curve, int64_t n, int64_t nbatch) {
-    MsmPlan p = msm_plan(curve, (uint32_t)n, (uint32_t)nbatch, 0);
+    MsmPlan p = msm_plan(curve, (uint32_t)n, (uint32_t)nbatch, 0);  // general plan: an upper bound for fixed-base too
     size_t a = (size_t)nbatch * 64, b = (size_t)nbatch * p.nwin * 128;
     return a > b ? a : b;
 }
@@ -103,7 +103,7 @@ void run_and_fetch(int curve, const PointTable& tab, const uint8_t* d_scalars, i
                    uint8_t* d_scratch_out, uint8_t* out, cudaStream_t st) {
     const char* force_dev = getenv("PORLA_DEVICE_FINALIZE");
     if (nbatch <= kHostFinalizeMaxBatch && !(force_dev && force_dev[0] == '1')) {
-        MsmPlan p = msm_plan(curve, (uint32_t)n, (uint32_t)nbatch, opt.window_bits);
+        MsmPlan p = msm_plan_table(tab, (uint32_t)n, (uint32_t)nbatch, opt.window_bits, opt.shared_points);
         opt.window_bits = p.c;
         opt.d_window_sums = d_scratch_out;
         size_t bytes = (size_t)nbatch * p.nwin * 128;
@@ -185,6 +185,11 @@ void upload_srs() {
     for (size_t i = 0; i < g_kzg.srs_g1.size(); i++) g1_marshal(g_kzg.srs_g1[i], bytes.data() + 64 * i);
     table_import_host(kCurveBn254, bytes.data(), PORLA_POINT_BE64, (uint32_t)g_kzg.srs_g1.size(), &g_kzg.srs_table,
                       g_stage.stream);
+    // the SRS is a fixed base: expand it once so that commitments need no per-window reduction
+    if (!getenv("PORLA_NO_FIXED_BASE")) {
+        table_precompute(&g_kzg.srs_table, 0, (uint32_t)g_kzg.srs_g1.size(), 1, g_stage.stream);
+        PORLA_CUDA(cudaStreamSynchronize(g_stage.stream));
+    }
     g_kzg.have_table = true;
 }
 
@@ -444,6 +449,12 @@ porla_table* porla_table_create_multiples(int curve, const void* scalars, int64_
     return t;
 }
 
+int porla_table_precompute(porla_table* t, int window_bits, int64_t n_hint, int64_t batch_hint, void* cuda_stream) {
+    int c = table_precompute(&t->t, window_bits, (uint32_t)n_hint, (uint32_t)batch_hint, (cudaStream_t)cuda_stream);
+    PORLA_CUDA(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+    return c;
+}
+
 int64_t porla_table_len(const porla_table* t) { return t->t.n; }
 int64_t porla_table_num_infinity(const porla_table* t) { return t->t.n_inf; }
 
@@ -512,6 +523,7 @@ void porla_msm_window_sums_device(const porla_table* t, const void* d_scalars, i
     opt.window_bits = msm_plan(t->t.curve, (uint32_t)n, 1, window_bits).c;
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.shared_points = 1;
+    opt.no_fixed_base = 1;  // the sharded protocol exchanges nwin window sums per rank
     opt.d_window_sums = d_window_sums;
     msm_device(t->t.curve, t->t, (const uint8_t*)d_scalars, (uint32_t)n, 1, opt, nullptr, nullptr, (cudaStream_t)cuda_stream);
 }

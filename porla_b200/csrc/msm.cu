@@ -76,6 +76,7 @@ int stage_timing_read(float* ms_out) {
 template <class C> void import_impl(const uint8_t*, int, uint32_t, PointTable*, cudaStream_t);
 template <class C> void import_into_impl(const uint8_t*, int, uint32_t, void*, uint8_t*, cudaStream_t);
 template <class C> void msm_impl(const PointTable&, const uint8_t*, uint32_t, uint32_t, const MsmOptions&, uint8_t*, void*, cudaStream_t);
+template <class C> void precompute_impl(PointTable*, int, cudaStream_t);
 template <class C> void combine_impl(const void*, uint32_t, uint32_t, int, uint8_t*, cudaStream_t);
 template <class C> void scalar_mul_impl(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);
 template <class C> void export_impl(const void*, uint32_t, int, uint8_t*, cudaStream_t);
@@ -110,6 +111,37 @@ int choose_window(int curve, uint32_t n, uint32_t nbatch) {
         }
     }
     return best_c;
+}
+
+int choose_window_fixed_base(int curve, uint32_t n, uint32_t nbatch) {
+    const int bits = scalar_bits(curve);
+    double best = 1e300;
+    int best_c = 8;
+    for (int c = 4; c <= 22; c++) {
+        int nwin = (bits + 1 + c - 1) / c;
+        double nb = (double)(1u << (c - 1));
+        double cost = (double)nwin * (double)n + 4.0 * nb;   // one shared bucket set per MSM
+        if ((double)nbatch * nb * 128.0 > 48.0e9) continue;
+        if ((double)nwin * (double)n >= 2.0e9) continue;
+        if (cost < best) {
+            best = cost;
+            best_c = c;
+        }
+    }
+    return best_c;
+}
+
+int table_precompute(PointTable* t, int c, uint32_t n_hint, uint32_t batch_hint, cudaStream_t stream) {
+    device_init();
+    if (c <= 0) c = choose_window_fixed_base(t->curve, n_hint ? n_hint : t->n, batch_hint ? batch_hint : 1);
+    if (t->curve == kCurveBn254) precompute_impl<Bn254>(t, c, stream);
+    else precompute_impl<Secp256k1>(t, c, stream);
+    return c;
+}
+
+MsmPlan msm_plan_table(const PointTable& t, uint32_t n, uint32_t nbatch, int window_bits, int shared_points) {
+    if (t.fb_c > 0 && shared_points && (window_bits == 0 || window_bits == t.fb_c)) return MsmPlan{t.fb_c, 1};
+    return msm_plan(t.curve, n, nbatch, window_bits);
 }
 
 MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits) {
@@ -185,6 +217,7 @@ void table_import_into(int curve, const uint8_t* d_bytes, int fmt, uint32_t n, v
 void table_free(PointTable* t) {
     if (t->d_points) PORLA_CUDA(cudaFree(t->d_points));
     if (t->d_flags) PORLA_CUDA(cudaFree(t->d_flags));
+    if (t->d_fb_points) PORLA_CUDA(cudaFree(t->d_fb_points));
     *t = PointTable{};
 }
 

@@ -28,6 +28,12 @@ struct PointTable {
     uint32_t n = 0;
     uint32_t n_inf = 0;
     int curve = 0;
+    // Optional fixed-base expansion (table_precompute): fb_points[w*n + i] = 2^(fb_c*w) * P_i for
+    // w < fb_nwin.  With it, every window of an MSM over this table shares ONE bucket set: no
+    // per-window bucket reduction and no doublings in the window combine.
+    int fb_c = 0;
+    int fb_nwin = 0;
+    void* d_fb_points = nullptr;
 };
 
 // Import `n` external 64-byte points that already live on the device.
@@ -37,6 +43,10 @@ void table_import_device(int curve, const uint8_t* d_bytes, int point_fmt, uint3
 void table_import_host(int curve, const uint8_t* h_bytes, int point_fmt, uint32_t n, PointTable* out,
                        cudaStream_t stream);
 void table_free(PointTable* t);
+// Builds the fixed-base expansion for window size c (0 = choose for MSMs of `n_hint` terms, `batch_hint`
+// per launch).  One-time cost of ~254 doublings + fb_nwin inversions per point; fb_nwin * n * 64 bytes.
+int table_precompute(PointTable* t, int c, uint32_t n_hint, uint32_t batch_hint, cudaStream_t stream);
+int choose_window_fixed_base(int curve, uint32_t n, uint32_t nbatch);
 // Import into caller-provided device buffers (n*64 B points, n B flags): no allocation, no sync.
 // The returned table borrows the buffers (do not table_free it).
 void table_import_into(int curve, const uint8_t* d_bytes, int point_fmt, uint32_t n, void* d_points_out,
@@ -50,6 +60,7 @@ struct MsmOptions {
     // When set, receives the nbatch*nwin per-window sums (XYZZ, 128 B each, window-major per MSM)
     // and the device finaliser is skipped: the caller combines them with finalize_host().
     void* d_window_sums = nullptr;
+    int no_fixed_base = 0;    // ignore the table's fixed-base expansion (callers that need nwin window sums)
 };
 
 struct MsmPlan {
@@ -57,6 +68,9 @@ struct MsmPlan {
     int nwin;   // windows per scalar
 };
 MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits);
+// Plan for a specific table: when its fixed-base expansion applies, nwin = 1 (a single shared
+// bucket set, so one "window sum" per MSM and no doublings) and c = the expansion's window size.
+MsmPlan msm_plan_table(const PointTable& t, uint32_t n, uint32_t nbatch, int window_bits, int shared_points);
 
 // Host-side tail of one MSM: Horner over the window sums (c doublings per window), affine
 // normalisation, serialisation.  h_window_sums: nwin XYZZ records as produced on the device.

@@ -79,14 +79,20 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     sh.n = n;
     sh.nbatch = nbatch;
     sh.shared = opt.shared_points ? 1u : 0u;
-    sh.c = opt.window_bits > 0 ? opt.window_bits : choose_window(curve, n, nbatch);
+    const bool fixed = table.fb_c > 0 && opt.shared_points && !opt.no_fixed_base &&
+                       (opt.window_bits == 0 || opt.window_bits == table.fb_c);
+    sh.c = fixed ? table.fb_c : (opt.window_bits > 0 ? opt.window_bits : choose_window(curve, n, nbatch));
     sh.nwin = (C::kScalarBits + 1 + sh.c - 1) / sh.c;
     sh.nbuckets = 1u << (sh.c - 1);
+    sh.fixed_n = fixed ? table.n : 0u;
+    // window slots that own a bucket set: one per (msm, window), or one per msm in fixed-base mode
+    const int slot_windows = fixed ? 1 : sh.nwin;
 
-    const uint64_t slots = (uint64_t)nbatch * sh.nwin;
+    const uint64_t slots = (uint64_t)nbatch * slot_windows;
     const uint64_t nbt64 = slots * sh.nbuckets;
     const uint64_t pairs64 = (uint64_t)nbatch * n * sh.nwin;
-    if (nbt64 >= (1ull << 32) || pairs64 >= (1ull << 32) || (uint64_t)nbatch * n >= (1ull << 31)) {
+    if (nbt64 >= (1ull << 32) || pairs64 >= (1ull << 32) || (uint64_t)nbatch * n >= (1ull << 31) ||
+        (fixed && (uint64_t)table.n * sh.nwin >= (1ull << 31))) {
         fprintf(stderr, "[libmultiexp/porla_b200] FATAL: MSM shape too large for 32-bit indexing\n");
         abort();
     }
@@ -98,7 +104,8 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     uint32_t chunk = 64;
     while (chunk > 16 && (uint64_t)nbt / chunk < 148ull * 256ull) chunk >>= 1;
     while (chunk > 4 && sh.nbuckets / chunk < 4) chunk >>= 1;
-    uint32_t threads_per_slot = (sh.nbuckets + chunk - 1) / chunk;
+    if (chunk > sh.nbuckets) chunk = sh.nbuckets;
+    uint32_t threads_per_slot = (sh.nbuckets + chunk - 1) / chunk;  // nbuckets and chunk are powers of two
     uint32_t blocks_per_slot = (threads_per_slot + kRedThreads - 1) / kRedThreads;
 
     // accumulation geometry: slice length L (pairs per thread)
@@ -128,7 +135,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     XYZZ<F>* partials = g_arena.take<XYZZ<F>>(slots * blocks_per_slot);
     XYZZ<F>* wsum = g_arena.take<XYZZ<F>>(slots);
 
-    const Affine<F>* points = reinterpret_cast<const Affine<F>*>(table.d_points);
+    const Affine<F>* points = reinterpret_cast<const Affine<F>*>(fixed ? table.d_fb_points : table.d_points);
     // the cold kernels see the same records through the compact (outlined-multiply) field type
     using FC = typename C::FC;
     using XC = XYZZ<FC>;
@@ -186,8 +193,11 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         fprintf(stderr, "[libmultiexp/porla_b200] FATAL: too many window slots for one launch\n");
         abort();
     }
-    const uint32_t rgrid = (uint32_t)(slots * blocks_per_slot);
-    k_reduce<C><<<rgrid, kRedThreads, 0, stream>>>((const XC*)buckets, sh.nbuckets, chunk, threads_per_slot, (XC*)partials);
+    const uint32_t rgrid = threads_per_slot >= (uint32_t)kRedThreads
+                               ? (uint32_t)(slots * blocks_per_slot)
+                               : (uint32_t)((slots + kRedThreads / threads_per_slot - 1) / (kRedThreads / threads_per_slot));
+    k_reduce<C><<<rgrid, kRedThreads, 0, stream>>>((const XC*)buckets, sh.nbuckets, chunk, threads_per_slot, (uint32_t)slots,
+                                                   (XC*)partials);
     LAUNCHED();
     const XYZZ<F>* window_sums = partials;
     if (blocks_per_slot > 1) {
@@ -199,12 +209,30 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     if (opt.d_window_sums) {
         PORLA_CUDA(cudaMemcpyAsync(opt.d_window_sums, window_sums, slots * sizeof(XYZZ<F>), cudaMemcpyDeviceToDevice, stream));
     } else {
-        k_finalize<C><<<nbatch, 64, sh.nwin * sizeof(XYZZ<F>), stream>>>(
-            (const XC*)window_sums, 1, sh.nwin, sh.c, opt.out_fmt, d_out, reinterpret_cast<XC*>(d_out_xyzz));
+        k_finalize<C><<<(nbatch + 31) / 32, 32, 0, stream>>>((const XC*)window_sums, nbatch, slot_windows, sh.c, opt.out_fmt, d_out,
+                                                            reinterpret_cast<XC*>(d_out_xyzz));
         LAUNCHED();
     }
     g_stage_timer.mark(kNumStages, stream);
     PORLA_CUDA(cudaGetLastError());
+}
+
+template <class C>
+void precompute_impl(PointTable* t, int c, cudaStream_t stream) {
+    using FC = typename C::FC;
+    const int nwin = (C::kScalarBits + 1 + c - 1) / c;
+    if (t->d_fb_points) PORLA_CUDA(cudaFree(t->d_fb_points));
+    void* out = nullptr;
+    PORLA_CUDA(cudaMalloc(&out, (size_t)nwin * (t->n ? t->n : 1) * sizeof(Affine<FC>)));
+    if (t->n) {
+        k_precompute_windows<C><<<(t->n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<FC>*>(t->d_points), t->n, c, nwin,
+                                                                      reinterpret_cast<Affine<FC>*>(out));
+        LAUNCHED();
+        PORLA_CUDA(cudaGetLastError());
+    }
+    t->d_fb_points = out;
+    t->fb_c = c;
+    t->fb_nwin = nwin;
 }
 
 template <class C>
@@ -248,6 +276,7 @@ void field_mul_impl(const void* d_a, const void* d_b, uint32_t n, void* d_out, c
     template void msm_impl<C>(const PointTable&, const uint8_t*, uint32_t, uint32_t, const MsmOptions&, uint8_t*,      \
                               void*, cudaStream_t);                                                                    \
     template void combine_impl<C>(const void*, uint32_t, uint32_t, int, uint8_t*, cudaStream_t);                       \
+    template void precompute_impl<C>(PointTable*, int, cudaStream_t);                                                  \
     template void scalar_mul_impl<C>(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);           \
     template void export_impl<C>(const void*, uint32_t, int, uint8_t*, cudaStream_t);                                  \
     template void field_mul_impl<C>(const void*, const void*, uint32_t, void*, cudaStream_t);

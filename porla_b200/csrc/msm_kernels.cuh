@@ -31,6 +31,7 @@ struct MsmShape {
     int c;               // window bits
     int nwin;            // windows per scalar
     uint32_t nbuckets;   // buckets per window = 2^(c-1)
+    uint32_t fixed_n;    // 0: general.  > 0: fixed-base table of stride fixed_n (windows share buckets)
 };
 
 // ---------------------------------------------------------------------------- small helpers
@@ -179,6 +180,25 @@ __global__ void k_export_points(const Affine<typename C::F>* __restrict__ in, ui
     store_u256(out, 2 * (size_t)i + 1, fmt == kPointBE64, y.v);
 }
 
+// Fixed-base expansion: out[w*n + i] = 2^(c*w) * P_i, affine, for w < nwin (out[i] = P_i).
+template <class C>
+__global__ void __launch_bounds__(128)
+k_precompute_windows(const Affine<typename C::FC>* __restrict__ in, uint32_t n, int c, int nwin,
+                     Affine<typename C::FC>* __restrict__ out) {
+    using F = typename C::FC;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = ld16(in + i);
+    st16(out + i, p);
+    XYZZ<F> r = XYZZ<F>::from_affine(p);
+    for (int w = 1; w < nwin; w++) {
+        for (int k = 0; k < c; k++) r = r.dbl();
+        Affine<F> a = r.to_affine();
+        st16(out + (size_t)w * n + i, a);
+        r = XYZZ<F>::from_affine(a);   // restart from the affine form: keeps zz = zzz = 1
+    }
+}
+
 // ---------------------------------------------------------------------------- recoding
 // Signed c-bit digits: d_w in [-2^(c-1), 2^(c-1)], bucket id |d_w| - 1; nwin*c > bits of the
 // order, so the top digit never overflows.
@@ -205,7 +225,9 @@ k_digits(const uint8_t* __restrict__ scalars, int big_endian,
         s[8] = 0;
         reduce_scalar<C>(s);
         uint32_t carry = 0;
-        const uint32_t slot_base = m * (uint32_t)sh.nwin * sh.nbuckets;
+        // general: one bucket set per (msm, window); fixed-base: one per msm, the window selects the
+        // pre-multiplied copy 2^(c*w) * P_i of the point instead
+        const uint32_t slot_base = sh.fixed_n ? m * sh.nbuckets : m * (uint32_t)sh.nwin * sh.nbuckets;
         for (int w0 = 0; w0 < w_end; w0 += kBatch) {
             uint32_t bucket[kBatch], val[kBatch];
 #pragma unroll
@@ -223,8 +245,13 @@ k_digits(const uint8_t* __restrict__ scalars, int big_endian,
                     carry = neg;
                     uint32_t mag = neg ? ((1u << sh.c) - d) : d;
                     if (mag != 0 && w >= w_begin && w < w_end) {
-                        bucket[k] = slot_base + (uint32_t)w * sh.nbuckets + (mag - 1);
-                        val[k] = pidx | (neg << 31);
+                        if (sh.fixed_n) {
+                            bucket[k] = slot_base + (mag - 1);
+                            val[k] = ((uint32_t)w * sh.fixed_n + pidx) | (neg << 31);
+                        } else {
+                            bucket[k] = slot_base + (uint32_t)w * sh.nbuckets + (mag - 1);
+                            val[k] = pidx | (neg << 31);
+                        }
                     }
                 }
             }
@@ -493,16 +520,31 @@ constexpr int kRedThreads = 64;
 template <class C>
 __global__ void __launch_bounds__(kRedThreads)
 k_reduce(const XYZZ<typename C::FC>* __restrict__ buckets, uint32_t nb, uint32_t chunk,
-         uint32_t threads_per_slot, XYZZ<typename C::FC>* __restrict__ partials) {
+         uint32_t threads_per_slot, uint32_t total_slots, XYZZ<typename C::FC>* __restrict__ partials) {
     using F = typename C::FC;
     __shared__ XYZZ<F> sh[kRedThreads];
-    // 1-D grid (slot-major): gridDim.y would cap the number of window slots at 65535
-    const uint32_t blocks_per_slot = (threads_per_slot + kRedThreads - 1) / kRedThreads;
-    const uint32_t slot = blockIdx.x / blocks_per_slot;
-    const uint32_t blk = blockIdx.x - slot * blocks_per_slot;
-    const uint32_t t = blk * blockDim.x + threadIdx.x;
+    // Geometry (1-D grid; gridDim.y would cap the number of window slots at 65535):
+    //   threads_per_slot >= 64: blocks_per_slot blocks per slot, one partial per block;
+    //   threads_per_slot  < 64 (a power of two; small windows of batched MSMs): 64/threads_per_slot
+    //   slots per block, the shared-memory tree stops at the slot boundary, one partial per slot.
+    uint32_t slot, t, group;
+    size_t out_index;
+    if (threads_per_slot >= kRedThreads) {
+        const uint32_t blocks_per_slot = (threads_per_slot + kRedThreads - 1) / kRedThreads;
+        slot = blockIdx.x / blocks_per_slot;
+        const uint32_t blk = blockIdx.x - slot * blocks_per_slot;
+        t = blk * kRedThreads + threadIdx.x;
+        group = kRedThreads;
+        out_index = (size_t)slot * blocks_per_slot + blk;
+    } else {
+        const uint32_t slots_per_block = kRedThreads / threads_per_slot;
+        slot = blockIdx.x * slots_per_block + threadIdx.x / threads_per_slot;
+        t = threadIdx.x % threads_per_slot;
+        group = threads_per_slot;
+        out_index = slot;
+    }
     XYZZ<F> acc = XYZZ<F>::inf();
-    if (t < threads_per_slot) {
+    if (slot < total_slots && t < threads_per_slot) {
         const XYZZ<F>* base = buckets + (size_t)slot * nb;
         uint32_t lo = t * chunk;
         uint32_t hi = lo + chunk < nb ? lo + chunk : nb;
@@ -519,15 +561,16 @@ k_reduce(const XYZZ<typename C::FC>* __restrict__ buckets, uint32_t nb, uint32_t
     }
     sh[threadIdx.x] = acc;
     __syncthreads();
-    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) {
+    const uint32_t local = threadIdx.x % group;
+    for (uint32_t o = group / 2; o > 0; o >>= 1) {
+        if (local < o) {
             XYZZ<F> a = sh[threadIdx.x];
             a.add(sh[threadIdx.x + o]);
             sh[threadIdx.x] = a;
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) st16(partials + (size_t)slot * blocks_per_slot + blk, sh[0]);
+    if (local == 0 && slot < total_slots) st16(partials + out_index, sh[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------- window sums
@@ -556,32 +599,24 @@ k_window_sums(const XYZZ<typename C::FC>* __restrict__ partials, uint32_t count,
 }
 
 // ---------------------------------------------------------------------------- finalisation
-// One block per MSM.  Thread w sums the partials of window w; thread 0 then runs Horner over the
-// windows (c doublings each; doubling infinity is free so leading empty windows cost nothing),
-// normalises to affine and serialises.  out_fmt: kPointBE64 / kPointLE64 external bytes
+// One thread per MSM: Horner over the window sums (c doublings each; doubling infinity is free so
+// leading empty windows cost nothing), normalise to affine, serialise.  out_fmt: kPointBE64 / kPointLE64 external bytes
 // (canonical, not Montgomery); out_xyzz (optional) receives the un-normalised sum for multi-GPU
 // combination.
 template <class C>
-__global__ void k_finalize(const XYZZ<typename C::FC>* __restrict__ partials, uint32_t blocks_per_slot,
-                           int nwin, int c, int out_fmt, uint8_t* __restrict__ out,
-                           XYZZ<typename C::FC>* __restrict__ out_xyzz) {
+__global__ void __launch_bounds__(32)
+k_finalize(const XYZZ<typename C::FC>* __restrict__ wsums, uint32_t nbatch, int nwin, int c, int out_fmt,
+           uint8_t* __restrict__ out, XYZZ<typename C::FC>* __restrict__ out_xyzz) {
     using F = typename C::FC;
-    extern __shared__ uint4 sh_raw[];
-    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(sh_raw);
-    const uint32_t m = blockIdx.x;
-    for (int w = threadIdx.x; w < nwin; w += blockDim.x) {
-        const XYZZ<F>* p = partials + ((size_t)m * nwin + w) * blocks_per_slot;
-        XYZZ<F> s = ld16(p);
-        for (uint32_t k = 1; k < blocks_per_slot; k++) s.add(ld16(p + k));
-        sh[w] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
+    // one thread per MSM (a batch of MSMs fills warps; a single MSM is one serial chain)
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nbatch) return;
+    const XYZZ<F>* ws = wsums + (size_t)m * nwin;
     XYZZ<F> r = XYZZ<F>::inf();
     for (int w = nwin - 1; w >= 0; w--) {
         if (!r.is_inf())
             for (int k = 0; k < c; k++) r = r.dbl();
-        r.add(sh[w]);
+        r.add(ld16(ws + w));
     }
     if (out_xyzz) st16(out_xyzz + m, r);
     if (out) {

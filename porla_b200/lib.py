@@ -25,7 +25,7 @@ LEGACY_SYMBOLS = [
 NEW_SYMBOLS = [
     "porla_device_init", "porla_launch_count", "compute_multi_exp_batch",
     "compute_digest_from_srs_batch", "porla_table_create", "porla_table_create_multiples",
-    "porla_table_len", "porla_table_num_infinity", "porla_table_export", "porla_table_destroy",
+    "porla_table_precompute", "porla_table_len", "porla_table_num_infinity", "porla_table_export", "porla_table_destroy",
     "porla_msm_device", "porla_msm_resident", "porla_msm_plan", "porla_msm_window_sums_device",
     "porla_msm_finalize_host", "porla_msm_combine_device", "porla_msm_host", "porla_choose_window",
     "porla_scalar_mul_batch_device", "porla_secp256k1_ecmult_multi_var",
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
         "compute_digest_from_srs_batch": (None, [GS, LL, GS]),
         "porla_table_create": (P, [I, P, C.c_int64, I, I, P]),
         "porla_table_create_multiples": (P, [I, P, C.c_int64, I, I, P]),
+        "porla_table_precompute": (I, [P, I, C.c_int64, C.c_int64, P]),
         "porla_table_len": (C.c_int64, [P]),
         "porla_table_num_infinity": (C.c_int64, [P]),
         "porla_table_export": (None, [P, I, P, I, P]),
@@ -263,6 +264,10 @@ class Table:
             buf = bytearray(scalars)
             ptr = C.cast((C.c_ubyte * len(buf)).from_buffer(buf), C.c_void_p)
         return cls(load().porla_table_create_multiples(curve, ptr, n, scalar_fmt, int(on_device), C.c_void_p(stream)), curve)
+
+    def precompute(self, window_bits: int = 0, n_hint: int = 0, batch_hint: int = 1, stream: int = 0) -> int:
+        """Fixed-base expansion (2^(c*w) * P_i for every window); returns the window size used."""
+        return int(load().porla_table_precompute(C.c_void_p(self.handle), window_bits, n_hint, batch_hint, C.c_void_p(stream)))
 
     def __len__(self) -> int:
         return int(load().porla_table_len(C.c_void_p(self.handle)))

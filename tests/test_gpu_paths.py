@@ -227,3 +227,36 @@ def test_compressed_flag_inputs_follow_setbytes():
     got = pb.bn254_multi_exp(bytes(raw), b"".join(map(be, sc)), 4)
     want = O.msm_naive(BN, sc, [pts[0], pts[1], None, O.neg(BN, pts[3])])
     assert got == O.bn254_marshal(want)
+
+
+@pytest.mark.parametrize("curve,c", [(pb.CURVE_BN254, BN), (pb.CURVE_SECP256K1, SE)])
+def test_fixed_base_tables_match_general_path(curve, c):
+    """Precomputed 2^(c*w)*P_i tables (one shared bucket set) give the same bytes as the general path,
+    for single MSMs (host and device finalisers), prefixes of the table and batches."""
+    import torch
+    n, nb = 700, 6
+    rnd = random.Random(41)
+    G = (c.gx, c.gy)
+    ks = [rnd.randrange(c.n) for _ in range(n)]
+    ks[3] = 0                                               # an infinity point in the table
+    tab = pb.Table.multiples_of_generator(curve, b"".join(le(k) for k in ks), n, pb.SCALAR_LE32)
+    ss = [rnd.randrange(1 << 256) for _ in range(nb * n)]
+    d_sc = _dev(b"".join(le(s) for s in ss))
+    general = torch.zeros(64 * nb, dtype=torch.uint8, device="cuda")
+    tab.msm_device(d_sc.data_ptr(), n, general.data_ptr(), nbatch=nb, scalar_fmt=pb.SCALAR_LE32, shared_points=True)
+    torch.cuda.synchronize()
+    want0 = O.mul(c, sum(s * k for s, k in zip(ss[:n], ks)) % c.n, G)
+    enc = lambda P: bytes(64) if P is None else be(P[0]) + be(P[1])
+    assert bytes(general[:64].cpu().numpy().tobytes()) == enc(want0)
+    for wb in (0, 5, 11):
+        cfb = tab.precompute(wb, n, nb)
+        assert cfb == wb or wb == 0
+        fixed = torch.zeros(64 * nb, dtype=torch.uint8, device="cuda")
+        tab.msm_device(d_sc.data_ptr(), n, fixed.data_ptr(), nbatch=nb, scalar_fmt=pb.SCALAR_LE32, shared_points=True)
+        torch.cuda.synchronize()
+        assert torch.equal(fixed, general), wb
+        assert tab.msm_resident(d_sc.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32) == enc(want0)
+        m = 123                                             # a prefix of the table
+        wantp = O.mul(c, sum(s * k for s, k in zip(ss[:m], ks[:m])) % c.n, G)
+        assert tab.msm_resident(d_sc.data_ptr(), m, scalar_fmt=pb.SCALAR_LE32) == enc(wantp)
+    tab.destroy()
