@@ -177,6 +177,9 @@ double porla_measure_pint(int variant, double min_seconds);
 /* out[i] = a[i] (*) b[i], the device field product on raw 8x32 LE limbs: a*b mod p for secp256k1,
  * the Montgomery product a*b*2^-256 mod p for BN254. */
 void porla_debug_field_mul(int curve, const void* a, const void* b, int64_t n, void* out);
+/* Same with a selectable device routine: op 0 the product, 1 the dedicated squaring a*a, 2 the fused
+ * product-sum a*b + b*(a+b) (one reduction) -- the three multipliers the mixed addition uses. */
+void porla_debug_field_op(int curve, int op, const void* a, const void* b, int64_t n, void* out);
 /* out[i] = a[i] + b[i] on external 64-byte points (host-side group law, the code behind add_point). */
 void porla_debug_point_add_host(int curve, const void* a, const void* b, int64_t n, int point_fmt, void* out);
 

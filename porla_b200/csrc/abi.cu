@@ -552,7 +552,7 @@ void porla_scalar_mul_batch_device(const porla_table* t, const void* d_scalars, 
     PORLA_CUDA(cudaFreeAsync(d_aff, st));
 }
 
-void porla_debug_field_mul(int curve, const void* a, const void* b, int64_t n, void* out) {
+void porla_debug_field_op(int curve, int op, const void* a, const void* b, int64_t n, void* out) {
     device_init();
     std::lock_guard<std::mutex> lock(g_io_mu);
     size_t bytes = (size_t)n * 32;
@@ -560,9 +560,13 @@ void porla_debug_field_mul(int curve, const void* a, const void* b, int64_t n, v
     cudaStream_t st = g_stage.stream;
     PORLA_CUDA(cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, st));
     PORLA_CUDA(cudaMemcpyAsync(d + bytes, b, bytes, cudaMemcpyHostToDevice, st));
-    field_mul_device(curve, d, d + bytes, (uint32_t)n, d + 2 * bytes, st);
+    field_mul_device(curve, d, d + bytes, (uint32_t)n, op, d + 2 * bytes, st);
     PORLA_CUDA(cudaMemcpyAsync(out, d + 2 * bytes, bytes, cudaMemcpyDeviceToHost, st));
     PORLA_CUDA(cudaStreamSynchronize(st));
+}
+
+void porla_debug_field_mul(int curve, const void* a, const void* b, int64_t n, void* out) {
+    porla_debug_field_op(curve, 0, a, b, n, out);
 }
 
 }  // extern "C"

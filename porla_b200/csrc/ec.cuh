@@ -89,7 +89,7 @@ struct alignas(16) XYZZ {
         F ppp = p * pp;
         F qq = x * pp;
         F x3 = r.sqr() - ppp - qq.dbl();
-        y = r * (qq - x3) - y * ppp;
+        y = F::mul2add(r, qq - x3, y.neg(), ppp);   // r (qq - x3) - y ppp with one reduction
         x = x3;
         zz = zz * pp;
         zzz = zzz * ppp;

@@ -148,6 +148,176 @@ PORLA_HD uint32_t sub256(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 #endif
 }
 
+
+#ifdef __CUDA_ARCH__
+// ------------------------------------------------------------------------------------------
+// Carry-chain building blocks (device).  r points at 2k consecutive 32-bit accumulator limbs that
+// start on a 64-bit aligned slot of their row; every mad.lo.cc/madc.hi.cc pair becomes one
+// IMAD.WIDE.U32(.X).  `top` is the limb right above the chain and receives the carry-out.
+// ------------------------------------------------------------------------------------------
+PORLA_D void mac4(uint32_t* r, uint32_t& top, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t s) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(top)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(s));
+}
+PORLA_D void mac3(uint32_t* r, uint32_t& top, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t s) {
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(top)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(s));
+}
+PORLA_D void mac2(uint32_t* r, uint32_t& top, uint32_t x0, uint32_t x1, uint32_t s) {
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(top)
+        : "r"(x0), "r"(x1), "r"(s));
+}
+PORLA_D void mac1(uint32_t* r, uint32_t& top, uint32_t x0, uint32_t s) {
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(top)
+        : "r"(x0), "r"(s));
+}
+
+// T[0..15] = a * b, schoolbook on two rows: E holds the products that land on even limbs
+// (E[k] = limb k), O those on odd limbs (O[k] = limb k + 1).  Row i's carry-out goes to a limb that
+// so far holds nothing but earlier carry-outs, so no carry ever ripples further.
+PORLA_D void mul_wide_device(const uint32_t* a, const uint32_t* b, uint32_t* T) {
+    uint32_t E[16], O[16];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        uint64_t pe = (uint64_t)a[j] * b[0], po = (uint64_t)a[j + 1] * b[0];
+        E[j] = (uint32_t)pe;
+        E[j + 1] = (uint32_t)(pe >> 32);
+        O[j] = (uint32_t)po;
+        O[j + 1] = (uint32_t)(po >> 32);
+    }
+#pragma unroll
+    for (int j = 8; j < 16; j++) E[j] = O[j] = 0;
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        if (i & 1) {
+            if (i + 9 < 16) mac4(E + i + 1, E[i + 9], a[1], a[3], a[5], a[7], b[i]);
+            else { uint32_t drop = 0; mac4(E + i + 1, drop, a[1], a[3], a[5], a[7], b[i]); }
+            mac4(O + i - 1, O[i + 7], a[0], a[2], a[4], a[6], b[i]);
+        } else {
+            mac4(E + i, E[i + 8], a[0], a[2], a[4], a[6], b[i]);
+            mac4(O + i, O[i + 8], a[1], a[3], a[5], a[7], b[i]);
+        }
+    }
+    T[0] = E[0];
+    asm("add.cc.u32 %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32 %14, %29, %44;"
+        : "=r"(T[1]), "=r"(T[2]), "=r"(T[3]), "=r"(T[4]), "=r"(T[5]), "=r"(T[6]), "=r"(T[7]), "=r"(T[8]),
+          "=r"(T[9]), "=r"(T[10]), "=r"(T[11]), "=r"(T[12]), "=r"(T[13]), "=r"(T[14]), "=r"(T[15])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
+          "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+          "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
+          "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+}
+
+// T[0..15] = a^2: the 28 off-diagonal products once (same two-row scheme), doubled, plus the 8
+// squares a_i^2 in one chain: 36 multiplies instead of 64.
+PORLA_D void sqr_wide_device(const uint32_t* a, uint32_t* T) {
+    uint32_t E[16], O[16];  // E[k] = limb k (even-sum products), O[k] = limb k + 1 (odd-sum products)
+#pragma unroll
+    for (int j = 0; j < 16; j++) E[j] = O[j] = 0;
+    // odd sums i + j: chains start at limb 2i + 1 = O[2i]
+    mac4(O + 0, O[8], a[1], a[3], a[5], a[7], a[0]);    // (0,1) (0,3) (0,5) (0,7)
+    mac3(O + 2, O[8], a[2], a[4], a[6], a[1]);          // (1,2) (1,4) (1,6)
+    mac3(O + 4, O[10], a[3], a[5], a[7], a[2]);         // (2,3) (2,5) (2,7)
+    mac2(O + 6, O[10], a[4], a[6], a[3]);               // (3,4) (3,6)
+    mac2(O + 8, O[12], a[5], a[7], a[4]);               // (4,5) (4,7)
+    mac1(O + 10, O[12], a[6], a[5]);                    // (5,6)
+    mac1(O + 12, O[14], a[7], a[6]);                    // (6,7)
+    // even sums: chains start at limb 2i + 2 = E[2i + 2]
+    mac3(E + 2, E[8], a[2], a[4], a[6], a[0]);          // (0,2) (0,4) (0,6)
+    mac3(E + 4, E[10], a[3], a[5], a[7], a[1]);         // (1,3) (1,5) (1,7)
+    mac2(E + 6, E[10], a[4], a[6], a[2]);               // (2,4) (2,6)
+    mac2(E + 8, E[12], a[5], a[7], a[3]);               // (3,5) (3,7)
+    mac1(E + 10, E[12], a[6], a[4]);                    // (4,6)
+    mac1(E + 12, E[14], a[7], a[5]);                    // (5,7)
+    // S = E + (O << 32)   (limbs 1..15; limb 0 of the off-diagonal sum is zero)
+    uint32_t S[16];
+    S[0] = 0;
+    asm("add.cc.u32 %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32 %14, %29, %44;"
+        : "=r"(S[1]), "=r"(S[2]), "=r"(S[3]), "=r"(S[4]), "=r"(S[5]), "=r"(S[6]), "=r"(S[7]), "=r"(S[8]),
+          "=r"(S[9]), "=r"(S[10]), "=r"(S[11]), "=r"(S[12]), "=r"(S[13]), "=r"(S[14]), "=r"(S[15])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
+          "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+          "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
+          "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+    // T = 2 S  (funnel shifts; S < 2^511)
+#pragma unroll
+    for (int k = 15; k > 0; k--) T[k] = __funnelshift_l(S[k - 1], S[k], 1);
+    T[0] = 0;
+    // T += sum a_i^2 * 2^(64 i): one 16-limb chain
+    asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+        "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+        "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+        "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+        "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+        "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+        "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+        "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+        "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+        "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+        "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+        "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+        "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+        "madc.hi.u32 %15, %23, %23, %15;"
+        : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]),
+          "+r"(T[8]), "+r"(T[9]), "+r"(T[10]), "+r"(T[11]), "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+}
+#endif  // __CUDA_ARCH__
+
 // ------------------------------------------------------------------------------------------
 // Field element
 // ------------------------------------------------------------------------------------------
@@ -343,6 +513,156 @@ struct alignas(16) Fp {
         r.final_sub(0);
         return r;
     }
+
+    // (E, O) += x * s on the two-row layout of mont_round: O (limbs 1..8) takes the odd limbs of x,
+    // E (limbs 0..7) the even ones, E's carry-out lands on limb 8 = O[7].
+    static PORLA_D void mac_row(uint32_t* E, uint32_t* O, const uint32_t* x, uint32_t s) {
+        asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+            "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+            "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+            "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+            "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+            "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+            "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+            "madc.hi.u32 %7, %11, %12, %7;"
+            : "+r"(O[0]), "+r"(O[1]), "+r"(O[2]), "+r"(O[3]), "+r"(O[4]), "+r"(O[5]), "+r"(O[6]), "+r"(O[7])
+            : "r"(x[1]), "r"(x[3]), "r"(x[5]), "r"(x[7]), "r"(s));
+        mac4(E, O[7], x[0], x[2], x[4], x[6], s);
+    }
+
+    // Montgomery product-sum (a*b + c*d) / 2^256 mod p with ONE interleaved reduction: each CIOS round
+    // adds a*b_i and c*d_i before the reduction step.  Intermediate T < a + c + p < 2^256 and the
+    // result is below (2 p^2) / 2^256 + p < 1.5 p, so one conditional subtraction normalises it.
+    // Saves one 64-multiply reduction against two separate products (used for y3 in the mixed add).
+    static PORLA_D Fp mul2add_mont_device(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+        uint32_t even[8], odd[8];
+        mont_round2<true>(even, odd, a.v, b.v[0], c.v, d.v[0]);
+        mont_round2<false>(odd, even, a.v, b.v[1], c.v, d.v[1]);
+        mont_round2<false>(even, odd, a.v, b.v[2], c.v, d.v[2]);
+        mont_round2<false>(odd, even, a.v, b.v[3], c.v, d.v[3]);
+        mont_round2<false>(even, odd, a.v, b.v[4], c.v, d.v[4]);
+        mont_round2<false>(odd, even, a.v, b.v[5], c.v, d.v[5]);
+        mont_round2<false>(even, odd, a.v, b.v[6], c.v, d.v[6]);
+        mont_round2<false>(odd, even, a.v, b.v[7], c.v, d.v[7]);
+        Fp r;
+        merge_rows(r.v, even, odd);
+        r.final_sub(0);
+        return r;
+    }
+
+    // r = E + (O[1..7] one limb lower): the closing addition of the two-row CIOS
+    static PORLA_D void merge_rows(uint32_t* r, const uint32_t* even, const uint32_t* odd) {
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, 0;"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+            : "r"(even[0]), "r"(even[1]), "r"(even[2]), "r"(even[3]), "r"(even[4]), "r"(even[5]),
+              "r"(even[6]), "r"(even[7]), "r"(odd[1]), "r"(odd[2]), "r"(odd[3]), "r"(odd[4]),
+              "r"(odd[5]), "r"(odd[6]), "r"(odd[7]));
+    }
+
+    template <bool FIRST>
+    static PORLA_D void mont_round2(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, const uint32_t* c,
+                                    uint32_t di) {
+        mont_round_product<FIRST>(E, O, a, bi);
+        mac_row(E, O, c, di);
+        uint32_t mi = E[0] * P::kInv;
+        uint32_t m[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) m[j] = P::mod(j);
+        mac_row(E, O, m, mi);
+    }
+
+    // The product half of a CIOS round (see mont_round): slides the window down one limb and adds a * bi.
+    template <bool FIRST>
+    static PORLA_D void mont_round_product(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi) {
+        if (FIRST) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                uint64_t po = (uint64_t)a[j + 1] * bi, pe = (uint64_t)a[j] * bi;
+                O[j] = (uint32_t)po;
+                O[j + 1] = (uint32_t)(po >> 32);
+                E[j] = (uint32_t)pe;
+                E[j + 1] = (uint32_t)(pe >> 32);
+            }
+        } else {
+            asm("add.cc.u32 %0, %0, %2;\n\t"
+                "madc.lo.cc.u32 %1, %9, %13, %3;\n\t"
+                "madc.hi.cc.u32 %2, %9, %13, %4;\n\t"
+                "madc.lo.cc.u32 %3, %10, %13, %5;\n\t"
+                "madc.hi.cc.u32 %4, %10, %13, %6;\n\t"
+                "madc.lo.cc.u32 %5, %11, %13, %7;\n\t"
+                "madc.hi.cc.u32 %6, %11, %13, %8;\n\t"
+                "madc.lo.cc.u32 %7, %12, %13, 0;\n\t"
+                "madc.hi.u32 %8, %12, %13, 0;"
+                : "+r"(E[0]), "+r"(O[0]), "+r"(O[1]), "+r"(O[2]), "+r"(O[3]), "+r"(O[4]),
+                  "+r"(O[5]), "+r"(O[6]), "+r"(O[7])
+                : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(bi));
+            mac4(E, O[7], a[0], a[2], a[4], a[6], bi);
+        }
+    }
+
+    // One round of REDC on the two-row layout without a product term: slide the window down one limb
+    // (plain additions), then add mi * p so that the lowest limb cancels.
+    template <bool FIRST>
+    static PORLA_D void redc_round(uint32_t* E, uint32_t* O) {
+        if (!FIRST) {
+            // E[0] += O[1]; O[j] = O[j + 2] + carry; the top two limbs of the slid row are zero
+            asm("add.cc.u32 %0, %0, %2;\n\t"
+                "addc.cc.u32 %1, %3, 0;\n\t"
+                "addc.cc.u32 %2, %4, 0;\n\t"
+                "addc.cc.u32 %3, %5, 0;\n\t"
+                "addc.cc.u32 %4, %6, 0;\n\t"
+                "addc.cc.u32 %5, %7, 0;\n\t"
+                "addc.cc.u32 %6, %8, 0;\n\t"
+                "addc.u32 %7, 0, 0;\n\t"
+                "mov.u32 %8, 0;"
+                : "+r"(E[0]), "+r"(O[0]), "+r"(O[1]), "+r"(O[2]), "+r"(O[3]), "+r"(O[4]), "+r"(O[5]),
+                  "+r"(O[6]), "+r"(O[7]));
+        }
+        uint32_t m[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) m[j] = P::mod(j);
+        uint32_t mi = E[0] * P::kInv;
+        mac_row(E, O, m, mi);
+    }
+
+    // REDC of an 8-limb value: lo / 2^256 mod p (result <= p), i.e. the CIOS loop with the multiplier
+    // (1, 0, ..., 0).
+    static PORLA_D void redc8_device(const uint32_t* lo, uint32_t* r) {
+        uint32_t even[8], odd[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            even[j] = lo[j];
+            odd[j] = 0;
+        }
+        redc_round<true>(even, odd);
+        redc_round<false>(odd, even);
+        redc_round<false>(even, odd);
+        redc_round<false>(odd, even);
+        redc_round<false>(even, odd);
+        redc_round<false>(odd, even);
+        redc_round<false>(even, odd);
+        redc_round<false>(odd, even);
+        merge_rows(r, even, odd);
+    }
+
+    // a^2 / 2^256 mod p: 36-multiply wide square, REDC of the low half, plus the high half
+    // (REDC(lo + hi 2^256) = REDC(lo) + hi; REDC(lo) <= p and hi < p^2 / 2^256 < p / 4).
+    static PORLA_D Fp sqr_mont_device(const Fp& a) {
+        uint32_t T[16], lo[8];
+        sqr_wide_device(a.v, T);
+        redc8_device(T, lo);
+        Fp r;
+        add256(r.v, lo, T + 8);
+        r.final_sub(0);
+        return r;
+    }
 #endif
 
     // portable Montgomery CIOS (host, and reference for the device path)
@@ -447,7 +767,19 @@ struct alignas(16) Fp {
     }
 
     PORLA_HD friend Fp operator*(const Fp& a, const Fp& b) { return mul(a, b); }
-    PORLA_HD Fp sqr() const { return mul(*this, *this); }
+    PORLA_HD Fp sqr() const {
+#ifdef __CUDA_ARCH__
+        if constexpr (P::kMontgomery && !kCompact) return sqr_mont_device(*this);
+#endif
+        return mul(*this, *this);
+    }
+    // a*b + c*d (one reduction on the Montgomery device path)
+    PORLA_HD static Fp mul2add(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+#ifdef __CUDA_ARCH__
+        if constexpr (P::kMontgomery && !kCompact) return mul2add_mont_device(a, b, c, d);
+#endif
+        return mul(a, b) + mul(c, d);
+    }
 
     PORLA_HD static Fp mul_inlined(const Fp& a, const Fp& b) {
         if (P::kMontgomery) {

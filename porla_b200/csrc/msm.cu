@@ -80,7 +80,7 @@ template <class C> void precompute_impl(PointTable*, int, cudaStream_t);
 template <class C> void combine_impl(const void*, uint32_t, uint32_t, int, uint8_t*, cudaStream_t);
 template <class C> void scalar_mul_impl(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);
 template <class C> void export_impl(const void*, uint32_t, int, uint8_t*, cudaStream_t);
-template <class C> void field_mul_impl(const void*, const void*, uint32_t, void*, cudaStream_t);
+template <class C> void field_mul_impl(const void*, const void*, uint32_t, int, void*, cudaStream_t);
 
 #define DISPATCH(curve, fn, ...)                                  \
     do {                                                          \
@@ -90,6 +90,16 @@ template <class C> void field_mul_impl(const void*, const void*, uint32_t, void*
 
 // ---------------------------------------------------------------------------- window choice
 static int scalar_bits(int curve) { return curve == kCurveBn254 ? Bn254::kScalarBits : Secp256k1::kScalarBits; }
+
+// Cost of one bucket in the reduction, in units of one bucket-accumulation mixed addition
+// (measured: k_stitch + k_reduce time per bucket / k_accumulate time per pair).
+static double bucket_cost() {
+    static const double v = [] {
+        const char* e = getenv("PORLA_BUCKET_COST");
+        return e && atof(e) > 0 ? atof(e) : 4.0;
+    }();
+    return v;
+}
 
 int choose_window(int curve, uint32_t n, uint32_t nbatch) {
     const char* env = getenv("PORLA_WINDOW_BITS");
@@ -101,7 +111,7 @@ int choose_window(int curve, uint32_t n, uint32_t nbatch) {
         int nwin = (bits + 1 + c - 1) / c;
         double nb = (double)(1u << (c - 1));
         // one mixed add per (point, window); ~4 mixed-add equivalents per bucket in the reduction
-        double cost = (double)nwin * ((double)n + 4.0 * nb);
+        double cost = (double)nwin * ((double)n + bucket_cost() * nb);
         double total_buckets = (double)nbatch * nwin * nb;
         if (total_buckets > 3.0e9) continue;           // 32-bit bucket ids
         if (total_buckets * 128.0 > 48.0e9) continue;  // bucket array budget
@@ -248,10 +258,10 @@ void export_points_device(int curve, const void* d_affine, uint32_t n, int fmt, 
     DISPATCH(curve, export_impl, d_affine, n, fmt, d_out, stream);
 }
 
-void field_mul_device(int curve, const void* d_a, const void* d_b, uint32_t n, void* d_out, cudaStream_t stream) {
+void field_mul_device(int curve, const void* d_a, const void* d_b, uint32_t n, int op, void* d_out, cudaStream_t stream) {
     device_init();
     if (!n) return;
-    DISPATCH(curve, field_mul_impl, d_a, d_b, n, d_out, stream);
+    DISPATCH(curve, field_mul_impl, d_a, d_b, n, op, d_out, stream);
 }
 
 }  // namespace porla

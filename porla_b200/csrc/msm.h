@@ -95,7 +95,7 @@ void scalar_mul_device(int curve, const PointTable& table, const uint8_t* d_scal
                        uint32_t n, void* d_out_affine, cudaStream_t stream);
 void export_points_device(int curve, const void* d_affine, uint32_t n, int point_fmt, uint8_t* d_out,
                           cudaStream_t stream);
-void field_mul_device(int curve, const void* d_a, const void* d_b, uint32_t n, void* d_out,
+void field_mul_device(int curve, const void* d_a, const void* d_b, uint32_t n, int op, void* d_out,
                       cudaStream_t stream);
 
 // Per-stage CUDA-event timing of the most recent msm_device call (count, scan, scatter, accumulate,

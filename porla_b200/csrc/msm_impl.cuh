@@ -110,8 +110,17 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
 
     // accumulation geometry: slice length L (pairs per thread)
     const uint64_t pairs_cap = pairs64 ? pairs64 : 1;
-    uint32_t L = 64;
-    while (L > 4 && pairs_cap / L < 148ull * 512ull * 4ull) L >>= 1;
+    // One "wave" = the threads of k_accumulate resident at once (4 blocks x 128 threads per SM at 106
+    // registers).  L is the slice length that fills a whole number of waves with slices of at most 64
+    // pairs; small MSMs get one wave of short slices, never slices so short that stitching the cut
+    // buckets costs more than the additions (L = 4 made a 2^16-point MSM spend 6x longer in k_stitch
+    // than in k_accumulate).
+    const uint64_t wave = 148ull * 4ull * kAccThreads;
+    const uint64_t waves = (pairs_cap + wave * 64 - 1) / (wave * 64);
+    uint32_t L = (uint32_t)((pairs_cap + waves * wave - 1) / (waves * wave));
+    if (L < 16) L = 16;
+    if (L > 64) L = 64;
+    if (const char* e = getenv("PORLA_SLICE_LEN")) { if (atoi(e) >= 2) L = (uint32_t)atoi(e); }
     const uint32_t nslices_cap = (uint32_t)((pairs_cap + L - 1) / L);
     const uint32_t long_cap = (uint32_t)(pairs_cap / ((uint64_t)L * kStitchSerial)) + 2;
 
@@ -177,8 +186,12 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         k_accumulate<C><<<(nslices_cap + kAccThreads - 1) / kAccThreads, kAccThreads, 0, stream>>>(
             points, sorted, grand, L, buckets, part_head, part_tail);
         LAUNCHED();
-        k_stitch<C><<<(nslices_cap + 63) / 64, 64, 0, stream>>>(sorted, grand, L, (XC*)buckets, (const XC*)part_head,
-                                                               (const XC*)part_tail, long_count, long_runs);
+        if (getenv("PORLA_STITCH_COMPACT"))
+            k_stitch<C, FC><<<(nslices_cap + 63) / 64, 64, 0, stream>>>(sorted, grand, L, (XC*)buckets, (const XC*)part_head,
+                                                                       (const XC*)part_tail, long_count, long_runs);
+        else
+            k_stitch<C, F><<<(nslices_cap + 63) / 64, 64, 0, stream>>>(sorted, grand, L, buckets, part_head, part_tail,
+                                                                      long_count, long_runs);
         LAUNCHED();
         k_stitch_long<C><<<148, kLongThreads, 0, stream>>>(sorted, grand, L, (XC*)buckets, (const XC*)part_head, long_count,
                                                           long_runs);
@@ -262,9 +275,9 @@ void export_impl(const void* d_affine, uint32_t n, int fmt, uint8_t* d_out, cuda
 }
 
 template <class C>
-void field_mul_impl(const void* d_a, const void* d_b, uint32_t n, void* d_out, cudaStream_t stream) {
+void field_mul_impl(const void* d_a, const void* d_b, uint32_t n, int op, void* d_out, cudaStream_t stream) {
     using F = typename C::F;
-    k_field_mul<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const F*>(d_a), reinterpret_cast<const F*>(d_b), n,
+    k_field_mul<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const F*>(d_a), reinterpret_cast<const F*>(d_b), n, op,
                                                        reinterpret_cast<F*>(d_out));
     LAUNCHED();
     PORLA_CUDA(cudaGetLastError());
@@ -279,6 +292,6 @@ void field_mul_impl(const void* d_a, const void* d_b, uint32_t n, void* d_out, c
     template void precompute_impl<C>(PointTable*, int, cudaStream_t);                                                  \
     template void scalar_mul_impl<C>(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);           \
     template void export_impl<C>(const void*, uint32_t, int, uint8_t*, cudaStream_t);                                  \
-    template void field_mul_impl<C>(const void*, const void*, uint32_t, void*, cudaStream_t);
+    template void field_mul_impl<C>(const void*, const void*, uint32_t, int, void*, cudaStream_t);
 
 }  // namespace porla

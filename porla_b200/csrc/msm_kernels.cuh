@@ -366,6 +366,9 @@ k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ copy, uint32_t n,
 // slice boundary leaves a partial sum: part_head[t] (the bucket continues from slice t-1) or
 // part_tail[t] (it continues into slice t+1).  k_stitch then adds the partials of each cut bucket.
 constexpr int kAccThreads = 128;
+#ifndef PORLA_ACC_MIN_BLOCKS
+#define PORLA_ACC_MIN_BLOCKS 4
+#endif
 
 template <class C>
 PORLA_D Affine<typename C::F> load_signed_point(const Affine<typename C::F>* __restrict__ points,
@@ -376,7 +379,7 @@ PORLA_D Affine<typename C::F> load_signed_point(const Affine<typename C::F>* __r
 }
 
 template <class C>
-__global__ void __launch_bounds__(kAccThreads)
+__global__ void __launch_bounds__(kAccThreads, PORLA_ACC_MIN_BLOCKS)
 k_accumulate(const Affine<typename C::F>* __restrict__ points, const uint2* __restrict__ sorted,
              const uint32_t* __restrict__ total_pairs, uint32_t L,
              XYZZ<typename C::F>* __restrict__ buckets, XYZZ<typename C::F>* __restrict__ part_head,
@@ -421,13 +424,12 @@ k_accumulate(const Affine<typename C::F>* __restrict__ points, const uint2* __re
 // covers.  Buckets longer than L * kStitchSerial pairs are finished by k_stitch_long (a block each).
 constexpr uint32_t kStitchSerial = 48;
 
-template <class C>
+template <class C, class F>
 __global__ void __launch_bounds__(64)
 k_stitch(const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_pairs, uint32_t L,
-         XYZZ<typename C::FC>* __restrict__ buckets, const XYZZ<typename C::FC>* __restrict__ part_head,
-         const XYZZ<typename C::FC>* __restrict__ part_tail, uint32_t* __restrict__ long_count,
+         XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ part_head,
+         const XYZZ<F>* __restrict__ part_tail, uint32_t* __restrict__ long_count,
          uint2* __restrict__ long_runs) {
-    using F = typename C::FC;
     const uint32_t M = *total_pairs;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t start64 = (uint64_t)t * L;
@@ -684,12 +686,16 @@ __global__ void k_point_add(const Affine<typename C::FC>* __restrict__ a,
 }
 
 // out[i] = a[i] * b[i] on raw field elements (internal form) -- unit-test hook for the PTX path
+// op 0: a*b   1: a^2   2: a*b + b*(a+b) through the fused product-sum
 template <class C>
 __global__ void k_field_mul(const typename C::F* __restrict__ a, const typename C::F* __restrict__ b,
-                            uint32_t n, typename C::F* __restrict__ out) {
+                            uint32_t n, int op, typename C::F* __restrict__ out) {
+    using F = typename C::F;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[i] = a[i] * b[i];
+    if (op == 0) out[i] = a[i] * b[i];
+    else if (op == 1) out[i] = a[i].sqr();
+    else out[i] = F::mul2add(a[i], b[i], b[i], a[i] + b[i]);
 }
 
 }  // namespace porla

@@ -10,7 +10,7 @@ import os
 import struct
 from typing import Optional, Sequence
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmultiexp.so")
+LIB_PATH = os.environ.get("PORLA_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmultiexp.so")
 
 CURVE_BN254, CURVE_SECP256K1 = 0, 1
 SCALAR_BE32, SCALAR_LE32 = 0, 1
@@ -29,7 +29,7 @@ NEW_SYMBOLS = [
     "porla_msm_device", "porla_msm_resident", "porla_msm_plan", "porla_msm_window_sums_device",
     "porla_msm_finalize_host", "porla_msm_combine_device", "porla_msm_host", "porla_choose_window",
     "porla_scalar_mul_batch_device", "porla_secp256k1_ecmult_multi_var",
-    "porla_secp256k1_gej_serialize", "porla_debug_field_mul", "porla_debug_point_add_host", "porla_measure_pint",
+    "porla_secp256k1_gej_serialize", "porla_debug_field_mul", "porla_debug_field_op", "porla_debug_point_add_host", "porla_measure_pint",
     "porla_stage_timing_enable", "porla_stage_timing_read",
 ]
 
@@ -113,6 +113,7 @@ def load() -> C.CDLL:
         "porla_stage_timing_enable": (None, [I]),
         "porla_stage_timing_read": (I, [C.POINTER(C.c_float)]),
         "porla_debug_field_mul": (None, [I, P, P, C.c_int64, P]),
+        "porla_debug_field_op": (None, [I, I, P, P, C.c_int64, P]),
         "porla_debug_point_add_host": (None, [I, P, P, C.c_int64, I, P]),
     }
     for name, (res, args) in sig.items():

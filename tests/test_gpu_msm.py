@@ -57,6 +57,29 @@ def test_field_mul_matches_bigint(curve, c):
         assert got == a[i] * b[i] * rinv % c.p, i
 
 
+@pytest.mark.parametrize("curve,c", [(pb.CURVE_BN254, BN), (pb.CURVE_SECP256K1, SE)])
+@pytest.mark.parametrize("op", [1, 2])
+def test_field_square_and_product_sum_match_bigint(curve, c, op):
+    """The dedicated squaring (36 products) and the fused product-sum a*b + b*(a+b) (one reduction)
+    that the bucket update uses, on edge values and random residues."""
+    rnd = random.Random(10 + op)
+    n = 4096
+    a = [rnd.randrange(c.p) for _ in range(n)]
+    b = [rnd.randrange(c.p) for _ in range(n)]
+    edge = [0, 1, 2, c.p - 1, c.p - 2, (1 << 255) % c.p, (1 << 32) - 1, ((1 << 256) - 1) % c.p, c.p >> 1]
+    for i, (x, y) in enumerate((x, y) for x in edge for y in edge):
+        a[i], b[i] = x, y
+    le = lambda v: v.to_bytes(32, "little")
+    ab, bb, ob = bytearray(b"".join(map(le, a))), bytearray(b"".join(map(le, b))), bytearray(32 * n)
+    pb.load().porla_debug_field_op(curve, op, (C.c_ubyte * len(ab)).from_buffer(ab), (C.c_ubyte * len(bb)).from_buffer(bb), n,
+                                   (C.c_ubyte * len(ob)).from_buffer(ob))
+    rinv = pow(1 << 256, -1, c.p) if c is BN else 1
+    for i in range(n):
+        got = int.from_bytes(ob[32 * i:32 * i + 32], "little")
+        want = a[i] * a[i] if op == 1 else a[i] * b[i] + b[i] * ((a[i] + b[i]) % c.p)
+        assert got == want * rinv % c.p, (i, op)
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 17, 128, 766, 1500])
 def test_compute_multi_exp_matches_oracle(n):
     rnd = random.Random(n)
