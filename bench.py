@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log2n", type=int, default=int(os.environ.get("PORLA_BENCH_LOG2N", "20")))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample-log2n", type=int, default=16)
+    ap.add_argument("--cpu-sample-log2n", type=int, default=22,
+                    help="log2 size of the CPU-baseline sample (bounded by --log2n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", default=os.environ.get("PORLA_BENCH_SWEEP", "16,24"),
                     help="extra sizes (log2) timed at N=1 and reported under 'sweep'")
@@ -78,8 +79,8 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    log2s = min(args.log2n, args.cpu_sample_log2n + 2)
-    steps = max(1, min(args.steps, 3))
+    log2s = min(args.log2n, args.cpu_sample_log2n)
+    steps = max(1, min(args.steps, 5))
     rate, sec = cpu_port_rate(log2s, threads, steps=steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "points/s", "n_gpus": args.gpus,
@@ -98,23 +99,51 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
+    """Samples SM clock, power and throttle reasons DURING the timed region.  NVML (a few hundred
+    microseconds per sample) so that even a 50 ms region gets tens of samples; falls back to
+    nvidia-smi (the recipe's clocks line) when NVML is unusable."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1e3
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        bit = lambda name: bool(r & getattr(n, name, 0))
+        return [str(sm), str(self.sm_max), "%.1f" % pw,
+                "Active" if bit("nvmlClocksThrottleReasonHwSlowdown") else "Not Active",
+                "Active" if bit("nvmlClocksThrottleReasonHwThermalSlowdown") else "Not Active",
+                "Active" if bit("nvmlClocksThrottleReasonSwThermalSlowdown") else "Not Active",
+                "Active" if bit("nvmlClocksThrottleReasonSwPowerCap") else "Not Active"]
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.samples.append(self.sample_nvml())
+                    time.sleep(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
-                pass
-            time.sleep(0.05)
+                self.nvml = None
+            time.sleep(0.02)
 
     def summary(self):
         if not self.samples:
@@ -125,7 +154,8 @@ class ClockSampler(threading.Thread):
             if any(len(s) > col and s[col].lower().startswith("active") for s in self.samples):
                 reasons.append(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(self.samples[0][1])),
-                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples), "reasons": reasons}
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples), "reasons": reasons,
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------ our arm

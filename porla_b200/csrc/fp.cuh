@@ -730,7 +730,12 @@ struct alignas(16) Fp {
             prev = t[8 + i];
         }
         c += prev;  // value of limbs 8.. (< 2^34)
-        // fold 2: add c*(2^32 + 977)
+        return fold_special_tail(r, c);
+    }
+
+    // Folds 2 and 3 of the special-form reduction: r (8 limbs) + c * (2^32 + 977), c < 2^34, then one
+    // more wrap if that carried past 2^256, then the conditional subtraction.
+    PORLA_HD static Fp fold_special_tail(uint32_t* r, uint64_t c) {
         uint64_t d = (c & 0xffffffffull) * 977u + r[0];
         r[0] = (uint32_t)d;
         d >>= 32;
@@ -766,10 +771,53 @@ struct alignas(16) Fp {
         return out;
     }
 
+#ifdef __CUDA_ARCH__
+    // Device special-form reduction of a 16-limb product T for p = 2^256 - (2^32 + 977):
+    // fold 1 is  lo + hi * 977 + (hi << 32)  on the two-row layout of mul_wide_device (the even limbs
+    // of hi times 977 land on 64-bit aligned slots of `acc`, the odd ones on those of row O, which
+    // starts out holding hi itself = the (hi << 32) term); IMAD.WIDE carry chains throughout.
+    static PORLA_D Fp fold_special_device(const uint32_t* T) {
+        uint32_t acc[10], O[9];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            acc[i] = T[i];
+            O[i] = T[8 + i];
+        }
+        acc[8] = 0;
+        O[8] = 0;
+        mac4(acc, acc[8], T[8], T[10], T[12], T[14], 977u);
+        mac4(O, O[8], T[9], T[11], T[13], T[15], 977u);
+        asm("add.cc.u32 %0, %0, %9;\n\t"
+            "addc.cc.u32 %1, %1, %10;\n\t"
+            "addc.cc.u32 %2, %2, %11;\n\t"
+            "addc.cc.u32 %3, %3, %12;\n\t"
+            "addc.cc.u32 %4, %4, %13;\n\t"
+            "addc.cc.u32 %5, %5, %14;\n\t"
+            "addc.cc.u32 %6, %6, %15;\n\t"
+            "addc.cc.u32 %7, %7, %16;\n\t"
+            "addc.u32 %8, %17, 0;"
+            : "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+              "+r"(acc[8]), "=r"(acc[9])
+            : "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]));
+        return fold_special_tail(acc, (uint64_t)acc[8] + ((uint64_t)acc[9] << 32));
+    }
+    static PORLA_D Fp mul_special_device(const Fp& a, const Fp& b) {
+        uint32_t T[16];
+        mul_wide_device(a.v, b.v, T);
+        return fold_special_device(T);
+    }
+    static PORLA_D Fp sqr_special_device(const Fp& a) {
+        uint32_t T[16];
+        sqr_wide_device(a.v, T);
+        return fold_special_device(T);
+    }
+#endif
+
     PORLA_HD friend Fp operator*(const Fp& a, const Fp& b) { return mul(a, b); }
     PORLA_HD Fp sqr() const {
 #ifdef __CUDA_ARCH__
         if constexpr (P::kMontgomery && !kCompact) return sqr_mont_device(*this);
+        if constexpr (!P::kMontgomery && !kCompact) return sqr_special_device(*this);
 #endif
         return mul(*this, *this);
     }
@@ -789,7 +837,11 @@ struct alignas(16) Fp {
             return mul_mont_portable(a, b);
 #endif
         } else {
+#ifdef __CUDA_ARCH__
+            return mul_special_device(a, b);
+#else
             return mul_special_portable(a, b);
+#endif
         }
     }
     PORLA_HD static Fp mul(const Fp& a, const Fp& b) {

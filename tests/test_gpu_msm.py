@@ -47,6 +47,11 @@ def test_field_mul_matches_bigint(curve, c):
     a[0], b[0] = c.p - 1, c.p - 1
     a[1], b[1] = 0, 5
     a[2], b[2] = 1, c.p - 1
+    # values that drive the special-form folds / the last Montgomery subtraction to their corners
+    edge = [0, 1, 2, c.p - 1, c.p - 2, (1 << 255) % c.p, (1 << 32) - 1, ((1 << 256) - 1) % c.p, c.p >> 1,
+            (1 << 224) - 1, c.p - (1 << 32), (c.p + 1) // 2]
+    for i, (x, y) in enumerate((x, y) for x in edge for y in edge):
+        a[3 + i], b[3 + i] = x, y
     le = lambda v: v.to_bytes(32, "little")
     ab, bb, ob = bytearray(b"".join(map(le, a))), bytearray(b"".join(map(le, b))), bytearray(32 * n)
     pb.load().porla_debug_field_mul(curve, (C.c_ubyte * len(ab)).from_buffer(ab), (C.c_ubyte * len(bb)).from_buffer(bb), n,
