@@ -139,7 +139,9 @@ inline G2A g2_add(const G2A& p, const G2A& q, Fq2* lambda = nullptr) {
 inline G2A g2_mul(const G2A& p, const Fr& k_internal) {
     Fr k = k_internal.from_internal();
     G2A r;
-    for (int i = 255; i >= 0; i--) {
+    int top = 255;  // skip leading zeros: kzg.Verify multiplies by the 64-bit opening point (main.go:157)
+    while (top >= 0 && !((k.v[top >> 5] >> (top & 31)) & 1u)) top--;
+    for (int i = top; i >= 0; i--) {
         r = g2_add(r, r);
         if ((k.v[i >> 5] >> (i & 31)) & 1u) r = g2_add(r, p);
     }

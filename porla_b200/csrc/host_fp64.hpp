@@ -176,6 +176,7 @@ struct alignas(16) Fp64 {
     static Fp64 mul(const Fp64& a, const Fp64& b) { return P::kMontgomery ? mul_mont(a, b) : mul_special(a, b); }
     friend Fp64 operator*(const Fp64& a, const Fp64& b) { return mul(a, b); }
     Fp64 sqr() const { return mul(*this, *this); }
+    static Fp64 mul2add(const Fp64& a, const Fp64& b, const Fp64& c, const Fp64& d) { return mul(a, b) + mul(c, d); }
 
     Fp64 to_internal() const {
         if (!P::kMontgomery) return *this;
