@@ -149,6 +149,18 @@ int porla_stage_timing_read(float* ms_out);
 void porla_scalar_mul_batch_device(const porla_table* t, const void* d_scalars, int64_t n,
                                    int scalar_fmt, int out_fmt, void* d_out, void* cuda_stream);
 
+/* One radix-2 butterfly stage of Porla's "FFT in the exponent" (CRebuild / mix, Server.hpp:1548-1687,
+ * :1209-1328; Client.hpp:921-976), which the reference issues as mult_point + add_point + neg_point +
+ * add_point per butterfly (main.go:196-222): for every j < m/2 and k = j, j + m, j + 2m, ... < n
+ *       t = w_j * P[k + m/2];   P[k] <- P[k] + t;   P[k + m/2] <- P[k] - t
+ * `twiddles` holds the m/2 scalars w_j (32 bytes each, reduced mod the group order).  m is a power of
+ * two >= 2 dividing n.  The device form works in place on a resident table (all log2 n stages of a
+ * rebuild run without leaving HBM: porla_table_create, one call per stage, porla_table_export); the
+ * host-buffer form does one stage on n x 64-byte gnark Marshal records in place.  Either curve. */
+void porla_butterfly_stage_device(porla_table* t, int64_t m, const void* twiddles, int scalar_fmt,
+                                  int twiddles_on_device, void* cuda_stream);
+extern void bn254_butterfly_stage(GoSlice* points, GoInt n, GoInt m, GoSlice* twiddles);
+
 /* ---- secp256k1 (IPA mode).  Mirrors of the reference structs (field_5x52.h:12-21,
  * group.h:13-28, scalar_4x64.h:13-15, util.h:19-22, ecmult.h:32). */
 typedef struct { uint64_t n[5]; } porla_secp256k1_fe;

@@ -26,6 +26,7 @@ from .lib import (  # noqa: F401
     bn254_multi_exp,
     bn254_multi_exp_batch,
     bn254_compare,
+    bn254_butterfly_stage,
     Kzg,
     Table,
     msm_host,

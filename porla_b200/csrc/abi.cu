@@ -552,6 +552,37 @@ void porla_scalar_mul_batch_device(const porla_table* t, const void* d_scalars, 
     PORLA_CUDA(cudaFreeAsync(d_aff, st));
 }
 
+void porla_butterfly_stage_device(porla_table* t, int64_t m, const void* twiddles, int scalar_fmt, int twiddles_on_device,
+                                  void* cuda_stream) {
+    if (m < 2 || (m & (m - 1)) || (int64_t)t->t.n % m) die("porla_butterfly_stage_device: m must be a power of two dividing the table length");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const uint8_t* d_tw = (const uint8_t*)twiddles;
+    uint8_t* d_tmp = nullptr;
+    if (!twiddles_on_device) {
+        PORLA_CUDA(cudaMallocAsync(&d_tmp, (size_t)(m / 2) * 32, st));
+        PORLA_CUDA(cudaMemcpyAsync(d_tmp, twiddles, (size_t)(m / 2) * 32, cudaMemcpyHostToDevice, st));
+        d_tw = d_tmp;
+    }
+    butterfly_stage_device(&t->t, (uint32_t)m, d_tw, scalar_fmt == PORLA_SCALAR_BE32, st);
+    if (d_tmp) {
+        PORLA_CUDA(cudaFreeAsync(d_tmp, st));
+        PORLA_CUDA(cudaStreamSynchronize(st));   // the host twiddle buffer may be reused by the caller
+    }
+}
+
+void bn254_butterfly_stage(GoSlice* points, GoInt n, GoInt m, GoSlice* twiddles) {
+    if (n < 0 || points->len < n * 64 || twiddles->len < (m / 2) * 32)
+        die("bn254_butterfly_stage: slices shorter than n points / m/2 twiddles");
+    if (n == 0) return;
+    device_init();
+    g_stage.init();
+    porla_table t;
+    table_import_host(kCurveBn254, (const uint8_t*)points->data, PORLA_POINT_BE64, (uint32_t)n, &t.t, g_stage.stream);
+    porla_butterfly_stage_device(&t, m, twiddles->data, PORLA_SCALAR_BE32, 0, g_stage.stream);
+    porla_table_export(&t, PORLA_POINT_BE64, points->data, 0, g_stage.stream);
+    table_free(&t.t);
+}
+
 void porla_debug_field_op(int curve, int op, const void* a, const void* b, int64_t n, void* out) {
     device_init();
     std::lock_guard<std::mutex> lock(g_io_mu);

@@ -80,6 +80,7 @@ template <class C> void precompute_impl(PointTable*, int, cudaStream_t);
 template <class C> void combine_impl(const void*, uint32_t, uint32_t, int, uint8_t*, cudaStream_t);
 template <class C> void scalar_mul_impl(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);
 template <class C> void export_impl(const void*, uint32_t, int, uint8_t*, cudaStream_t);
+template <class C> void butterfly_impl(PointTable*, uint32_t, const uint8_t*, int, cudaStream_t);
 template <class C> void field_mul_impl(const void*, const void*, uint32_t, int, void*, cudaStream_t);
 
 #define DISPATCH(curve, fn, ...)                                  \
@@ -250,6 +251,17 @@ void scalar_mul_device(int curve, const PointTable& table, const uint8_t* d_scal
     device_init();
     if (!n) return;
     DISPATCH(curve, scalar_mul_impl, table, d_scalars, scalar_be, n, d_out_affine, stream);
+}
+
+void butterfly_stage_device(PointTable* t, uint32_t m, const uint8_t* d_twiddles, int scalar_be, cudaStream_t stream) {
+    device_init();
+    if (t->d_fb_points) {   // the expansion describes the old points
+        PORLA_CUDA(cudaStreamSynchronize(stream));
+        PORLA_CUDA(cudaFree(t->d_fb_points));
+        t->d_fb_points = nullptr;
+        t->fb_c = t->fb_nwin = 0;
+    }
+    DISPATCH(t->curve, butterfly_impl, t, m, d_twiddles, scalar_be, stream);
 }
 
 void export_points_device(int curve, const void* d_affine, uint32_t n, int fmt, uint8_t* d_out, cudaStream_t stream) {

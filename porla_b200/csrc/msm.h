@@ -93,6 +93,10 @@ void msm_combine_device(int curve, const void* d_parts, uint32_t count, uint32_t
 // Elementwise batched kernels.
 void scalar_mul_device(int curve, const PointTable& table, const uint8_t* d_scalars, int scalar_be,
                        uint32_t n, void* d_out_affine, cudaStream_t stream);
+// One radix-2 butterfly stage of the "FFT in the exponent", in place on a resident table whose length is a
+// multiple of m (m a power of two >= 2): see k_butterfly.  d_twiddles: m/2 scalars of 32 bytes on the device.
+// Invalidates the table's fixed-base expansion.
+void butterfly_stage_device(PointTable* t, uint32_t m, const uint8_t* d_twiddles, int scalar_be, cudaStream_t stream);
 void export_points_device(int curve, const void* d_affine, uint32_t n, int point_fmt, uint8_t* d_out,
                           cudaStream_t stream);
 void field_mul_device(int curve, const void* d_a, const void* d_b, uint32_t n, int op, void* d_out,

@@ -267,6 +267,21 @@ void scalar_mul_impl(const PointTable& table, const uint8_t* d_scalars, int scal
 }
 
 template <class C>
+void butterfly_impl(PointTable* t, uint32_t m, const uint8_t* d_twiddles, int scalar_be, cudaStream_t stream) {
+    using F = typename C::FC;
+    const uint32_t nb = t->n / 2;
+    if (!nb) return;
+    if (!t->d_flags) {   // outputs may be infinity (A0 = +-t): from now on the table carries flags
+        PORLA_CUDA(cudaMalloc(&t->d_flags, t->n));
+        PORLA_CUDA(cudaMemsetAsync(t->d_flags, 0, t->n, stream));
+    }
+    k_butterfly<C><<<(nb + 127) / 128, 128, 0, stream>>>(reinterpret_cast<Affine<F>*>(t->d_points), t->d_flags, t->n, m,
+                                                        d_twiddles, scalar_be);
+    LAUNCHED();
+    PORLA_CUDA(cudaGetLastError());
+}
+
+template <class C>
 void export_impl(const void* d_affine, uint32_t n, int fmt, uint8_t* d_out, cudaStream_t stream) {
     using F = typename C::F;
     k_export_points<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<F>*>(d_affine), n, fmt, d_out);
@@ -292,6 +307,7 @@ void field_mul_impl(const void* d_a, const void* d_b, uint32_t n, int op, void* 
     template void precompute_impl<C>(PointTable*, int, cudaStream_t);                                                  \
     template void scalar_mul_impl<C>(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);           \
     template void export_impl<C>(const void*, uint32_t, int, uint8_t*, cudaStream_t);                                  \
+    template void butterfly_impl<C>(PointTable*, uint32_t, const uint8_t*, int, cudaStream_t);                         \
     template void field_mul_impl<C>(const void*, const void*, uint32_t, int, void*, cudaStream_t);
 
 }  // namespace porla

@@ -672,6 +672,60 @@ k_scalar_mul(const Affine<typename C::FC>* __restrict__ points, uint32_t npoints
     st16(out + i, r.to_affine());
 }
 
+// One radix-2 stage of Porla's "FFT in the exponent" (CRebuild / mix: /root/reference/porla/Server/
+// Server.hpp:1548-1687 and :1209-1328, Client.hpp:921-976): for every j < m/2 and k = j, j + m, ... < n
+//     t = w_j * P[k + m/2];   P[k] <- P[k] + t;   P[k + m/2] <- P[k] - t
+// which the reference issues as mult_point + add_point + neg_point + add_point per butterfly
+// (main.go:196-222) or secp256k1_ecmult + 2 gej_add_var in IPA mode.  One thread per butterfly, in
+// place on the resident affine table; both outputs share one field inversion.  flags[] (1 =
+// infinity) is rewritten so that MSMs over the table keep skipping infinities.
+template <class C>
+__global__ void __launch_bounds__(128)
+k_butterfly(Affine<typename C::FC>* __restrict__ pts, uint8_t* __restrict__ flags, uint32_t n, uint32_t m,
+            const uint8_t* __restrict__ twiddles, int big_endian) {
+    using F = typename C::FC;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t m2 = m >> 1;
+    if (b >= n / 2) return;
+    const uint32_t j = b % m2, k = (b / m2) * m + j;
+    uint32_t s[8];
+    load_u256(twiddles, j, big_endian, s);
+    reduce_scalar<C>(s);
+    const Affine<F> a0 = ld16(pts + k), a1 = ld16(pts + k + m2);
+    XYZZ<F> t = XYZZ<F>::inf();
+    if (!a1.is_inf()) {
+        int top = 255;
+        while (top >= 0 && !((s[top >> 5] >> (top & 31)) & 1u)) top--;
+        for (int i = top; i >= 0; i--) {
+            t = t.dbl();
+            if ((s[i >> 5] >> (i & 31)) & 1u) t.madd(a1);
+        }
+    }
+    XYZZ<F> r0 = t, r1 = t.neg();
+    r0.madd(a0);
+    r1.madd(a0);
+    // joint normalisation: 1/zzz0 and 1/zzz1 from one inversion of their product
+    Affine<F> o0 = Affine<F>::inf(), o1 = Affine<F>::inf();
+    if (r0.is_inf() || r1.is_inf()) {
+        o0 = r0.to_affine();
+        o1 = r1.to_affine();
+    } else {
+        F inv = (r0.zzz * r1.zzz).inverse();
+        F i0 = inv * r1.zzz, i1 = inv * r0.zzz;
+        F t0 = r0.zz * i0, t1 = r1.zz * i1;   // 1/zz = (zz/zzz)^2
+        o0.x = r0.x * t0.sqr();
+        o0.y = r0.y * i0;
+        o1.x = r1.x * t1.sqr();
+        o1.y = r1.y * i1;
+    }
+    st16(pts + k, o0);
+    st16(pts + k + m2, o1);
+    if (flags) {
+        flags[k] = o0.is_inf() ? 1 : 0;
+        flags[k + m2] = o1.is_inf() ? 1 : 0;
+    }
+}
+
 // out[i] = a[i] + b[i]
 template <class C>
 __global__ void k_point_add(const Affine<typename C::FC>* __restrict__ a,

@@ -31,6 +31,7 @@ NEW_SYMBOLS = [
     "porla_scalar_mul_batch_device", "porla_secp256k1_ecmult_multi_var",
     "porla_secp256k1_gej_serialize", "porla_debug_field_mul", "porla_debug_field_op", "porla_debug_point_add_host", "porla_measure_pint",
     "porla_stage_timing_enable", "porla_stage_timing_read",
+    "porla_butterfly_stage_device", "bn254_butterfly_stage",
 ]
 
 
@@ -112,6 +113,8 @@ def load() -> C.CDLL:
         "porla_measure_pint": (C.c_double, [I, C.c_double]),
         "porla_stage_timing_enable": (None, [I]),
         "porla_stage_timing_read": (I, [C.POINTER(C.c_float)]),
+        "porla_butterfly_stage_device": (None, [P, C.c_int64, P, I, I, P]),
+        "bn254_butterfly_stage": (None, [GS, LL, LL, GS]),
         "porla_debug_field_mul": (None, [I, P, P, C.c_int64, P]),
         "porla_debug_field_op": (None, [I, I, P, P, C.c_int64, P]),
         "porla_debug_point_add_host": (None, [I, P, P, C.c_int64, I, P]),
@@ -179,6 +182,12 @@ def bn254_multi_exp_batch(points: bytes, scalars: bytes, length: int, batch: int
     sc, pt = bytearray(scalars), bytearray(points)
     load().compute_multi_exp_batch(C.byref(_slice(sc)), C.byref(_slice(pt)), length, batch, C.byref(_slice(out)))
     return bytes(out)
+
+
+def bn254_butterfly_stage(points: bytearray, n: int, m: int, twiddles: bytes) -> None:
+    """One stage of the FFT in the exponent, in place on n 64-byte MAC_Blocks (the loop body of
+    Server.hpp:1577-1608 for every butterfly of the stage): twiddles = m/2 bn254_scalars (32 B BE)."""
+    load().bn254_butterfly_stage(C.byref(_slice(points)), n, m, C.byref(_slice(bytearray(twiddles))))
 
 
 def bn254_compare(a: bytes, b: bytes) -> bool:
@@ -298,6 +307,12 @@ class Table:
         load().porla_msm_resident(C.c_void_p(self.handle), C.c_void_p(d_scalars), n, scalar_fmt, window_bits, out_fmt,
                                   C.cast(out, C.c_void_p), C.c_void_p(stream))
         return bytes(out)
+
+    def butterfly_stage(self, m: int, twiddles: bytes, scalar_fmt: int = SCALAR_BE32, stream: int = 0) -> None:
+        """In-place radix-2 butterfly stage over the resident table (host twiddles, m/2 x 32 bytes)."""
+        tw = bytearray(twiddles)
+        load().porla_butterfly_stage_device(C.c_void_p(self.handle), m, C.cast((C.c_ubyte * len(tw)).from_buffer(tw), C.c_void_p),
+                                            scalar_fmt, 0, C.c_void_p(stream))
 
     def destroy(self) -> None:
         if self.handle:

@@ -19,7 +19,7 @@ def declared_symbols():
         if n in ("defined", "sizeof") or n.startswith("porla_secp256k1_ecmult_multi_callback"):
             continue
         names.add(n)
-    return {n for n in names if n.startswith("porla_") or n in L.LEGACY_SYMBOLS or n.startswith("compute_")} - {"fn"}
+    return {n for n in names if n.startswith("porla_") or n in L.LEGACY_SYMBOLS or n.startswith("compute_") or n.startswith("bn254_")} - {"fn"}
 
 
 def test_library_exports_every_declared_symbol():

@@ -260,3 +260,60 @@ def test_fixed_base_tables_match_general_path(curve, c):
         wantp = O.mul(c, sum(s * k for s, k in zip(ss[:m], ks[:m])) % c.n, G)
         assert tab.msm_resident(d_sc.data_ptr(), m, scalar_fmt=pb.SCALAR_LE32) == enc(wantp)
     tab.destroy()
+
+
+# ------------------------------------------------------------------ FFT in the exponent
+def _butterfly_oracle(c, pts, m, tw):
+    """The loop body of Server.hpp:1577-1608 for every butterfly of one stage, on big-int points."""
+    out = list(pts)
+    m2 = m // 2
+    for j in range(m2):
+        for k in range(j, len(pts), m):
+            t = O.mul(c, tw[j] % c.n, pts[k + m2])
+            out[k] = O.add(c, pts[k], t)
+            out[k + m2] = O.add(c, pts[k], O.neg(c, t))
+    return out
+
+
+def test_butterfly_stage_host_buffers_match_oracle_with_edge_cases():
+    rnd = random.Random(77)
+    n, m = 16, 4
+    pts = bn254_points(n)
+    tw = [rnd.randrange(1 << 256), 1]                     # >= r: reduced like fr.SetBytes (main.go:208)
+    pts[2] = None                                          # A1 = infinity (alignment MACs start as infinity)
+    pts[4] = None                                          # A0 = infinity
+    pts[9] = O.mul(BN, 1, pts[11])                         # j = 1 (w = 1): A0 == t  -> doubling / A0 - t = infinity
+    pts[13] = O.neg(BN, pts[15])                           # A0 == -t -> A0 + t = infinity
+    buf = bytearray(b"".join(O.bn254_marshal(P) for P in pts))
+    pb.bn254_butterfly_stage(buf, n, m, b"".join(be(t) for t in tw))
+    want = _butterfly_oracle(BN, pts, m, tw)
+    assert bytes(buf) == b"".join(O.bn254_marshal(P) for P in want)
+
+
+@pytest.mark.parametrize("curve,c", [(pb.CURVE_BN254, BN), (pb.CURVE_SECP256K1, SE)])
+def test_fft_in_exponent_all_stages_resident(curve, c):
+    """All log2 n stages on a resident table, then an MSM over the transformed table (the infinity flags
+    written by the butterflies must be honoured)."""
+    rnd = random.Random(5 + curve)
+    n = 32
+    G = (c.gx, c.gy)
+    pts = [O.mul(c, rnd.randrange(1, c.n), G) for _ in range(n)]
+    pts[5] = None
+    enc = lambda L: b"".join(bytes(64) if P is None else be(P[0]) + be(P[1]) for P in L)
+    t = pb.Table.from_host(curve, enc(pts))
+    cur = list(pts)
+    m = 2
+    while m <= n:
+        tw = [rnd.randrange(c.n) for _ in range(m // 2)]
+        tw[0] = 1
+        t.butterfly_stage(m, b"".join(be(x) for x in tw))
+        cur = _butterfly_oracle(c, cur, m, tw)
+        m *= 2
+    assert t.export() == enc(cur)
+    import torch
+    sc = [rnd.randrange(c.n) for _ in range(n)]
+    d_sc = torch.frombuffer(bytearray(b"".join(be(s) for s in sc)), dtype=torch.uint8).cuda()
+    got = t.msm_resident(d_sc.data_ptr(), n)
+    exp = O.msm(c, sc, cur)
+    assert got == (bytes(64) if exp is None else be(exp[0]) + be(exp[1]))
+    t.destroy()
