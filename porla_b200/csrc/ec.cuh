@@ -158,7 +158,8 @@ using SecpFpCompact = Fp<Secp256k1FpParams, true>;
 struct Bn254 {
     using F = Bn254Fp;
     using FC = Bn254FpCompact;  // same layout, non-inlined multiplier (cold kernels)
-    static constexpr int kScalarBits = 254;
+    static constexpr int kScalarBits = 254;     // bits the window recoder covers (r < 2^254)
+    static constexpr bool kHalveScalar = false;
     // r (scalar field order), little-endian 32-bit limbs
     PORLA_HD static constexpr uint32_t order(int i) {
         constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
@@ -171,7 +172,10 @@ struct Bn254 {
 struct Secp256k1 {
     using F = SecpFp;
     using FC = SecpFpCompact;
-    static constexpr int kScalarBits = 256;
+    // n is just below 2^256: scalars above n/2 are recoded as -(n - s), so 255 magnitude bits (plus the
+    // carry of the signed digits) span exactly 16 windows of 16 bits instead of 17 with a 1-bit top window.
+    static constexpr int kScalarBits = 255;
+    static constexpr bool kHalveScalar = true;
     PORLA_HD static constexpr uint32_t order(int i) {
         constexpr uint32_t m[8] = {0xd0364141u, 0xbfd25e8cu, 0xaf48a03bu, 0xbaaedce6u,
                                    0xfffffffeu, 0xffffffffu, 0xffffffffu, 0xffffffffu};

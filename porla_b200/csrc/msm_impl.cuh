@@ -99,11 +99,14 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     const uint32_t nbt = (uint32_t)nbt64;
     const uint32_t ntiles = (nbt + kScanTile - 1) / kScanTile;
 
-    // reduction geometry: enough threads to fill the machine, chunks as long as that allows
-    // (each thread pays a fixed ~20-operation weighting step, so chunks below 16 buckets waste work)
+    // reduction geometry: every thread pays a fixed ~17-addition weighting step on top of 2 additions per
+    // bucket, so long chunks waste less work, but the kernel is latency-bound until the machine is full
+    // (one dependent XYZZ addition is ~7 us on a lone warp).  Measured optimum (2^16 .. 2^22 points): about
+    // 24 k threads in total; chunks of 4 .. 64 buckets.
     uint32_t chunk = 64;
-    while (chunk > 16 && (uint64_t)nbt / chunk < 148ull * 256ull) chunk >>= 1;
+    while (chunk > 4 && (uint64_t)nbt / chunk < 24576ull) chunk >>= 1;
     while (chunk > 4 && sh.nbuckets / chunk < 4) chunk >>= 1;
+    if (const char* e = getenv("PORLA_REDUCE_CHUNK")) { if (atoi(e) >= 1) chunk = (uint32_t)atoi(e); }
     if (chunk > sh.nbuckets) chunk = sh.nbuckets;
     uint32_t threads_per_slot = (sh.nbuckets + chunk - 1) / chunk;  // nbuckets and chunk are powers of two
     uint32_t blocks_per_slot = (threads_per_slot + kRedThreads - 1) / kRedThreads;
@@ -122,7 +125,11 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     if (L > 64) L = 64;
     if (const char* e = getenv("PORLA_SLICE_LEN")) { if (atoi(e) >= 2) L = (uint32_t)atoi(e); }
     const uint32_t nslices_cap = (uint32_t)((pairs_cap + L - 1) / L);
-    const uint32_t long_cap = (uint32_t)(pairs_cap / ((uint64_t)L * kStitchSerial)) + 2;
+    // One serial XYZZ addition is ~7 us of latency: with few slices in flight (small MSMs) a bucket cut into
+    // dozens of slices is better finished by a cooperating block; with the machine full, the serial loop in
+    // every owner thread has the higher throughput (2^24, c = 20: 16 k top-window buckets of 17 slices).
+    const uint32_t serial_limit = nslices_cap < 200000u ? kStitchSerialSmall : kStitchSerial;
+    const uint32_t long_cap = (uint32_t)(pairs_cap / ((uint64_t)L * serial_limit)) + 2;
 
     std::lock_guard<std::mutex> lock(g_engine_mu);
     size_t need = Arena::padded(nbt, 4) * 2 + Arena::padded(ntiles + 1, 4) + 512 +
@@ -188,10 +195,10 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         LAUNCHED();
         if (getenv("PORLA_STITCH_COMPACT"))
             k_stitch<C, FC><<<(nslices_cap + 63) / 64, 64, 0, stream>>>(sorted, grand, L, (XC*)buckets, (const XC*)part_head,
-                                                                       (const XC*)part_tail, long_count, long_runs);
+                                                                       (const XC*)part_tail, long_count, long_runs, serial_limit);
         else
             k_stitch<C, F><<<(nslices_cap + 63) / 64, 64, 0, stream>>>(sorted, grand, L, buckets, part_head, part_tail,
-                                                                      long_count, long_runs);
+                                                                      long_count, long_runs, serial_limit);
         LAUNCHED();
         k_stitch_long<C><<<148, kLongThreads, 0, stream>>>(sorted, grand, L, (XC*)buckets, (const XC*)part_head, long_count,
                                                           long_runs);

@@ -224,6 +224,18 @@ k_digits(const uint8_t* __restrict__ scalars, int big_endian,
         load_u256(scalars, idx, big_endian, s);
         s[8] = 0;
         reduce_scalar<C>(s);
+        uint32_t flip = 0;   // s > order/2: use order - s and the negated point
+        if (C::kHalveScalar) {
+            uint32_t ord[8], t[8], u[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) ord[k] = C::order(k);
+            sub256(t, ord, s);                 // order - s  (s < order)
+            if (sub256(u, t, s)) {             // order - s < s
+                flip = 1;
+#pragma unroll
+                for (int k = 0; k < 8; k++) s[k] = t[k];
+            }
+        }
         uint32_t carry = 0;
         // general: one bucket set per (msm, window); fixed-base: one per msm, the window selects the
         // pre-multiplied copy 2^(c*w) * P_i of the point instead
@@ -241,9 +253,10 @@ k_digits(const uint8_t* __restrict__ scalars, int big_endian,
                     uint32_t lo = s[word < 8 ? word : 8];
                     uint32_t hi = s[word < 7 ? word + 1 : 8];
                     uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry;
-                    uint32_t neg = d > half;
-                    carry = neg;
-                    uint32_t mag = neg ? ((1u << sh.c) - d) : d;
+                    uint32_t dneg = d > half;
+                    carry = dneg;
+                    uint32_t mag = dneg ? ((1u << sh.c) - d) : d;
+                    uint32_t neg = dneg ^ flip;
                     if (mag != 0 && w >= w_begin && w < w_end) {
                         if (sh.fixed_n) {
                             bucket[k] = slot_base + (mag - 1);
@@ -422,14 +435,15 @@ k_accumulate(const Affine<typename C::F>* __restrict__ points, const uint2* __re
 // One thread per slice boundary owner: slice t owns the cut bucket that STARTS inside it and runs on
 // into slice t+1; it adds part_tail[t] and the part_head[] of every following slice the bucket
 // covers.  Buckets longer than L * kStitchSerial pairs are finished by k_stitch_long (a block each).
-constexpr uint32_t kStitchSerial = 48;
+constexpr uint32_t kStitchSerial = 48;       // throughput setting: many cut buckets, every thread busy
+constexpr uint32_t kStitchSerialSmall = 8;   // latency setting: few slices in total, hand long runs to a block early
 
 template <class C, class F>
 __global__ void __launch_bounds__(64)
 k_stitch(const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_pairs, uint32_t L,
          XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ part_head,
          const XYZZ<F>* __restrict__ part_tail, uint32_t* __restrict__ long_count,
-         uint2* __restrict__ long_runs) {
+         uint2* __restrict__ long_runs, uint32_t serial_limit) {
     const uint32_t M = *total_pairs;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t start64 = (uint64_t)t * L;
@@ -445,7 +459,7 @@ k_stitch(const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_pa
     uint32_t u = t + 1, cnt = 0;
     XYZZ<F> acc = ld16(part_tail + t);
     for (;;) {
-        if (cnt == kStitchSerial) {                   // hand the rest to the cooperative kernel
+        if (cnt == serial_limit) {                    // hand the rest to the cooperative kernel
             st16(buckets + key, acc);
             uint32_t slot = atomicAdd(long_count, 1u);
             long_runs[slot] = make_uint2(key, u);
