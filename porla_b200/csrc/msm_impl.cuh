@@ -131,8 +131,13 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     const uint32_t serial_limit = nslices_cap < 200000u ? kStitchSerialSmall : kStitchSerial;
     const uint32_t long_cap = (uint32_t)(pairs_cap / ((uint64_t)L * serial_limit)) + 2;
 
+    // sort path: shared-memory radix partition (two MSD passes) for large single MSMs, else one returning
+    // global atomic per pair
+    const bool radix = nbatch == 1 && n >= (1u << 19) && sh.nwin <= 30 && sh.c >= 9 && sh.c <= 20 && (sh.nbuckets >> (sh.c / 2)) <= (uint32_t)kPartMaxBins && !getenv("PORLA_ATOMIC_SCATTER");
+    const int lb = sh.c / 2;                                   // coarse bin = 2^lb consecutive buckets
+    const uint32_t ncoarse = radix ? (nbt >> lb) : 0u;
     std::lock_guard<std::mutex> lock(g_engine_mu);
-    size_t need = Arena::padded(nbt, 4) * 2 + Arena::padded(ntiles + 1, 4) + 512 +
+    size_t need = (radix ? Arena::padded(pairs_cap, 8) + Arena::padded(ncoarse, 4) : 0) + Arena::padded(nbt, 4) * 2 + Arena::padded(ntiles + 1, 4) + 512 +
                   Arena::padded(pairs_cap, 8) + Arena::padded(nbt, sizeof(XYZZ<F>)) +
                   2 * Arena::padded(nslices_cap, sizeof(XYZZ<F>)) + Arena::padded(long_cap, 8) +
                   Arena::padded(slots * blocks_per_slot, sizeof(XYZZ<F>)) + Arena::padded(slots, sizeof(XYZZ<F>));
@@ -144,6 +149,8 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     uint32_t* grand = g_arena.take<uint32_t>(1);       // total number of (point, window) pairs
     uint32_t* long_count = g_arena.take<uint32_t>(1);
     uint2* sorted = g_arena.take<uint2>(pairs_cap);
+    uint2* part = radix ? g_arena.take<uint2>(pairs_cap) : nullptr;
+    uint32_t* coarse_cursor = radix ? g_arena.take<uint32_t>(ncoarse) : nullptr;
     XYZZ<F>* buckets = g_arena.take<XYZZ<F>>(nbt);
     XYZZ<F>* part_head = g_arena.take<XYZZ<F>>(nslices_cap);
     XYZZ<F>* part_tail = g_arena.take<XYZZ<F>>(nslices_cap);
@@ -176,6 +183,23 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         k_scan_add<<<ntiles, kScanThreads, 0, stream>>>(offsets, counters, nbt, tile_sums);
         LAUNCHED();
         g_stage_timer.mark(kStageScatter, stream);
+        if (radix) {
+            static std::once_flag attr_once;
+            const size_t smem1 = ((size_t)9 * kPartTile + 2 * kPartMaxBins) * 4 + (size_t)kPartTile * 8;
+            const size_t smem2 = (size_t)2 * kFineHist * 4 + (size_t)kFineTile * 8;
+            std::call_once(attr_once, [=] {
+                PORLA_CUDA(cudaFuncSetAttribute(k_partition_coarse<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+                PORLA_CUDA(cudaFuncSetAttribute(k_partition_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            });
+            k_init_coarse<<<(ncoarse + 255) / 256, 256, 0, stream>>>(offsets, nbt, lb, ncoarse, coarse_cursor);
+            LAUNCHED();
+            k_partition_coarse<C><<<(n + kPartTile - 1) / kPartTile, kPartThreads, smem1, stream>>>(
+                d_scalars, opt.scalar_be, table.d_flags, sh, lb, coarse_cursor, part);
+            LAUNCHED();
+            k_partition_fine<<<(uint32_t)((pairs_cap + kFineTile - 1) / kFineTile), kFineThreads, smem2, stream>>>(part, grand, lb,
+                                                                                                             counters, sorted);
+            LAUNCHED();
+        } else {
         // windows per scatter launch: keep the written region of `sorted` (8 B per pair) around 64 MB
         int wgroup = sh.nwin;
         if (nbatch == 1) {
@@ -188,6 +212,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
             int w1 = w0 + wgroup < sh.nwin ? w0 + wgroup : sh.nwin;
             k_digits<C, true><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, w0, w1, counters, sorted);
             LAUNCHED();
+        }
         }
         g_stage_timer.mark(kStageAccumulate, stream);
         k_accumulate<C><<<(nslices_cap + kAccThreads - 1) / kAccThreads, kAccThreads, 0, stream>>>(

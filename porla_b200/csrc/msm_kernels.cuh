@@ -370,6 +370,215 @@ k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ copy, uint32_t n,
         }
 }
 
+// ---------------------------------------------------------------------------- shared-memory radix partition
+// Large single MSMs sort their (bucket, point) pairs in two most-significant-digit passes instead of one
+// returning global atomic per pair (k_digits<SCATTER>, bound by L2 atomic round trips: ncu long-scoreboard).
+// The exact bucket offsets are already known from the histogram + scan, so every coarse bin (2^lb
+// consecutive buckets) owns a contiguous range of the output and no pass needs its own global histogram.
+//
+//   pass 1  k_partition_coarse: a block takes a tile of kPartTile scalars, reduces them once into shared
+//           memory (SoA words + the per-window carry bits of the signed recoding), then for each window:
+//           shared-memory histogram over the window's coarse bins (atomicAdd returns the rank inside the
+//           block), block scan, ONE global atomic per (block, bin) to reserve a run in the bin's range, the
+//           pairs are grouped by bin in shared memory and written out as coalesced runs into `part`.
+//   pass 2  k_partition_fine: a block takes kFineTile consecutive pairs of `part` (one or two coarse bins),
+//           ranks them per bucket in a shared-memory histogram, reserves a run per (block, bucket) with one
+//           global atomic on the bucket cursor, groups the pairs by bucket in shared memory and writes them
+//           to their final place in `sorted` as coalesced runs.  Pairs whose bucket lies beyond the shared
+//           histogram (sparse inputs) take one global atomic each.
+constexpr int kPartThreads = 512;
+constexpr int kPartPerThread = 4;
+constexpr int kPartTile = kPartThreads * kPartPerThread;   // 2048 scalars: 64 KB of reduced words in smem
+constexpr int kPartMaxBins = 1024;                         // coarse bins per window
+constexpr int kFineThreads = 512;
+constexpr int kFinePerThread = 8;
+constexpr int kFineTile = kFineThreads * kFinePerThread;   // 4096 pairs
+constexpr uint32_t kFineHist = 4096;                       // shared histogram entries of pass 2
+constexpr uint32_t kMetaSkip = 1u << 30, kMetaFlip = 1u << 31;
+
+static __global__ void k_init_coarse(const uint32_t* __restrict__ offsets, uint32_t nbt, int lb, uint32_t ncoarse,
+                                     uint32_t* __restrict__ coarse_cursor) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < ncoarse) coarse_cursor[g] = offsets[(size_t)g << lb];
+}
+
+template <class C>
+__global__ void __launch_bounds__(kPartThreads, 2)
+k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const uint8_t* __restrict__ inf_flags,
+                   MsmShape sh, int lb, uint32_t* __restrict__ coarse_cursor, uint2* __restrict__ part) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* sw = smem;                                   // [8][kPartTile] reduced scalar words
+    uint32_t* meta = sw + 8 * kPartTile;                   // carry bit per window | skip | flip
+    uint32_t* cnt = meta + kPartTile;                      // [kPartMaxBins] counts, then local offsets
+    uint32_t* delta = cnt + kPartMaxBins;                  // [kPartMaxBins] reserved global base - local offset
+    uint2* stage = reinterpret_cast<uint2*>(delta + kPartMaxBins);   // [kPartTile] pairs grouped by bin
+    __shared__ uint32_t s_total;
+    const uint32_t ncw = sh.nbuckets >> lb;                // coarse bins per window (<= kPartMaxBins)
+    const uint32_t half = 1u << (sh.c - 1);
+    const uint32_t mask = (1u << sh.c) - 1u;
+    const uint32_t tile0 = blockIdx.x * kPartTile;
+    // ---- reduce the tile's scalars once, note the carries of the signed recoding
+#pragma unroll 1
+    for (int q = 0; q < kPartPerThread; q++) {
+        const uint32_t p = q * kPartThreads + threadIdx.x;
+        const uint32_t i = tile0 + p;
+        uint32_t m = kMetaSkip;
+        uint32_t s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (i < sh.n && !(inf_flags && inf_flags[i])) {
+            load_u256(scalars, i, big_endian, s);
+            reduce_scalar<C>(s);
+            m = 0;
+            if (C::kHalveScalar) {
+                uint32_t ord[8], t[8], u[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) ord[k] = C::order(k);
+                sub256(t, ord, s);
+                if (sub256(u, t, s)) {
+                    m = kMetaFlip;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) s[k] = t[k];
+                }
+            }
+            uint32_t carry = 0;
+            for (int w = 0; w < sh.nwin; w++) {
+                uint32_t pos = (uint32_t)w * sh.c;
+                uint32_t word = pos >> 5, sft = pos & 31;
+                uint32_t lo = s[word < 8 ? word : 8];
+                uint32_t hi = s[word < 7 ? word + 1 : 8];
+                m |= carry << w;
+                uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry;
+                carry = d > half;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) sw[k * kPartTile + p] = s[k];
+        meta[p] = m;
+    }
+    // ---- one window at a time
+    const uint32_t ept = (ncw + kPartThreads - 1) / kPartThreads;   // bins per thread in the scan (<= 2)
+    for (int w = 0; w < sh.nwin; w++) {
+        for (uint32_t b = threadIdx.x; b < ncw; b += kPartThreads) cnt[b] = 0;
+        __syncthreads();
+        const uint32_t pos = (uint32_t)w * sh.c;
+        const uint32_t word = pos >> 5, sft = pos & 31;
+        const uint32_t key0 = sh.fixed_n ? 0u : (uint32_t)w * sh.nbuckets;
+        // packed per item: bucket (20 bits) | rank within (block, bin) (11 bits) | sign
+        uint32_t item[kPartPerThread];
+#pragma unroll
+        for (int q = 0; q < kPartPerThread; q++) {
+            const uint32_t p = q * kPartThreads + threadIdx.x;
+            const uint32_t m = meta[p];
+            item[q] = 0xffffffffu;
+            if (!(m & kMetaSkip)) {
+                uint32_t lo = word < 8 ? sw[word * kPartTile + p] : 0u;
+                uint32_t hi = word < 7 ? sw[(word + 1) * kPartTile + p] : 0u;
+                uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + ((m >> w) & 1u);
+                uint32_t dneg = d > half;
+                uint32_t mag = dneg ? ((1u << sh.c) - d) : d;
+                if (mag != 0) {
+                    uint32_t r = atomicAdd(&cnt[(mag - 1) >> lb], 1u);     // r < kPartTile = 2^11
+                    item[q] = (mag - 1) | (r << 20) | ((dneg ^ (m >> 31)) << 31);
+                }
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the bin counts (local offsets), one global reservation per non-empty bin
+        {
+            uint32_t v[2], sum = 0;
+            const uint32_t b0 = threadIdx.x * ept;
+            for (uint32_t k = 0; k < ept; k++) {
+                v[k] = b0 + k < ncw ? cnt[b0 + k] : 0u;
+                sum += v[k];
+            }
+            uint32_t ex = block_exclusive_scan(sum, &s_total);
+            for (uint32_t k = 0; k < ept; k++) {
+                if (b0 + k < ncw) {
+                    cnt[b0 + k] = ex;
+                    delta[b0 + k] = v[k] ? atomicAdd(&coarse_cursor[(key0 >> lb) + b0 + k], v[k]) - ex : 0u;
+                }
+                ex += v[k];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kPartPerThread; q++) {
+            if (item[q] == 0xffffffffu) continue;
+            const uint32_t bucket = item[q] & 0xfffffu, r = (item[q] >> 20) & 0x7ffu, neg = item[q] >> 31;
+            const uint32_t pidx = tile0 + q * kPartThreads + threadIdx.x;
+            stage[cnt[bucket >> lb] + r] =
+                make_uint2(key0 + bucket, (sh.fixed_n ? (uint32_t)w * sh.fixed_n + pidx : pidx) | (neg << 31));
+        }
+        __syncthreads();
+        const uint32_t total = s_total;
+        for (uint32_t j = threadIdx.x; j < total; j += kPartThreads) {
+            const uint2 e = stage[j];
+            part[delta[(e.x - key0) >> lb] + j] = e;
+        }
+    }
+}
+
+static __global__ void __launch_bounds__(kFineThreads, 3)
+k_partition_fine(const uint2* __restrict__ part, const uint32_t* __restrict__ total_pairs, int lb,
+                 uint32_t* __restrict__ cursor, uint2* __restrict__ sorted) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* cnt = smem;                                   // [kFineHist] counts, then local offsets
+    uint32_t* delta = cnt + kFineHist;                      // [kFineHist] reserved global base - local offset
+    uint2* stage = reinterpret_cast<uint2*>(delta + kFineHist);   // [kFineTile] pairs grouped by bucket
+    __shared__ uint32_t s_total;
+    const uint32_t M = *total_pairs;
+    const uint64_t lo64 = (uint64_t)blockIdx.x * kFineTile;
+    if (lo64 >= M) return;
+    const uint32_t lo = (uint32_t)lo64;
+    const uint32_t hi = M - lo > (uint32_t)kFineTile ? lo + kFineTile : M;
+    for (uint32_t b = threadIdx.x; b < kFineHist; b += kFineThreads) cnt[b] = 0;
+    const uint32_t kbase = (__ldg(&part[lo].x) >> lb) << lb;
+    __syncthreads();
+    uint2 e[kFinePerThread];
+    uint32_t rank[kFinePerThread];
+#pragma unroll
+    for (int q = 0; q < kFinePerThread; q++) {
+        const uint32_t idx = lo + q * kFineThreads + threadIdx.x;
+        e[q] = make_uint2(0xffffffffu, 0u);
+        if (idx < hi) {
+            e[q] = __ldg(&part[idx]);
+            const uint32_t rel = e[q].x - kbase;      // pass 1 keeps coarse bins in order, so rel >= 0
+            if (rel < kFineHist) rank[q] = atomicAdd(&cnt[rel], 1u);
+        }
+    }
+    __syncthreads();
+    {
+        constexpr uint32_t ept = kFineHist / kFineThreads;   // 8
+        uint32_t v[ept], sum = 0;
+        const uint32_t b0 = threadIdx.x * ept;
+#pragma unroll
+        for (uint32_t k = 0; k < ept; k++) {
+            v[k] = cnt[b0 + k];
+            sum += v[k];
+        }
+        uint32_t ex = block_exclusive_scan(sum, &s_total);
+#pragma unroll
+        for (uint32_t k = 0; k < ept; k++) {
+            cnt[b0 + k] = ex;
+            delta[b0 + k] = v[k] ? atomicAdd(&cursor[kbase + b0 + k], v[k]) - ex : 0u;
+            ex += v[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kFinePerThread; q++) {
+        if (e[q].x == 0xffffffffu) continue;
+        const uint32_t rel = e[q].x - kbase;
+        if (rel < kFineHist) stage[cnt[rel] + rank[q]] = e[q];
+        else sorted[atomicAdd(&cursor[e[q].x], 1u)] = e[q];
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    for (uint32_t j = threadIdx.x; j < total; j += kFineThreads) {
+        const uint2 x = stage[j];
+        sorted[delta[x.x - kbase] + j] = x;
+    }
+}
+
 // ---------------------------------------------------------------------------- accumulation
 // Load-balanced segmented accumulation.  `sorted` holds the M (bucket id, point index | sign << 31)
 // pairs grouped by bucket.  Thread t owns the fixed-length slice [t*L, (t+1)*L) regardless of where

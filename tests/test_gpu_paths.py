@@ -317,3 +317,51 @@ def test_fft_in_exponent_all_stages_resident(curve, c):
     exp = O.msm(c, sc, cur)
     assert got == (bytes(64) if exp is None else be(exp[0]) + be(exp[1]))
     t.destroy()
+
+
+# ------------------------------------------------------------------ shared-memory radix partition (n >= 2^19)
+@pytest.mark.parametrize("curve,c", [(pb.CURVE_BN254, BN), (pb.CURVE_SECP256K1, SE)])
+@pytest.mark.parametrize("kind", ["uniform", "constant", "small31", "top_heavy", "zeros_and_infinities"])
+def test_radix_partition_sort_matches_atomic_scatter_and_closed_form(curve, c, kind, monkeypatch):
+    """2^19 + 37 terms (ragged last tile): the two sort paths must give the same bytes, and the result must
+    equal (sum s_i k_i) G for the table {k_i G}."""
+    import numpy as np
+    import torch
+    n = (1 << 19) + 37
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7 + len(kind))
+    ks = torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda", generator=g)
+    ks[:, 2:] = 0                                               # 64-bit multipliers: cheap table, cheap closed form
+    ss = torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda", generator=g)
+    if kind == "constant":
+        ss[:] = ss[0]
+    elif kind == "small31":
+        ss[:, 1:] = 0
+        ss[:, 0] &= 0x7FFFFFFF
+    elif kind == "top_heavy":
+        ss[:, :7] = 0
+        ss[:, 7] &= 0x3
+        ss[:, 7] |= 0x10000000
+    elif kind == "zeros_and_infinities":
+        ss[::3] = 0
+        ks[5::7] = 0                                            # 0 * G = infinity in the table
+    tab = pb.Table.multiples_of_generator(curve, ks.data_ptr(), n, pb.SCALAR_LE32, on_device=True)
+    if kind == "zeros_and_infinities":
+        assert tab.num_infinity > 0
+    got = tab.msm_resident(ss.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32)
+    monkeypatch.setenv("PORLA_ATOMIC_SCATTER", "1")
+    ref = tab.msm_resident(ss.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32)
+    monkeypatch.delenv("PORLA_ATOMIC_SCATTER")
+    assert got == ref
+
+    def to_ints(t):
+        a = t.cpu().numpy().view(np.uint32).astype(object)
+        v = a[:, 0]
+        for j in range(1, 8):
+            v = v + (a[:, j] << (32 * j))
+        return v
+    kv, sv = to_ints(ks), to_ints(ss)
+    total = int(sum((int(s) % c.n) * int(k) for s, k in zip(sv, kv)) % c.n)
+    exp = O.mul(c, total, (c.gx, c.gy))
+    assert got == (bytes(64) if exp is None else be(exp[0]) + be(exp[1]))
+    tab.destroy()
