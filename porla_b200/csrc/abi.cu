@@ -40,12 +40,18 @@ std::mutex g_io_mu;                 // serialises the staging buffers below
 // staging: one device buffer for inputs/outputs of host-buffer calls + a stream
 struct Staging {
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // H2D of the second half overlaps the MSM of the first (msm_host_split)
+    cudaEvent_t ev[2] = {nullptr, nullptr};
     uint8_t* d_buf = nullptr;
     size_t cap = 0;
     uint8_t* h_pinned = nullptr;
     size_t h_cap = 0;
     void init() {
-        if (!stream) PORLA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        if (!stream) {
+            PORLA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            PORLA_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            for (auto& e : ev) PORLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
     }
     uint8_t* dev(size_t bytes) {
         init();
@@ -121,6 +127,46 @@ void run_and_fetch(int curve, const PointTable& tab, const uint8_t* d_scalars, i
     memcpy(out, h, (size_t)nbatch * 64);
 }
 
+// One large MSM from host buffers, as two halves of the point range: the host-to-device copy of the second
+// half (PCIe, ~50 GB/s: 96 B per term) runs while the first half is being multiplied, and the two sets of
+// per-window sums are added by the host finaliser exactly as the multi-GPU path does.  Worth it from 2^19
+// terms (below that the second bucket reduction costs more than the copy it hides).  Caller holds g_io_mu.
+void msm_host_split(int curve, const uint8_t* scalars, const uint8_t* points, int64_t n, int scalar_fmt, int point_fmt,
+                    uint8_t* out) {
+    auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const int64_t half[2] = {n / 2, n - n / 2};
+    const MsmPlan plan = msm_plan(curve, (uint32_t)half[1], 1, 0);
+    const size_t ws_bytes = (size_t)plan.nwin * 128;
+    size_t sc_off = 0, pt_off = pad((size_t)n * 32), tab_off = pt_off + pad((size_t)n * 64), fl_off = tab_off + pad((size_t)n * 64),
+           ws_off = fl_off + pad((size_t)n);
+    uint8_t* d = g_stage.dev(ws_off + 2 * pad(ws_bytes));
+    cudaStream_t st = g_stage.stream, cs = g_stage.copy_stream;
+    MsmOptions opt;
+    opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
+    opt.out_fmt = point_fmt;
+    opt.shared_points = 1;
+    opt.window_bits = plan.c;
+    opt.no_fixed_base = 1;
+    int64_t first = 0;
+    for (int h = 0; h < 2; h++) {
+        const size_t a = (size_t)first, m = (size_t)half[h];
+        PORLA_CUDA(cudaMemcpyAsync(d + sc_off + a * 32, scalars + a * 32, m * 32, cudaMemcpyHostToDevice, cs));
+        PORLA_CUDA(cudaMemcpyAsync(d + pt_off + a * 64, points + a * 64, m * 64, cudaMemcpyHostToDevice, cs));
+        PORLA_CUDA(cudaEventRecord(g_stage.ev[h], cs));
+        PORLA_CUDA(cudaStreamWaitEvent(st, g_stage.ev[h], 0));
+        PointTable tab;
+        table_import_into(curve, d + pt_off + a * 64, point_fmt, (uint32_t)m, d + tab_off + a * 64, d + fl_off + a, &tab, st);
+        opt.d_window_sums = d + ws_off + h * pad(ws_bytes);
+        msm_device(curve, tab, d + sc_off + a * 32, (uint32_t)m, 1, opt, nullptr, nullptr, st);
+        first += half[h];
+    }
+    uint8_t* hbuf = g_stage.pinned(2 * ws_bytes);
+    for (int h = 0; h < 2; h++)
+        PORLA_CUDA(cudaMemcpyAsync(hbuf + h * ws_bytes, d + ws_off + h * pad(ws_bytes), ws_bytes, cudaMemcpyDeviceToHost, st));
+    PORLA_CUDA(cudaStreamSynchronize(st));
+    finalize_host_parts(curve, hbuf, 2, plan.nwin, plan.c, opt.out_fmt, out);
+}
+
 // Host-buffer MSM core.  Scalars/points are copied to the device, points imported (the import
 // kernel also decodes gnark's compressed-flag encodings), nbatch MSMs run, results copied back.
 void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int64_t n, int64_t nbatch,
@@ -132,6 +178,11 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
     }
     device_init();
     std::lock_guard<std::mutex> lock(g_io_mu);
+    g_stage.init();
+    if (nbatch == 1 && n >= (1 << 19) && !getenv("PORLA_NO_SPLIT")) {
+        msm_host_split(curve, scalars, points, n, scalar_fmt, point_fmt, out);
+        return;
+    }
     const size_t total = (size_t)n * (size_t)nbatch;
     // staging layout: scalars | raw points | imported table | infinity flags | result scratch
     auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };

@@ -365,3 +365,33 @@ def test_radix_partition_sort_matches_atomic_scatter_and_closed_form(curve, c, k
     exp = O.mul(c, total, (c.gx, c.gy))
     assert got == (bytes(64) if exp is None else be(exp[0]) + be(exp[1]))
     tab.destroy()
+
+
+def test_host_buffer_msm_pipelined_halves_match_single_pass(monkeypatch):
+    """compute_multi_exp from host buffers at 2^19 + 3 terms runs as two pipelined halves (copy of the
+    second overlaps the MSM of the first); must equal the single-pass result and the closed form."""
+    import numpy as np
+    import torch
+    n = (1 << 19) + 3
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4242)
+    ks = torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda", generator=g)
+    ks[:, 2:] = 0
+    ks[11] = 0                                                 # an infinity among the points
+    tab = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks.data_ptr(), n, pb.SCALAR_LE32, on_device=True)
+    pts = tab.export()
+    assert pts[64 * 11:64 * 12] == bytes(64)
+    rnd = random.Random(9)
+    sc = bytes(rnd.getrandbits(8) for _ in range(64)) * (n // 2) + bytes(32 * (n - 2 * (n // 2)))
+    sc = bytearray(sc)
+    sc[0:32] = be(BN.n + 5)                                    # >= r: reduced like fr.SetBytes
+    got = pb.bn254_multi_exp(pts, bytes(sc), n)
+    monkeypatch.setenv("PORLA_NO_SPLIT", "1")
+    ref = pb.bn254_multi_exp(pts, bytes(sc), n)
+    monkeypatch.delenv("PORLA_NO_SPLIT")
+    assert got == ref
+    kv = ks.cpu().numpy().view(np.uint32).astype(object)
+    kk = kv[:, 0] + (kv[:, 1] << 32)
+    total = sum((int.from_bytes(sc[32 * i:32 * i + 32], "big") % BN.n) * int(kk[i]) for i in range(n)) % BN.n
+    assert got == O.bn254_marshal(O.mul(BN, total, (1, 2)))
+    tab.destroy()
