@@ -342,7 +342,7 @@ def run_ours(args):
 
     # ---- CPU baseline beside it (bounded sample, host cores of this box)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         lgs = min(args.log2n, args.cpu_sample_log2n)
         rate, sec = cpu_port_rate(lgs, threads)
