@@ -398,7 +398,23 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _json_only_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the duration of the run and hand back the real stdout for the line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 if __name__ == "__main__":
+    _out = _json_only_stdout()
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001 -- the JSON line (and only it) goes to the real stdout
+        kw.setdefault("file", _out)
+        _print(*args, **kw)
+
     a = parse()
     if a.impl == "reference":
         run_reference(a)
