@@ -300,15 +300,23 @@ void scalar_mul_impl(const PointTable& table, const uint8_t* d_scalars, int scal
 
 template <class C>
 void butterfly_impl(PointTable* t, uint32_t m, const uint8_t* d_twiddles, int scalar_be, cudaStream_t stream) {
-    using F = typename C::FC;
     const uint32_t nb = t->n / 2;
     if (!nb) return;
     if (!t->d_flags) {   // outputs may be infinity (A0 = +-t): from now on the table carries flags
         PORLA_CUDA(cudaMalloc(&t->d_flags, t->n));
         PORLA_CUDA(cudaMemsetAsync(t->d_flags, 0, t->n, stream));
     }
-    k_butterfly<C><<<(nb + 127) / 128, 128, 0, stream>>>(reinterpret_cast<Affine<F>*>(t->d_points), t->d_flags, t->n, m,
-                                                        d_twiddles, scalar_be);
+    // Few butterflies (Porla's n = 1024 blocks: 512 threads) are pure latency: the inlined field type runs a
+    // lone warp's dependent multiplications about twice as fast as the outlined multiplier of the compact
+    // type; with the machine full the compact code (no instruction-cache pressure) wins.
+    const char* force = getenv("PORLA_BUTTERFLY_FIELD");
+    const bool inlined = force ? force[0] == 'i' : nb < 148u * 512u;
+    if (inlined)
+        k_butterfly<C, typename C::F><<<(nb + 127) / 128, 128, 0, stream>>>(
+            reinterpret_cast<Affine<typename C::F>*>(t->d_points), t->d_flags, t->n, m, d_twiddles, scalar_be);
+    else
+        k_butterfly<C, typename C::FC><<<(nb + 127) / 128, 128, 0, stream>>>(
+            reinterpret_cast<Affine<typename C::FC>*>(t->d_points), t->d_flags, t->n, m, d_twiddles, scalar_be);
     LAUNCHED();
     PORLA_CUDA(cudaGetLastError());
 }

@@ -902,11 +902,10 @@ k_scalar_mul(const Affine<typename C::FC>* __restrict__ points, uint32_t npoints
 // (main.go:196-222) or secp256k1_ecmult + 2 gej_add_var in IPA mode.  One thread per butterfly, in
 // place on the resident affine table; both outputs share one field inversion.  flags[] (1 =
 // infinity) is rewritten so that MSMs over the table keep skipping infinities.
-template <class C>
+template <class C, class F>
 __global__ void __launch_bounds__(128)
-k_butterfly(Affine<typename C::FC>* __restrict__ pts, uint8_t* __restrict__ flags, uint32_t n, uint32_t m,
+k_butterfly(Affine<F>* __restrict__ pts, uint8_t* __restrict__ flags, uint32_t n, uint32_t m,
             const uint8_t* __restrict__ twiddles, int big_endian) {
-    using F = typename C::FC;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t m2 = m >> 1;
     if (b >= n / 2) return;

@@ -54,6 +54,46 @@ out["compute_digest_ms"] = timeit(lambda: k.compute_digest(block))
 # batched align_MAC: 1024 block commitments in one launch sequence
 blocks = b"".join(be(rnd.randrange(1 << 256)) for _ in range(128 * 1024))
 out["compute_digest_from_srs_batch_1024_ms"] = timeit(lambda: k.compute_digest_from_srs_batch(blocks, 1024), reps=3, warm=1)
+# CRebuild_Cached on the MACs (Server.hpp:1548-1687): log2(n) butterfly stages over n = 1024 points.
+# Reference call pattern: per butterfly mult_point + add_point + neg_point + add_point through the C-ABI
+# (timed here on 64 butterflies and scaled); batched: one bn254 butterfly launch per stage on a resident table.
+nblk = 1024
+macs = loader.bn254_point_chain(G, step, nblk)
+stages = []
+m = 2
+while m <= nblk:
+    stages.append((m, b"".join(be(rnd.randrange(O.BN254.n)) for _ in range(m // 2))))
+    m *= 2
+
+
+def rebuild_batched():
+    t = pb.Table.from_host(pb.CURVE_BN254, macs)
+    for m_, tw in stages:
+        t.butterfly_stage(m_, tw)
+    res = t.export()
+    t.destroy()
+    return res
+
+
+def butterflies_per_call(count):
+    a0, a1 = bytearray(macs[:64]), bytearray(macs[64:128])
+    w = stages[3][1][:32]
+    for _ in range(count):
+        tm = bytearray(a1); pb.bn254_mult(tm, w)
+        um = bytearray(a0); pb.bn254_add(a0, bytes(tm))
+        pb.bn254_neg(tm); a1[:] = um; pb.bn254_add(a1, bytes(tm))
+
+
+out["crebuild_1024_batched_gpu_ms"] = timeit(rebuild_batched, reps=5, warm=2)
+per = timeit(lambda: butterflies_per_call(64), reps=3, warm=1) / 64
+out["butterfly_per_call_host_ms"] = per
+out["crebuild_1024_per_call_host_1thread_ms"] = per * (nblk // 2) * len(stages)
+# spot check: first stage against the per-call path
+chk = bytearray(macs)
+pb.bn254_butterfly_stage(chk, nblk, 2, stages[0][1])
+a0, a1 = bytearray(macs[:64]), bytearray(macs[64:128])
+tm = bytearray(a1); pb.bn254_mult(tm, stages[0][1][:32]); um = bytearray(a0); pb.bn254_add(a0, bytes(tm)); pb.bn254_neg(tm); a1[:] = um; pb.bn254_add(a1, bytes(tm))
+assert bytes(chk[:128]) == bytes(a0) + bytes(a1)
 for npts in (128, 766):
     r = out["n_points_%d" % npts]
     out["server_audit_msm_total_ms_n%d" % npts] = 2 * r["compute_multi_exp_ms"] + out["compute_digest_from_srs_ms"] + out["create_proof_ms"]
