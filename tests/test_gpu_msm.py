@@ -203,3 +203,36 @@ def test_secp256k1_adapter_callback():
     assert res == O.add(SE, O.msm(SE, sc, pts), O.mul(SE, 12345, (SE.gx, SE.gy)))
     ok, res = pb.secp256k1_ecmult_multi_var([], [], g_scalar=None)
     assert ok == 1 and res is None
+
+
+def test_secp256k1_adapter_edge_cases_of_the_reference_suite():
+    """The shapes of test_ecmult_multi (/root/reference/porla/Utils/secp256k1_lib/tests.c:3816-4053) through
+    the adapter: cancelling pairs, all-infinity, all-zero scalars, constant scalar, constant point, scalars
+    >= n (convert_ZZ_to_scalar does not reduce, utils.h:180-192), a failing callback."""
+    rnd = random.Random(31)
+    G = (SE.gx, SE.gy)
+    P, Q = O.mul(SE, 0x1234567, G), O.mul(SE, 0x7654321, G)
+    run = pb.secp256k1_ecmult_multi_var
+    # sc*P + (-sc)*P, and sc*P + sc*(-P)
+    sc = rnd.randrange(SE.n)
+    assert run([sc, SE.n - sc], [P, P], 0) == (1, None)
+    assert run([sc, sc], [P, O.neg(SE, P)], 0) == (1, None)
+    # all-infinity points / all-zero scalars, sizes straddling the reference's Strauss/Pippenger switch (88)
+    for n in (1, 2, 32, 88, 130):
+        assert run([rnd.randrange(SE.n) for _ in range(n)], [None] * n, 0) == (1, None)
+        assert run([0] * n, [O.mul(SE, i + 1, G) for i in range(n)], 0) == (1, None)
+    # constant scalar over many points, constant point under many scalars
+    n = 100
+    pts = [O.mul(SE, rnd.randrange(1, 1 << 64), G) for _ in range(n)]
+    assert run([sc] * n, pts, 0) == (1, O.mul(SE, sc, O.msm(SE, [1] * n, pts)))
+    scs = [rnd.randrange(SE.n) for _ in range(n)]
+    assert run(scs, [Q] * n, 0) == (1, O.mul(SE, sum(scs) % SE.n, Q))
+    # unreduced scalars
+    big = [SE.n + 5, (1 << 256) - 1, SE.n]
+    assert run(big, [P, Q, P], 0) == (1, O.msm(SE, [s % SE.n for s in big], [P, Q, P]))
+    # a callback that fails makes the call return 0 (ecmult_impl.h:700-703)
+    lib = pb.load()
+    from porla_b200.lib import SECP_CB, SecpGej
+    r = SecpGej()
+    ok = lib.porla_secp256k1_ecmult_multi_var(None, None, C.byref(r), None, SECP_CB(lambda s, p, i, d: 0), None, 4)
+    assert ok == 0 and r.infinity == 1
