@@ -161,6 +161,14 @@ void porla_butterfly_stage_device(porla_table* t, int64_t m, const void* twiddle
                                   int twiddles_on_device, void* cuda_stream);
 extern void bn254_butterfly_stage(GoSlice* points, GoInt n, GoInt m, GoSlice* twiddles);
 
+/* Batched Server::align_MAC, KZG branch (Server.hpp:478-562): for each of `batch` data blocks of
+ * n_samples chunks A[i] -- 64-byte little-endian integers below LCM = PRIME_MODULUS * r (utils.h:37-44) --
+ *       mod = A[i] % PRIME_MODULUS;   c[i] = (mod - A[i]) % r;   A[i] = mod;   align = kzg.Commit(c)
+ * in ONE launch sequence (limb arithmetic and the batch of fixed-base MSMs on the GPU).  `data` is updated in
+ * place (upper 32 bytes of every chunk become zero); align_out receives batch x 64 bytes, the values the
+ * reference adds to the alignment MACs with bn254_add (Server.hpp:560). */
+extern void bn254_align_mac_batch(GoSlice* data, GoInt batch, GoSlice* align_out);
+
 /* ---- secp256k1 (IPA mode).  Mirrors of the reference structs (field_5x52.h:12-21,
  * group.h:13-28, scalar_4x64.h:13-15, util.h:19-22, ecmult.h:32). */
 typedef struct { uint64_t n[5]; } porla_secp256k1_fe;

@@ -603,6 +603,35 @@ void porla_scalar_mul_batch_device(const porla_table* t, const void* d_scalars, 
     PORLA_CUDA(cudaFreeAsync(d_aff, st));
 }
 
+void bn254_align_mac_batch(GoSlice* data, GoInt batch, GoSlice* align_out) {
+    const int64_t n = g_kzg.n_samples;
+    if (batch < 0 || data->len < batch * n * 64) die("bn254_align_mac_batch: data shorter than batch*n_samples*64 bytes");
+    if (batch == 0) return;
+    if (!g_kzg.have_table) {
+        if (g_kzg.srs_g1.empty()) die("SRS not initialised (call init_SRS or init_SRS_from_data first)");
+        upload_srs();
+    }
+    device_init();
+    std::vector<uint8_t> res((size_t)batch * 64);
+    {
+        std::lock_guard<std::mutex> lock(g_io_mu);
+        const size_t total = (size_t)batch * n;
+        auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        size_t sc_off = pad(total * 64), out_off = sc_off + pad(total * 32);
+        uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(kCurveBn254, n, batch));
+        cudaStream_t st = g_stage.stream;
+        PORLA_CUDA(cudaMemcpyAsync(d, data->data, total * 64, cudaMemcpyHostToDevice, st));
+        align_scalars_device(reinterpret_cast<uint32_t*>(d), (uint32_t)total, d + sc_off, st);
+        PORLA_CUDA(cudaMemcpyAsync(data->data, d, total * 64, cudaMemcpyDeviceToHost, st));   // A[i] <- A[i] % PRIME_MODULUS
+        MsmOptions opt;
+        opt.scalar_be = 1;
+        opt.out_fmt = PORLA_POINT_BE64;
+        opt.shared_points = 1;
+        run_and_fetch(kCurveBn254, g_kzg.srs_table, d + sc_off, n, batch, opt, d + out_off, res.data(), st);
+    }
+    go_copy(align_out, res.data(), res.size());
+}
+
 void porla_butterfly_stage_device(porla_table* t, int64_t m, const void* twiddles, int scalar_fmt, int twiddles_on_device,
                                   void* cuda_stream) {
     if (m < 2 || (m & (m - 1)) || (int64_t)t->t.n % m) die("porla_butterfly_stage_device: m must be a power of two dividing the table length");

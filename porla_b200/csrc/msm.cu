@@ -81,6 +81,7 @@ template <class C> void combine_impl(const void*, uint32_t, uint32_t, int, uint8
 template <class C> void scalar_mul_impl(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);
 template <class C> void export_impl(const void*, uint32_t, int, uint8_t*, cudaStream_t);
 template <class C> void butterfly_impl(PointTable*, uint32_t, const uint8_t*, int, cudaStream_t);
+template <class C> void align_scalars_impl(uint32_t*, uint32_t, uint8_t*, cudaStream_t);
 template <class C> void field_mul_impl(const void*, const void*, uint32_t, int, void*, cudaStream_t);
 
 #define DISPATCH(curve, fn, ...)                                  \
@@ -269,6 +270,11 @@ void butterfly_stage_device(PointTable* t, uint32_t m, const uint8_t* d_twiddles
         t->fb_c = t->fb_nwin = 0;
     }
     DISPATCH(t->curve, butterfly_impl, t, m, d_twiddles, scalar_be, stream);
+}
+
+void align_scalars_device(uint32_t* d_data, uint32_t total, uint8_t* d_scalars_be, cudaStream_t stream) {
+    device_init();
+    align_scalars_impl<Bn254>(d_data, total, d_scalars_be, stream);   // the reference's KZG branch only (BN254 order)
 }
 
 void export_points_device(int curve, const void* d_affine, uint32_t n, int fmt, uint8_t* d_out, cudaStream_t stream) {

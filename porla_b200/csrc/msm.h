@@ -97,6 +97,9 @@ void scalar_mul_device(int curve, const PointTable& table, const uint8_t* d_scal
 // multiple of m (m a power of two >= 2): see k_butterfly.  d_twiddles: m/2 scalars of 32 bytes on the device.
 // Invalidates the table's fixed-base expansion.
 void butterfly_stage_device(PointTable* t, uint32_t m, const uint8_t* d_twiddles, int scalar_be, cudaStream_t stream);
+// Server::align_MAC's scalar preparation for `total` chunks of 64 bytes (16 LE limbs, values below
+// PRIME_MODULUS * r): chunk <- chunk % PRIME_MODULUS in place, scalars_be[i] = (chunk % PRIME_MODULUS - chunk) % r.
+void align_scalars_device(uint32_t* d_data, uint32_t total, uint8_t* d_scalars_be, cudaStream_t stream);
 void export_points_device(int curve, const void* d_affine, uint32_t n, int point_fmt, uint8_t* d_out,
                           cudaStream_t stream);
 void field_mul_device(int curve, const void* d_a, const void* d_b, uint32_t n, int op, void* d_out,

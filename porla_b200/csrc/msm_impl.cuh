@@ -322,6 +322,14 @@ void butterfly_impl(PointTable* t, uint32_t m, const uint8_t* d_twiddles, int sc
 }
 
 template <class C>
+void align_scalars_impl(uint32_t* d_data, uint32_t total, uint8_t* d_scalars_be, cudaStream_t stream) {
+    if (!total) return;
+    k_align_scalars<C><<<(total + 127) / 128, 128, 0, stream>>>(d_data, total, d_scalars_be);
+    LAUNCHED();
+    PORLA_CUDA(cudaGetLastError());
+}
+
+template <class C>
 void export_impl(const void* d_affine, uint32_t n, int fmt, uint8_t* d_out, cudaStream_t stream) {
     using F = typename C::F;
     k_export_points<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<F>*>(d_affine), n, fmt, d_out);
@@ -348,6 +356,7 @@ void field_mul_impl(const void* d_a, const void* d_b, uint32_t n, int op, void* 
     template void scalar_mul_impl<C>(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);           \
     template void export_impl<C>(const void*, uint32_t, int, uint8_t*, cudaStream_t);                                  \
     template void butterfly_impl<C>(PointTable*, uint32_t, const uint8_t*, int, cudaStream_t);                         \
+    template void align_scalars_impl<C>(uint32_t*, uint32_t, uint8_t*, cudaStream_t);                                  \
     template void field_mul_impl<C>(const void*, const void*, uint32_t, int, void*, cudaStream_t);
 
 }  // namespace porla

@@ -948,6 +948,71 @@ k_butterfly(Affine<F>* __restrict__ pts, uint8_t* __restrict__ flags, uint32_t n
     }
 }
 
+// ---- Server::align_MAC scalar preparation (/root/reference/porla/Server/Server.hpp:531-540, KZG branch)
+// rem = a mod m for a 512-bit a (16 LE limbs) and a 256-bit m: restoring shift-subtract, one bit per step.
+// The values are touched once and the kernel is a few hundred kilobytes of traffic per launch; no attempt
+// at a word-wise division is made.
+PORLA_D void mod512(const uint32_t* a, const uint32_t* m, uint32_t* rem) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) rem[k] = 0;
+    for (int bit = 511; bit >= 0; bit--) {
+        uint32_t top = rem[7] >> 31;
+#pragma unroll
+        for (int k = 7; k > 0; k--) rem[k] = (rem[k] << 1) | (rem[k - 1] >> 31);
+        rem[0] = (rem[0] << 1) | ((a[bit >> 5] >> (bit & 31)) & 1u);
+        uint32_t t[8];
+        uint32_t borrow = sub256(t, rem, m);
+        if (top | (borrow ^ 1u)) {   // 2 rem + bit >= m
+#pragma unroll
+            for (int k = 0; k < 8; k++) rem[k] = t[k];
+        }
+    }
+}
+
+// One thread per chunk:  mod = A % PRIME_MODULUS;  c = (mod - A) % r;  A <- mod;  c -> 32-byte big-endian
+// scalar for the commitment.  PRIME_MODULUS = 207 * 2^248 + 1 (utils.h:40), r = BN254 group order (utils.h:37).
+template <class C>
+__global__ void __launch_bounds__(128)
+k_align_scalars(uint32_t* __restrict__ data, uint32_t total, uint8_t* __restrict__ scalars_be) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    constexpr uint32_t kPrime[8] = {0x00000001u, 0u, 0u, 0u, 0u, 0u, 0u, 0xcf000000u};
+    uint32_t a[16], pm[8], ord[8], rem[8], d[16], t[8], c[8];
+    uint4* src = reinterpret_cast<uint4*>(data + (size_t)i * 16);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint4 v = src[k];
+        a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        pm[k] = kPrime[k];
+        ord[k] = C::order(k);
+    }
+    mod512(a, pm, rem);
+    // d = A - mod  (a multiple of PRIME_MODULUS, non-negative)
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        uint32_t sub = k < 8 ? rem[k] : 0u;
+        uint64_t v = (uint64_t)a[k] - sub - borrow;
+        d[k] = (uint32_t)v;
+        borrow = (uint32_t)(v >> 63);
+    }
+    mod512(d, ord, t);
+    // c = (-(A - mod)) mod r
+    bool zero = true;
+#pragma unroll
+    for (int k = 0; k < 8; k++) zero = zero && t[k] == 0;
+    sub256(c, ord, t);
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = zero ? 0u : c[k];
+    store_u256(scalars_be, i, 1, c);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        src[k] = k < 2 ? make_uint4(rem[4 * k], rem[4 * k + 1], rem[4 * k + 2], rem[4 * k + 3]) : make_uint4(0u, 0u, 0u, 0u);
+}
+
 // out[i] = a[i] + b[i]
 template <class C>
 __global__ void k_point_add(const Affine<typename C::FC>* __restrict__ a,

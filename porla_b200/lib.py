@@ -31,7 +31,7 @@ NEW_SYMBOLS = [
     "porla_scalar_mul_batch_device", "porla_secp256k1_ecmult_multi_var",
     "porla_secp256k1_gej_serialize", "porla_debug_field_mul", "porla_debug_field_op", "porla_debug_point_add_host", "porla_measure_pint",
     "porla_stage_timing_enable", "porla_stage_timing_read",
-    "porla_butterfly_stage_device", "bn254_butterfly_stage",
+    "porla_butterfly_stage_device", "bn254_butterfly_stage", "bn254_align_mac_batch",
 ]
 
 
@@ -115,6 +115,7 @@ def load() -> C.CDLL:
         "porla_stage_timing_read": (I, [C.POINTER(C.c_float)]),
         "porla_butterfly_stage_device": (None, [P, C.c_int64, P, I, I, P]),
         "bn254_butterfly_stage": (None, [GS, LL, LL, GS]),
+        "bn254_align_mac_batch": (None, [GS, LL, GS]),
         "porla_debug_field_mul": (None, [I, P, P, C.c_int64, P]),
         "porla_debug_field_op": (None, [I, I, P, P, C.c_int64, P]),
         "porla_debug_point_add_host": (None, [I, P, P, C.c_int64, I, P]),
@@ -233,6 +234,13 @@ class Kzg:
     def compute_digest_from_srs_batch(self, data: bytes, batch: int) -> bytes:
         out = bytearray(64 * batch)
         self.lib.compute_digest_from_srs_batch(C.byref(_slice(bytearray(data))), batch, C.byref(_slice(out)))
+        return bytes(out)
+
+    def align_mac_batch(self, data: bytearray, batch: int) -> bytes:
+        """Server::align_MAC for `batch` blocks at once (Server.hpp:478-562): data = batch*n*64 bytes of LE
+        chunk values below PRIME_MODULUS*r, reduced mod PRIME_MODULUS in place; returns batch*64 bytes."""
+        out = bytearray(64 * batch)
+        self.lib.bn254_align_mac_batch(C.byref(_slice(data)), batch, C.byref(_slice(out)))
         return bytes(out)
 
     def create_proof(self, random_point: int, data: bytes):

@@ -395,3 +395,28 @@ def test_host_buffer_msm_pipelined_halves_match_single_pass(monkeypatch):
     total = sum((int.from_bytes(sc[32 * i:32 * i + 32], "big") % BN.n) * int(kk[i]) for i in range(n)) % BN.n
     assert got == O.bn254_marshal(O.mul(BN, total, (1, 2)))
     tab.destroy()
+
+
+def test_align_mac_batch_matches_reference_arithmetic():
+    """Server::align_MAC (Server.hpp:531-560, KZG branch) for several blocks in one call: the chunk values are
+    reduced mod PRIME_MODULUS in place and the commitment of c = (A % PRIME - A) % r over the SRS comes back."""
+    PRIME = 207 * 2**248 + 1                                   # utils.h:40
+    LCM = PRIME * BN.n                                         # utils.h:42-43
+    n, batch = 64, 5
+    k = pb.Kzg(bytes.fromhex("ffeeddccbbaa99887766554433221100"), bytes.fromhex("00112233445566778899aabbccddeeff"))
+    blob = k.init_srs(n)
+    srs = [O.bn254_unmarshal(blob[132 + 32 * i:164 + 32 * i]) for i in range(n)]
+    rnd = random.Random(2718)
+    vals = [[rnd.randrange(LCM) for _ in range(n)] for _ in range(batch)]
+    vals[0][:6] = [0, PRIME, PRIME - 1, LCM - 1, BN.n, 7 * PRIME + 3]
+    vals[1] = [rnd.randrange(PRIME) for _ in range(n)]           # already reduced: every c is 0 -> infinity
+    data = bytearray(b"".join(v.to_bytes(64, "little") for row in vals for v in row))
+    got = k.align_mac_batch(data, batch)
+    for j, row in enumerate(vals):
+        cs = [((v % PRIME) - v) % BN.n for v in row]
+        exp = O.msm(BN, cs, srs)
+        assert got[64 * j:64 * j + 64] == O.bn254_marshal(exp), j
+        for i, v in enumerate(row):
+            off = 64 * (j * n + i)
+            assert int.from_bytes(data[off:off + 64], "little") == v % PRIME, (j, i)
+    assert got[64:128] == bytes(64)
