@@ -123,6 +123,10 @@ void porla_msm_device(const porla_table* t, const void* d_scalars, int64_t n, in
  * (set PORLA_DEVICE_FINALIZE=1 to keep it on the device). */
 void porla_msm_resident(const porla_table* t, const void* d_scalars, int64_t n, int scalar_fmt,
                         int window_bits, int out_fmt, void* h_out64, void* cuda_stream);
+/* One MSM over table[first .. first + n) with HOST scalars (n x 32 bytes) and the 64-byte result in host
+ * memory: the resident-generator form of compute_multi_exp (only the scalars cross PCIe). */
+void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const void* scalars, int64_t n,
+                                  int scalar_fmt, int out_fmt, void* out64);
 /* Building blocks of a range-sharded MSM (one process per GPU): every rank runs
  * the pipeline over its point range up to the per-window sums (nwin XYZZ records of 128 B, about
  * 2 KiB), the ranks all-gather them, and one host combines: add the parts window by window, Horner
@@ -185,6 +189,14 @@ typedef int (porla_secp256k1_ecmult_multi_callback)(porla_secp256k1_scalar* sc, 
 int porla_secp256k1_ecmult_multi_var(const porla_secp256k1_callback* error_callback, void* scratch,
                                      porla_secp256k1_gej* r, const porla_secp256k1_scalar* inp_g_sc,
                                      porla_secp256k1_ecmult_multi_callback cb, void* cbdata, size_t n);
+/* Generators resident in HBM for IPA mode: Porla multiplies the same `generators[]` array in every
+ * commitment, align_MAC and inner-product round (data.pt = &generators[start_chunk], Server.hpp:347,507,
+ * 2345,2395; Client.hpp:393,1588).  Upload them once (any field magnitude, infinity flags honoured), then
+ * r = sum_i scalars[i] * generators[first + i] with only the scalars crossing PCIe.  Same result
+ * conventions as porla_secp256k1_ecmult_multi_var; returns 0 if the range leaves the table. */
+porla_table* porla_secp256k1_table_create(const porla_secp256k1_ge* points, size_t n);
+int porla_secp256k1_ecmult_multi_table(const porla_table* t, size_t first, const porla_secp256k1_scalar* scalars,
+                                       size_t n, porla_secp256k1_gej* r);
 /* 33-byte SEC1 compressed form of a gej/ge result (eckey_impl.h:36-52); returns 0 for infinity. */
 int porla_secp256k1_gej_serialize(const porla_secp256k1_gej* a, unsigned char out33[33]);
 

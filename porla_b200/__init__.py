@@ -31,4 +31,5 @@ from .lib import (  # noqa: F401
     Table,
     msm_host,
     secp256k1_ecmult_multi_var,
+    SecpGenerators,
 )

@@ -561,6 +561,33 @@ void porla_msm_resident(const porla_table* t, const void* d_scalars, int64_t n, 
     run_and_fetch(t->t.curve, t->t, (const uint8_t*)d_scalars, n, 1, opt, d_ws, (uint8_t*)h_out64, st);
 }
 
+void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const void* scalars, int64_t n, int scalar_fmt,
+                                  int out_fmt, void* out64) {
+    if (first < 0 || n < 0 || first + n > (int64_t)t->t.n) die("porla_msm_table_host_scalars: range outside the table");
+    if (n == 0) {
+        memset(out64, 0, 64);
+        return;
+    }
+    device_init();
+    std::lock_guard<std::mutex> lock(g_io_mu);
+    size_t sc_bytes = (size_t)n * 32, out_off = (sc_bytes + 255) & ~(size_t)255;
+    uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(t->t.curve, n, 1));
+    cudaStream_t st = g_stage.stream;
+    PORLA_CUDA(cudaMemcpyAsync(d, scalars, sc_bytes, cudaMemcpyHostToDevice, st));
+    PointTable view = t->t;                       // a window [first, first + n) of the resident table
+    view.d_points = (uint8_t*)t->t.d_points + (size_t)first * 64;
+    view.d_flags = t->t.d_flags ? t->t.d_flags + first : nullptr;
+    view.n = (uint32_t)n;
+    view.d_fb_points = nullptr;                   // the fixed-base expansion is indexed from point 0
+    view.fb_c = view.fb_nwin = 0;
+    if (first == 0 && t->t.fb_c > 0) view = t->t;
+    MsmOptions opt;
+    opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
+    opt.out_fmt = out_fmt;
+    opt.shared_points = 1;
+    run_and_fetch(t->t.curve, view, d, n, 1, opt, d + out_off, (uint8_t*)out64, st);
+}
+
 void porla_msm_plan(int curve, int64_t n, int64_t nbatch, int window_bits, int* c_out, int* nwin_out) {
     MsmPlan p = msm_plan(curve, (uint32_t)n, (uint32_t)nbatch, window_bits);
     *c_out = p.c;

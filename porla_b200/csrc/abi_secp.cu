@@ -161,6 +161,42 @@ int porla_secp256k1_ecmult_multi_var(const porla_secp256k1_callback* error_callb
     return 1;
 }
 
+// ---- generators resident in HBM (BASELINE north star: "SRS and generator tables resident in HBM, uploaded
+// once at init").  Porla's IPA mode multiplies the SAME generator array in every commitment, align_MAC and
+// inner-product round (data.pt = &generators[start_chunk]: Server.hpp:347,507,2345,2395, Client.hpp:393,1588);
+// the callback adapter above re-uploads them on every call.
+porla_table* porla_secp256k1_table_create(const porla_secp256k1_ge* points, size_t n) {
+    std::vector<uint8_t> le(n * 64 + 64, 0);
+    for (size_t i = 0; i < n; i++) {
+        if (points[i].infinity) continue;           // stays 64 zero bytes = infinity
+        uint32_t xy[16];
+        fe_to_canonical(&points[i].x, xy);
+        fe_to_canonical(&points[i].y, xy + 8);
+        memcpy(le.data() + 64 * i, xy, 64);
+    }
+    return porla_table_create(PORLA_CURVE_SECP256K1, le.data(), (int64_t)n, PORLA_POINT_LE64, 0, nullptr);
+}
+
+int porla_secp256k1_ecmult_multi_table(const porla_table* t, size_t first, const porla_secp256k1_scalar* scalars, size_t n,
+                                       porla_secp256k1_gej* r) {
+    gej_set_infinity(r);
+    if (n == 0) return 1;
+    if ((int64_t)(first + n) > porla_table_len(t)) return 0;
+    uint8_t res[64];
+    porla_msm_table_host_scalars(t, (int64_t)first, scalars, (int64_t)n, PORLA_SCALAR_LE32, PORLA_POINT_LE64, res);
+    uint32_t xy[16];
+    memcpy(xy, res, 64);
+    bool inf = true;
+    for (int i = 0; i < 16; i++) inf = inf && xy[i] == 0;
+    if (inf) return 1;
+    canonical_to_fe(xy, &r->x);
+    canonical_to_fe(xy + 8, &r->y);
+    memset(&r->z, 0, sizeof(r->z));
+    r->z.n[0] = 1;
+    r->infinity = 0;
+    return 1;
+}
+
 int porla_secp256k1_gej_serialize(const porla_secp256k1_gej* a, unsigned char out33[33]) {
     if (a->infinity) return 0;
     SecpFp x, y, z;

@@ -32,6 +32,7 @@ NEW_SYMBOLS = [
     "porla_secp256k1_gej_serialize", "porla_debug_field_mul", "porla_debug_field_op", "porla_debug_point_add_host", "porla_measure_pint",
     "porla_stage_timing_enable", "porla_stage_timing_read",
     "porla_butterfly_stage_device", "bn254_butterfly_stage", "bn254_align_mac_batch",
+    "porla_msm_table_host_scalars", "porla_secp256k1_table_create", "porla_secp256k1_ecmult_multi_table",
 ]
 
 
@@ -116,6 +117,9 @@ def load() -> C.CDLL:
         "porla_butterfly_stage_device": (None, [P, C.c_int64, P, I, I, P]),
         "bn254_butterfly_stage": (None, [GS, LL, LL, GS]),
         "bn254_align_mac_batch": (None, [GS, LL, GS]),
+        "porla_msm_table_host_scalars": (None, [P, C.c_int64, P, C.c_int64, I, I, P]),
+        "porla_secp256k1_table_create": (P, [C.POINTER(SecpGe), C.c_size_t]),
+        "porla_secp256k1_ecmult_multi_table": (I, [P, C.c_size_t, C.POINTER(SecpScalar), C.c_size_t, C.POINTER(SecpGej)]),
         "porla_debug_field_mul": (None, [I, P, P, C.c_int64, P]),
         "porla_debug_field_op": (None, [I, I, P, P, C.c_int64, P]),
         "porla_debug_point_add_host": (None, [I, P, P, C.c_int64, I, P]),
@@ -348,6 +352,38 @@ def _int_to_fe(v: int) -> SecpFe:
 
 def _fe_to_int(fe: SecpFe) -> int:
     return sum(int(fe.n[i]) << (52 * i) for i in range(5))
+
+
+class SecpGenerators:
+    """secp256k1 generator array resident in HBM (the `generators[]` of Server.hpp:347 / Client.hpp:393)."""
+
+    def __init__(self, points: Sequence):
+        arr = (SecpGe * max(1, len(points)))()
+        for i, Pt in enumerate(points):
+            if Pt is None:
+                arr[i].infinity = 1
+            else:
+                arr[i].x, arr[i].y, arr[i].infinity = _int_to_fe(Pt[0]), _int_to_fe(Pt[1]), 0
+        self.n = len(points)
+        self.handle = load().porla_secp256k1_table_create(arr, self.n)
+
+    def multi(self, first: int, scalars: Sequence[int]):
+        """(ok, affine result or None) of sum scalars[i] * generators[first + i]."""
+        n = len(scalars)
+        sc = (SecpScalar * max(1, n))()
+        for k, s in enumerate(scalars):
+            for i in range(4):
+                sc[k].d[i] = (s >> (64 * i)) & 0xFFFFFFFFFFFFFFFF
+        r = SecpGej()
+        ok = load().porla_secp256k1_ecmult_multi_table(C.c_void_p(self.handle), first, sc, n, C.byref(r))
+        if r.infinity:
+            return ok, None
+        return ok, (_fe_to_int(r.x), _fe_to_int(r.y))
+
+    def destroy(self) -> None:
+        if self.handle:
+            load().porla_table_destroy(C.c_void_p(self.handle))
+            self.handle = 0
 
 
 def secp256k1_ecmult_multi_var(scalars: Sequence[int], points: Sequence, g_scalar: Optional[int] = None):

@@ -236,3 +236,25 @@ def test_secp256k1_adapter_edge_cases_of_the_reference_suite():
     r = SecpGej()
     ok = lib.porla_secp256k1_ecmult_multi_var(None, None, C.byref(r), None, SECP_CB(lambda s, p, i, d: 0), None, 4)
     assert ok == 0 and r.infinity == 1
+
+
+def test_secp256k1_resident_generators():
+    """Generators uploaded once (porla_secp256k1_table_create), MSMs over sub-ranges with host scalars: the
+    call shape of Porla's IPA commitments (data.pt = &generators[start_chunk], Server.hpp:347)."""
+    rnd = random.Random(99)
+    G = (SE.gx, SE.gy)
+    gens = [O.mul(SE, rnd.randrange(1, SE.n), G) for _ in range(130)]
+    gens[7] = None
+    tab = pb.SecpGenerators(gens)
+    for first, n in ((0, 130), (3, 40), (16, 16), (100, 30), (7, 1), (129, 1)):
+        sc = [rnd.randrange(1 << 256) for _ in range(n)]
+        if n > 4:
+            sc[2] = 0
+        ok, res = tab.multi(first, sc)
+        assert ok == 1 and res == O.msm(SE, [s % SE.n for s in sc], gens[first:first + n]), (first, n)
+    assert tab.multi(0, []) == (1, None)
+    assert tab.multi(120, [1] * 20)[0] == 0                    # leaves the table
+    # same answer as the callback adapter
+    sc = [rnd.randrange(SE.n) for _ in range(64)]
+    assert tab.multi(32, sc)[1] == pb.secp256k1_ecmult_multi_var(sc, gens[32:96], g_scalar=0)[1]
+    tab.destroy()
