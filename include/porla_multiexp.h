@@ -212,6 +212,9 @@ void porla_debug_field_mul(int curve, const void* a, const void* b, int64_t n, v
 /* Same with a selectable device routine: op 0 the product, 1 the dedicated squaring a*a, 2 the fused
  * product-sum a*b + b*(a+b) (one reduction) -- the three multipliers the mixed addition uses. */
 void porla_debug_field_op(int curve, int op, const void* a, const void* b, int64_t n, void* out);
+/* Host-only self-check of the pairing behind verify_proof: bilinearity identities that must hold / must fail,
+ * under both hard-part routines and both Miller-loop drivers.  Returns the number of failed checks. */
+int porla_debug_pairing_selfcheck(int rounds);
 /* out[i] = a[i] + b[i] on external 64-byte points (host-side group law, the code behind add_point). */
 void porla_debug_point_add_host(int curve, const void* a, const void* b, int64_t n, int point_fmt, void* out);
 

@@ -380,13 +380,13 @@ GoUint8 verify_proof(GoSlice* commitment_in, GoSlice* proof_H, GoSlice* proof_po
     Fr z = elem_from_be<Fr>((const uint8_t*)proof_point->data, (size_t)proof_point->len);
     Fr y = elem_from_be<Fr>((const uint8_t*)proof_claim->data, (size_t)proof_claim->len);
     if (!g_kzg.have_g2) die("verify_proof: SRS not initialised");
-    // e(C - [y]G1, G2) * e(-H, [tau]G2 - [z]G2) == 1
+    // kzg.Verify checks e(C - [y]G1, G2) * e(-H, [tau]G2 - [z]G2) == 1.  By bilinearity
+    // e(-H, -[z]G2) = e([z]H, G2), so the same predicate is e(C - [y]G1 + [z]H, G2) * e(-H, [tau]G2) == 1:
+    // only G1 scalar multiplications, and both G2 arguments are the fixed SRS points.
     G1A yg = g1_mul(g_kzg.srs_g1.empty() ? g1_generator() : g_kzg.srs_g1[0], y);
-    G1A lhs = g1_add(c, yg.neg());
-    G2A zg2 = g2_mul(g_kzg.g2[0], z);
-    G2A rhs2 = g2_add(g_kzg.g2[1], g2_neg(zg2));
+    G1A lhs = g1_add(g1_add(c, yg.neg()), g1_mul(hq, z));
     G1A ps[2] = {lhs, hq.neg()};
-    G2A qs[2] = {g_kzg.g2[0], rhs2};
+    G2A qs[2] = {g_kzg.g2[0], g_kzg.g2[1]};
     if (!pairing_product_is_one(ps, qs, 2)) {
         printf("Verifying is wrong\n");
         return 0;
@@ -688,6 +688,43 @@ void bn254_butterfly_stage(GoSlice* points, GoInt n, GoInt m, GoSlice* twiddles)
     porla_butterfly_stage_device(&t, m, twiddles->data, PORLA_SCALAR_BE32, 0, g_stage.stream);
     porla_table_export(&t, PORLA_POINT_BE64, points->data, 0, g_stage.stream);
     table_free(&t.t);
+}
+
+int porla_debug_pairing_selfcheck(int rounds) {
+    // Host-only consistency check of the verifier's pairing: for random a, b
+    //   e(aG1, bG2) * e(-(ab)G1, G2) == 1   and   e(aG1, bG2) * e(-(ab + 1)G1, G2) != 1
+    // under BOTH hard-part routines (the u-addition chain used in production and the plain 761-bit
+    // exponentiation), and the lockstep multi-pairing Miller loop agrees with the product of single loops.
+    int bad = 0;
+    std::mt19937_64 rng(12345);
+    G1A g1 = g1_generator();
+    G2A g2 = g2_generator();
+    for (int it = 0; it < rounds; it++) {
+        uint8_t ab[32], bb[32];
+        for (int i = 0; i < 32; i++) {
+            ab[i] = (uint8_t)rng();
+            bb[i] = (uint8_t)rng();
+        }
+        Fr a = elem_from_be<Fr>(ab, 32), b = elem_from_be<Fr>(bb, 32);
+        G1A pa = g1_mul(g1, a);
+        G2A qb = g2_mul(g2, b);
+        G1A pab = g1_mul(g1, a * b).neg();
+        G1A pab1 = g1_mul(g1, a * b + Fr::one()).neg();
+        for (int wrong = 0; wrong < 2; wrong++) {
+            G1A ps[2] = {pa, wrong ? pab1 : pab};
+            G2A qs[2] = {qb, g2};
+            Fq12 m = miller_loop_multi(ps, qs, 2);
+            Fq12 m2 = miller_loop(ps[0], qs[0]).mul_dense(miller_loop(ps[1], qs[1]));
+            Fq12 e1 = m.conj6().mul_dense(fq12_inv(m));
+            Fq12 e2 = m2.conj6().mul_dense(fq12_inv(m2));
+            Fq12 c1 = frob2(e1).mul_dense(e1), c2 = frob2(e2).mul_dense(e2);
+            bool chain1 = hard_part_chain(c1).is_one(), plain1 = hard_part_plain(c1).is_one();
+            bool chain2 = hard_part_chain(c2).is_one(), plain2 = hard_part_plain(c2).is_one();
+            bool expect = wrong == 0;
+            if (chain1 != expect || plain1 != expect || chain2 != expect || plain2 != expect) bad++;
+        }
+    }
+    return bad;
 }
 
 void porla_debug_field_op(int curve, int op, const void* a, const void* b, int64_t n, void* out) {

@@ -188,7 +188,8 @@ struct alignas(16) Fp64 {
         Fp64 o{{1, 0, 0, 0}};
         return mul(*this, o);
     }
-    Fp64 inverse() const {
+    // a^(p-2) by square-and-multiply: the reference routine the fast inverse below is tested against
+    Fp64 inverse_fermat() const {
         uint64_t e[4] = {P::mod(0) - 2, P::mod(1), P::mod(2), P::mod(3)};
         Fp64 r = one();
         for (int i = 255; i >= 0; i--) {
@@ -196,6 +197,64 @@ struct alignas(16) Fp64 {
             if ((e[i >> 6] >> (i & 63)) & 1) r = mul(r, *this);
         }
         return r;
+    }
+
+    // helpers of the binary extended Euclid below (plain 256-bit integers, bit 256 in `hi`)
+    static bool geq4(const uint64_t* a, const uint64_t* b) {
+        for (int i = 3; i >= 0; i--)
+            if (a[i] != b[i]) return a[i] > b[i];
+        return true;
+    }
+    static void shr1(uint64_t* a, uint64_t hi) {
+        a[0] = (a[0] >> 1) | (a[1] << 63);
+        a[1] = (a[1] >> 1) | (a[2] << 63);
+        a[2] = (a[2] >> 1) | (a[3] << 63);
+        a[3] = (a[3] >> 1) | (hi << 63);
+    }
+    // x <- x / 2 mod p  (p odd)
+    static void half_mod(uint64_t* x, const uint64_t* m) {
+        uint64_t hi = 0;
+        if (x[0] & 1) hi = add4(x, x, m);
+        shr1(x, hi);
+    }
+    // x <- x - y mod p, both below p
+    static void sub_mod(uint64_t* x, const uint64_t* y, const uint64_t* m) {
+        if (sub4(x, x, y)) add4(x, x, m);
+    }
+
+    // Modular inverse by the binary extended Euclidean algorithm (about 2 x 256 shift/subtract steps on
+    // four limbs: ~10x faster than the Fermat exponentiation; variable time, which is fine here: nothing
+    // secret flows through the MSM engine or the verifier).  Works on the stored representation: for a
+    // Montgomery element aR it computes (aR)^-1 and multiplies by R^2 twice to return a^-1 R.
+    // The inverse of zero is zero, like the Fermat routine.
+    Fp64 inverse() const {
+        if (is_zero()) return zero();
+        const uint64_t m[4] = {P::mod(0), P::mod(1), P::mod(2), P::mod(3)};
+        uint64_t u[4] = {v[0], v[1], v[2], v[3]}, w[4] = {m[0], m[1], m[2], m[3]};
+        uint64_t x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+        auto is_one = [](const uint64_t* a) { return a[0] == 1 && (a[1] | a[2] | a[3]) == 0; };
+        while (!is_one(u) && !is_one(w)) {
+            while (!(u[0] & 1)) {
+                shr1(u, 0);
+                half_mod(x1, m);
+            }
+            while (!(w[0] & 1)) {
+                shr1(w, 0);
+                half_mod(x2, m);
+            }
+            if (geq4(u, w)) {
+                sub4(u, u, w);
+                sub_mod(x1, x2, m);
+            } else {
+                sub4(w, w, u);
+                sub_mod(x2, x1, m);
+            }
+        }
+        Fp64 r;
+        memcpy(r.v, is_one(u) ? x1 : x2, 32);
+        if (!P::kMontgomery) return r;
+        Fp64 r2{{P::r2(0), P::r2(1), P::r2(2), P::r2(3)}};
+        return mul(mul(r, r2), r2);
     }
 };
 

@@ -80,3 +80,19 @@ def test_srs_blob_digest_and_verify_on_cpu():
     k2 = pb.Kzg(TAU, ALPHA)
     k2.init_srs_from_data(n, blob)
     assert k2.verify_proof(*args)
+
+
+def test_pairing_selfcheck_and_tampered_proofs():
+    """The verifier's pairing (multi-pairing Miller loop, u-addition-chain hard part) against its plain
+    counterparts on bilinearity identities, and kzg.Verify rejecting every tampered component."""
+    assert pb.load().porla_debug_pairing_selfcheck(3) == 0
+    g = golden("bn254.json")["kzg"]
+    k = pb.Kzg(TAU, ALPHA)
+    k.init_srs(g["n"])
+    c, h, z, y = bytes.fromhex(g["commit"]), bytes.fromhex(g["H"]), be(g["z"]), bytes.fromhex(g["claim"])
+    assert k.verify_proof(c, h, z, y)
+    other = O.bn254_marshal(O.mul(BN, 31337, G))
+    assert not k.verify_proof(other, h, z, y)
+    assert not k.verify_proof(c, other, z, y)
+    assert not k.verify_proof(c, h, be(g["z"] + 1), y)
+    assert not k.verify_proof(c, bytes(64), z, y)               # H = infinity
