@@ -120,8 +120,11 @@ int choose_window(int curve, uint32_t n, uint32_t nbatch) {
         // A window size that leaves only a few bits for the top window puts n / 2^(t-1) points into each
         // of its few buckets: contended counters in the sort and long serial stitches in the accumulation
         // (measured at 2^18: c = 13 -> 1.99 ms, c = 15 -> 1.33 ms).  Skip such sizes once the load matters.
+        // (A top window that still has >= 2^10 buckets spreads the load over enough threads: c = 20 at 2^26.)
         int t_top = bits + 1 - (nwin - 1) * c;
-        if (t_top < c - 1 && ((uint64_t)n >> (t_top > 1 ? t_top - 1 : 0)) > 1024) continue;
+        if (t_top < c - 1 && t_top <= 10 && ((uint64_t)n >> (t_top > 1 ? t_top - 1 : 0)) > 1024) continue;
+        // a partly filled top window still costs stitch latency (secp256k1 2^18: c = 13 -> 1.38 ms, c = 16 -> 1.23 ms)
+        if (t_top < c - 1 && ((uint64_t)n >> (t_top > 1 ? t_top - 1 : 0)) > 256) cost *= 1.15;
         if (cost < best) {
             best = cost;
             best_c = c;
@@ -141,7 +144,7 @@ int choose_window_fixed_base(int curve, uint32_t n, uint32_t nbatch) {
         if ((double)nbatch * nb * 128.0 > 48.0e9) continue;
         if ((double)nwin * (double)n >= 2.0e9) continue;
         int t_top = bits + 1 - (nwin - 1) * c;   // see choose_window: the short top window's digits pile up in a few buckets
-        if (t_top < c - 1 && ((uint64_t)n >> (t_top > 1 ? t_top - 1 : 0)) > 1024) continue;
+        if (t_top < c - 1 && t_top <= 10 && ((uint64_t)n >> (t_top > 1 ? t_top - 1 : 0)) > 1024) continue;
         if (cost < best) {
             best = cost;
             best_c = c;

@@ -420,3 +420,32 @@ def test_align_mac_batch_matches_reference_arithmetic():
             off = 64 * (j * n + i)
             assert int.from_bytes(data[off:off + 64], "little") == v % PRIME, (j, i)
     assert got[64:128] == bytes(64)
+
+
+def test_concurrent_callers_from_eight_threads():
+    """Porla calls compute_digest_from_srs / compute_multi_exp from up to 8 ThreadPool workers at once
+    (Server.hpp:1077-1078, :1977-1978): results under concurrency must equal the sequential ones."""
+    import threading
+    n = 64
+    k = pb.Kzg(bytes.fromhex("ffeeddccbbaa99887766554433221100"), bytes.fromhex("00112233445566778899aabbccddeeff"))
+    k.init_srs(n)
+    rnd = random.Random(808)
+    blocks = [b"".join(be(rnd.randrange(1 << 256)) for _ in range(n)) for _ in range(8)]
+    pts = enc_points(bn254_points(50))
+    scs = [b"".join(be(rnd.randrange(1 << 256)) for _ in range(50)) for _ in range(8)]
+    want_c = [k.compute_digest_from_srs(b) for b in blocks]
+    want_m = [pb.bn254_multi_exp(pts, s, 50) for s in scs]
+    errors = []
+
+    def worker(t):
+        for _ in range(10):
+            if k.compute_digest_from_srs(blocks[t]) != want_c[t]:
+                errors.append(("commit", t))
+            if pb.bn254_multi_exp(pts, scs[t], 50) != want_m[t]:
+                errors.append(("msm", t))
+            buf = bytearray(want_c[t])
+            pb.bn254_add(buf, want_m[t])
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errors, errors[:4]
