@@ -109,7 +109,7 @@ int choose_window(int curve, uint32_t n, uint32_t nbatch) {
     const int bits = scalar_bits(curve);
     double best = 1e300;
     int best_c = 4;
-    for (int c = 3; c <= 22; c++) {
+    for (int c = 3; c <= 20; c++) {   // 20: the widest window the shared-memory radix partition packs
         int nwin = (bits + 1 + c - 1) / c;
         double nb = (double)(1u << (c - 1));
         // one mixed add per (point, window); ~4 mixed-add equivalents per bucket in the reduction
@@ -119,12 +119,18 @@ int choose_window(int curve, uint32_t n, uint32_t nbatch) {
         if (total_buckets * 128.0 > 48.0e9) continue;  // bucket array budget
         // A window size that leaves only a few bits for the top window puts n / 2^(t-1) points into each
         // of its few buckets: contended counters in the sort and long serial stitches in the accumulation
-        // (measured at 2^18: c = 13 -> 1.99 ms, c = 15 -> 1.33 ms).  Skip such sizes once the load matters.
-        // (A top window that still has >= 2^10 buckets spreads the load over enough threads: c = 20 at 2^26.)
+        // (measured at 2^18: c = 13 -> 1.99 ms, c = 15 -> 1.33 ms; secp256k1 2^18: c = 13 -> 1.38 ms,
+        // c = 16 -> 1.23 ms).  Skip such sizes once the load matters, penalise them mildly below that.  A top
+        // window that still has more than 2^10 buckets spreads the load over enough threads (c = 20).
         int t_top = bits + 1 - (nwin - 1) * c;
-        if (t_top < c - 1 && t_top <= 10 && ((uint64_t)n >> (t_top > 1 ? t_top - 1 : 0)) > 1024) continue;
-        // a partly filled top window still costs stitch latency (secp256k1 2^18: c = 13 -> 1.38 ms, c = 16 -> 1.23 ms)
-        if (t_top < c - 1 && ((uint64_t)n >> (t_top > 1 ? t_top - 1 : 0)) > 256) cost *= 1.15;
+        if (t_top < c - 1 && t_top <= 10) {
+            uint64_t load_top = (uint64_t)n >> (t_top > 1 ? t_top - 1 : 0);
+            if (load_top > 1024) continue;
+            if (load_top > 256) cost *= 1.15;
+        }
+        // Buckets much longer than a slice (64 pairs) are cut into many partial sums that one owner thread
+        // per bucket adds serially while its warp idles (2^26: c = 17 -> 225 ms, c = 20 -> 168 ms).
+        cost *= 1.0 + 0.02 * ((double)n / nb) / 64.0;
         if (cost < best) {
             best = cost;
             best_c = c;
