@@ -158,6 +158,68 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def secp_config4(lib, pb, torch, stream, log2n=18):
+    """IPA-mode multi-exponentiation (BASELINE configs[3]): GPU through the host-buffer C-ABI entry and with
+    resident inputs, and the reference's own ecmult_multi_var on the host cores; results must be identical."""
+    import hashlib
+    from oracle import loader
+    ref = loader.secp_ref()
+    if ref is None:
+        return {"unavailable": "oracle/_ref/libsecp_ref.so not present"}
+    n = 1 << log2n
+    chain = C.create_string_buffer(64 * n)
+    ref.ref_secp_point_chain(hashlib.sha256(b"porla-seed").digest()[::-1], n, chain)
+    sc = b"".join(hashlib.sha256(b"cfg4" + i.to_bytes(4, "little")).digest() for i in range(n))
+    h = ref.ref_secp_prepare(sc, chain.raw, n)
+    o64, o33 = C.create_string_buffer(64), C.create_string_buffer(33)
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    ref.ref_secp_msm_prepared(h, n, 1, o64, o33)
+    t_ref1 = time.perf_counter() - t0
+    ref1 = o64.raw
+    t0 = time.perf_counter()
+    ref.ref_secp_msm_prepared(h, n, threads, o64, o33)
+    t_refn = time.perf_counter() - t0
+    ref.ref_secp_release(h)
+    # GPU, host buffers in and out (pinned; H2D + import + MSM + D2H inside the call)
+    h_sc = torch.frombuffer(bytearray(sc), dtype=torch.uint8).pin_memory()
+    h_pt = torch.frombuffer(bytearray(chain.raw), dtype=torch.uint8).pin_memory()
+    out = (C.c_ubyte * 64)()
+
+    def host_call():
+        lib.porla_msm_host(pb.CURVE_SECP256K1, C.c_void_p(h_sc.data_ptr()), C.c_void_p(h_pt.data_ptr()), n, 1,
+                           pb.SCALAR_LE32, pb.POINT_BE64, C.cast(out, C.c_void_p))
+        return bytes(out)
+    host_call()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        got = host_call()
+    t_e2e = (time.perf_counter() - t0) / reps
+    if got != o64.raw or got != ref1:
+        raise SystemExit("bench self-check failed: secp256k1 GPU result differs from the reference's ecmult_multi_var")
+    # GPU, inputs resident
+    tab = pb.Table.from_host(pb.CURVE_SECP256K1, chain.raw)
+    d_sc = torch.frombuffer(bytearray(sc), dtype=torch.uint8).cuda()
+    for _ in range(2):
+        tab.msm_resident(d_sc.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32, stream=stream)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        res = tab.msm_resident(d_sc.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32, stream=stream)
+    t_res = (time.perf_counter() - t0) / reps
+    tab.destroy()
+    if res != got:
+        raise SystemExit("bench self-check failed: secp256k1 resident and host-buffer results differ")
+    return {"workload": "secp256k1 multi-exponentiation, 2^%d terms (BASELINE.json configs[3])" % log2n,
+            "gpu_resident_points_per_s": n / t_res, "gpu_resident_ms": t_res * 1e3,
+            "gpu_e2e_points_per_s": n / t_e2e, "gpu_e2e_ms": t_e2e * 1e3,
+            "cpu_reference": {"kind": "reference", "what": "secp256k1_ecmult_multi_var of the vendored library (oracle/_ref), "
+                              "Pippenger-wNAF with GLV, scratch sized as Porla sizes it",
+                              "points_per_s_1_thread": n / t_ref1, "points_per_s_all_threads": n / t_refn, "cores": threads,
+                              "partitioning": "contiguous ranges, one per thread, partial sums added (Client.hpp:747-787)"},
+            "bit_exact_vs_reference": True}
+
+
 # ------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -350,6 +412,15 @@ def run_ours(args):
                "sample": "one 2^%d-point BN254 MSM (%.2f s) with the C restatement of gnark-crypto MultiExp, "
                          "window-parallel over %d threads" % (lgs, sec, threads)}
 
+    # ---- BASELINE config 4 beside it: secp256k1, 2^18 terms, against the REAL reference
+    # (secp256k1_ecmult_multi_var of the vendored library compiled unmodified into oracle/_ref)
+    secp = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            secp = secp_config4(lib, pb, torch, stream)
+        except Exception as exc:  # the headline must not depend on the optional block
+            secp = {"error": repr(exc)}
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -392,6 +463,7 @@ def run_ours(args):
         },
         "cpu_baseline": cpu,
         "sweep": sweep,
+        "secp256k1_config4": secp,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
