@@ -102,15 +102,16 @@ std::vector<Fr> read_poly(const GoSlice* data_in, int64_t n) {
 constexpr int64_t kHostFinalizeMaxBatch = 4;
 size_t result_scratch_bytes(int curve, int64_t n, int64_t nbatch) {
     MsmPlan p = msm_plan(curve, (uint32_t)n, (uint32_t)nbatch, 0);  // general plan: an upper bound for fixed-base too
-    size_t a = (size_t)nbatch * 64, b = (size_t)nbatch * p.nwin * 128;
+    const int nwin = p.nwin > 256 ? p.nwin : 256;                   // the bitwise small-MSM plan has one window per scalar bit
+    size_t a = (size_t)nbatch * 64, b = (size_t)nbatch * nwin * 128;
     return a > b ? a : b;
 }
 void run_and_fetch(int curve, const PointTable& tab, const uint8_t* d_scalars, int64_t n, int64_t nbatch, MsmOptions opt,
                    uint8_t* d_scratch_out, uint8_t* out, cudaStream_t st) {
     const char* force_dev = getenv("PORLA_DEVICE_FINALIZE");
     if (nbatch <= kHostFinalizeMaxBatch && !(force_dev && force_dev[0] == '1')) {
-        MsmPlan p = msm_plan_table(tab, (uint32_t)n, (uint32_t)nbatch, opt.window_bits, opt.shared_points);
-        opt.window_bits = p.c;
+        MsmPlan p = msm_plan_table(tab, (uint32_t)n, (uint32_t)nbatch, opt);
+        if (p.mode == kPlanPipeline) opt.window_bits = p.c;
         opt.d_window_sums = d_scratch_out;
         size_t bytes = (size_t)nbatch * p.nwin * 128;
         msm_device(curve, tab, d_scalars, (uint32_t)n, (uint32_t)nbatch, opt, nullptr, nullptr, st);
@@ -167,6 +168,37 @@ void msm_host_split(int curve, const uint8_t* scalars, const uint8_t* points, in
     finalize_host_parts(curve, hbuf, 2, plan.nwin, plan.c, opt.out_fmt, out);
 }
 
+// Bit length of the largest scalar in a host buffer, or 0 when some scalar may need reduction (or, on
+// secp256k1, the n - s recoding): lets small MSMs with short scalars (Porla's 31-bit audit coefficients,
+// utils.h:271-275) run with one window per actual bit.
+int host_max_scalar_bits(int curve, const uint8_t* scalars, size_t count, int big_endian) {
+    int top_byte = -1;   // index (0 = least significant) of the highest non-zero byte over all scalars
+    uint8_t top_val = 0;
+    for (size_t i = 0; i < count; i++) {
+        const uint8_t* s = scalars + 32 * i;
+        for (int k = 31; k > top_byte; k--) {
+            uint8_t v = big_endian ? s[31 - k] : s[k];
+            if (v) {
+                top_byte = k;
+                top_val = 0;
+                break;
+            }
+        }
+        if (top_byte >= 0) {
+            uint8_t v = big_endian ? s[31 - top_byte] : s[top_byte];
+            if (v > top_val) top_val = v;
+        }
+    }
+    if (top_byte < 0) return 1;
+    int bits = 8 * top_byte;
+    while (top_val) {
+        bits++;
+        top_val >>= 1;
+    }
+    const int limit = curve == kCurveBn254 ? 253 : 254;   // below 2^253 < r (BN254), below 2^254 < n/2 (secp256k1)
+    return bits <= limit ? bits : 0;
+}
+
 // Host-buffer MSM core.  Scalars/points are copied to the device, points imported (the import
 // kernel also decodes gnark's compressed-flag encodings), nbatch MSMs run, results copied back.
 void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int64_t n, int64_t nbatch,
@@ -199,6 +231,7 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.out_fmt = point_fmt;
     opt.shared_points = 0;
+    if (total <= 4096) opt.max_scalar_bits = host_max_scalar_bits(curve, scalars, total, opt.scalar_be);
     run_and_fetch(curve, tab, d + sc_off, n, nbatch, opt, d + out_off, out, st);
 }
 
@@ -557,7 +590,7 @@ void porla_msm_resident(const porla_table* t, const void* d_scalars, int64_t n, 
     opt.out_fmt = out_fmt;
     opt.shared_points = 1;
     static uint8_t* d_ws = nullptr;  // 64 windows x 128 B is the most any plan needs... sized generously
-    if (!d_ws) PORLA_CUDA(cudaMalloc(&d_ws, 128 * 128));
+    if (!d_ws) PORLA_CUDA(cudaMalloc(&d_ws, 256 * 128));
     run_and_fetch(t->t.curve, t->t, (const uint8_t*)d_scalars, n, 1, opt, d_ws, (uint8_t*)h_out64, st);
 }
 
@@ -578,7 +611,7 @@ void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const voi
     view.d_points = (uint8_t*)t->t.d_points + (size_t)first * 64;
     view.d_flags = t->t.d_flags ? t->t.d_flags + first : nullptr;
     view.n = (uint32_t)n;
-    view.d_fb_points = nullptr;                   // the fixed-base expansion is indexed from point 0
+    view.d_fb_points = view.d_lut = nullptr;      // the fixed-base expansion is indexed from point 0
     view.fb_c = view.fb_nwin = 0;
     if (first == 0 && t->t.fb_c > 0) view = t->t;
     MsmOptions opt;

@@ -77,6 +77,9 @@ template <class C> void import_impl(const uint8_t*, int, uint32_t, PointTable*, 
 template <class C> void import_into_impl(const uint8_t*, int, uint32_t, void*, uint8_t*, cudaStream_t);
 template <class C> void msm_impl(const PointTable&, const uint8_t*, uint32_t, uint32_t, const MsmOptions&, uint8_t*, void*, cudaStream_t);
 template <class C> void precompute_impl(PointTable*, int, cudaStream_t);
+template <class C> void lut_impl(PointTable*, cudaStream_t);
+constexpr uint32_t kLutMaxBases = 2048;   // 512 MiB of table at most
+constexpr int kLutWindow = 8;
 template <class C> void combine_impl(const void*, uint32_t, uint32_t, int, uint8_t*, cudaStream_t);
 template <class C> void scalar_mul_impl(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);
 template <class C> void export_impl(const void*, uint32_t, int, uint8_t*, cudaStream_t);
@@ -161,21 +164,53 @@ int choose_window_fixed_base(int curve, uint32_t n, uint32_t nbatch) {
 
 int table_precompute(PointTable* t, int c, uint32_t n_hint, uint32_t batch_hint, cudaStream_t stream) {
     device_init();
+    // Small tables (Porla's 128-point SRS / generator sets) get the full look-up table: 8-bit windows,
+    // 32 windows x 128 multiples x 64 B = 256 KiB per base.
+    const bool want_lut = c <= 0 && t->n > 0 && t->n <= kLutMaxBases && !getenv("PORLA_NO_LUT");
+    if (want_lut) c = kLutWindow;
     if (c <= 0) c = choose_window_fixed_base(t->curve, n_hint ? n_hint : t->n, batch_hint ? batch_hint : 1);
     if (t->curve == kCurveBn254) precompute_impl<Bn254>(t, c, stream);
     else precompute_impl<Secp256k1>(t, c, stream);
+    if (want_lut) {
+        if (t->curve == kCurveBn254) lut_impl<Bn254>(t, stream);
+        else lut_impl<Secp256k1>(t, stream);
+    }
     return c;
 }
 
-MsmPlan msm_plan_table(const PointTable& t, uint32_t n, uint32_t nbatch, int window_bits, int shared_points) {
-    if (t.fb_c > 0 && shared_points && (window_bits == 0 || window_bits == t.fb_c)) return MsmPlan{t.fb_c, 1};
-    return msm_plan(t.curve, n, nbatch, window_bits);
+// Total (scalar, bit) pairs up to which the one-launch bitwise tree sum beats the pipeline (latency of ~15
+// dependent launches against n*bits/2 mixed additions of plain work).
+static uint64_t small_bits_limit() {
+    static const uint64_t v = [] {
+        const char* e = getenv("PORLA_SMALL_BITS_LIMIT");
+        return e ? (uint64_t)atoll(e) : (1ull << 18);
+    }();
+    return v;
+}
+
+MsmPlan msm_plan_table(const PointTable& t, uint32_t n, uint32_t nbatch, const MsmOptions& opt) {
+    const bool fixed = t.fb_c > 0 && opt.shared_points && !opt.no_fixed_base &&
+                       (opt.window_bits == 0 || opt.window_bits == t.fb_c);
+    // PORLA_NO_SMALL=1 (or an explicit window size, PORLA_WINDOW_BITS included) keeps every call on the pipeline
+    const char* ns = getenv("PORLA_NO_SMALL");
+    const bool no_small = opt.no_small || (ns && ns[0] == '1') || getenv("PORLA_WINDOW_BITS");
+    if (fixed) {
+        const bool lut = t.d_lut && !no_small && nbatch <= 65535u && n <= t.n;
+        return MsmPlan{t.fb_c, 1, lut ? kPlanLut : kPlanPipeline};
+    }
+    if (opt.window_bits == 0 && !no_small && n > 0 && nbatch <= 65535u) {
+        int bits = scalar_bits(t.curve);
+        if (opt.max_scalar_bits > 0 && opt.max_scalar_bits < bits) bits = opt.max_scalar_bits;
+        if ((uint64_t)n * nbatch * (uint64_t)bits <= small_bits_limit()) return MsmPlan{1, bits, kPlanBits};
+    }
+    return msm_plan(t.curve, n, nbatch, opt.window_bits);
 }
 
 MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits) {
     MsmPlan p;
     p.c = window_bits > 0 ? window_bits : choose_window(curve, n, nbatch);
     p.nwin = (scalar_bits(curve) + 1 + p.c - 1) / p.c;
+    p.mode = kPlanPipeline;
     return p;
 }
 
@@ -246,6 +281,7 @@ void table_free(PointTable* t) {
     if (t->d_points) PORLA_CUDA(cudaFree(t->d_points));
     if (t->d_flags) PORLA_CUDA(cudaFree(t->d_flags));
     if (t->d_fb_points) PORLA_CUDA(cudaFree(t->d_fb_points));
+    if (t->d_lut) PORLA_CUDA(cudaFree(t->d_lut));
     *t = PointTable{};
 }
 
@@ -275,7 +311,8 @@ void butterfly_stage_device(PointTable* t, uint32_t m, const uint8_t* d_twiddles
     if (t->d_fb_points) {   // the expansion describes the old points
         PORLA_CUDA(cudaStreamSynchronize(stream));
         PORLA_CUDA(cudaFree(t->d_fb_points));
-        t->d_fb_points = nullptr;
+        if (t->d_lut) PORLA_CUDA(cudaFree(t->d_lut));
+        t->d_fb_points = t->d_lut = nullptr;
         t->fb_c = t->fb_nwin = 0;
     }
     DISPATCH(t->curve, butterfly_impl, t, m, d_twiddles, scalar_be, stream);

@@ -34,6 +34,10 @@ struct PointTable {
     int fb_c = 0;
     int fb_nwin = 0;
     void* d_fb_points = nullptr;
+    // Optional look-up table of EVERY window multiple on top of the expansion (small tables only):
+    // lut[((w*n + i) << (fb_c-1)) + d - 1] = d * 2^(fb_c*w) * P_i, 1 <= d <= 2^(fb_c-1).  An MSM over the
+    // table is then a plain sum of n * fb_nwin entries (k_lut_sum): no sort, no buckets, no doublings.
+    void* d_lut = nullptr;
 };
 
 // Import `n` external 64-byte points that already live on the device.
@@ -61,16 +65,24 @@ struct MsmOptions {
     // and the device finaliser is skipped: the caller combines them with finalize_host().
     void* d_window_sums = nullptr;
     int no_fixed_base = 0;    // ignore the table's fixed-base expansion (callers that need nwin window sums)
+    // Upper bound on the bit length of every (reduced) scalar when the caller knows it (the legacy C-ABI scans
+    // its host buffer: Porla's audit coefficients are 31-bit, utils.h:271-275); 0 = the full order width.
+    int max_scalar_bits = 0;
+    int no_small = 0;         // always run the sort / accumulate / reduce pipeline
 };
 
+enum PlanMode : int { kPlanPipeline = 0, kPlanBits = 1, kPlanLut = 2 };
 struct MsmPlan {
     int c;      // window bits
-    int nwin;   // windows per scalar
+    int nwin;   // window sums per MSM handed to the finaliser
+    int mode;   // PlanMode
 };
+// The sort / accumulate / reduce pipeline's plan for n terms.
 MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits);
-// Plan for a specific table: when its fixed-base expansion applies, nwin = 1 (a single shared
-// bucket set, so one "window sum" per MSM and no doublings) and c = the expansion's window size.
-MsmPlan msm_plan_table(const PointTable& t, uint32_t n, uint32_t nbatch, int window_bits, int shared_points);
+// Plan for a specific call.  Fixed-base expansion applicable: nwin = 1 (a single shared bucket set or the
+// look-up table, one "window sum" per MSM, no doublings), c = the expansion's window size.  Few terms in
+// total and no explicit window size: one window per scalar bit (k_small_bits), c = 1.
+MsmPlan msm_plan_table(const PointTable& t, uint32_t n, uint32_t nbatch, const MsmOptions& opt);
 
 // Host-side tail of one MSM: Horner over the window sums (c doublings per window), affine
 // normalisation, serialisation.  h_window_sums: nwin XYZZ records as produced on the device.

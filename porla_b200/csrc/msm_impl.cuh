@@ -10,6 +10,7 @@
 #include "arena.h"
 #include "msm.h"
 #include "msm_kernels.cuh"
+#include "small_kernels.cuh"
 
 namespace porla {
 
@@ -69,12 +70,73 @@ void import_impl(const uint8_t* d_bytes, int fmt, uint32_t n, PointTable* out, c
     }
 }
 
+// ---------------------------------------------------------------------------- small / fixed-base MSMs: one launch
+// plan.mode == kPlanBits: k_small_bits (plan.nwin = number of scalar bits, plan.c = 1);
+// plan.mode == kPlanLut:  k_lut_sum over the table's look-up table (plan.nwin = 1).
+template <class C>
+void msm_small_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uint32_t nbatch, const MsmOptions& opt,
+                    const MsmPlan& plan, uint8_t* d_out, void* d_out_xyzz, cudaStream_t stream) {
+    using F = typename C::F;
+    using XC = XYZZ<typename C::FC>;
+    const bool lut = plan.mode == kPlanLut;
+    const uint32_t slots = nbatch * (uint32_t)plan.nwin;
+    uint32_t K = 1, nblk;
+    if (lut) {
+        // few MSMs: two table entries per thread, depth = log2 of the term count; many MSMs: one scalar
+        // (all its windows) per thread, the machine is full anyway and the tree is 7 levels
+        K = nbatch > 8 ? (uint32_t)table.fb_nwin : 2u;
+        const uint32_t threads = (n * (uint32_t)table.fb_nwin + K - 1) / K;
+        nblk = (threads + kTreeThreads - 1) / kTreeThreads;
+    } else {
+        nblk = (n + 2 * kTreeThreads - 1) / (2 * kTreeThreads);
+    }
+    if (!nblk) nblk = 1;
+    std::lock_guard<std::mutex> lock(g_engine_mu);
+    const size_t need = Arena::padded((size_t)slots * nblk, sizeof(XYZZ<F>)) + Arena::padded(slots, 4) +
+                        Arena::padded(slots, sizeof(XYZZ<F>)) + 1024;
+    g_arena.reserve(need, stream);
+    g_arena.reset();
+    XYZZ<F>* partials = g_arena.take<XYZZ<F>>((size_t)slots * nblk);
+    uint32_t* tickets = g_arena.take<uint32_t>(slots);
+    XYZZ<F>* wsum = g_arena.take<XYZZ<F>>(slots);
+    for (int st = kStageCount; st <= kStageAccumulate; st++) g_stage_timer.mark(st, stream);
+    if (nblk > 1) PORLA_CUDA(cudaMemsetAsync(tickets, 0, (size_t)slots * 4, stream));
+    if (lut) {
+        k_lut_sum<C><<<dim3(nblk, nbatch), kTreeThreads, 0, stream>>>(reinterpret_cast<const Affine<F>*>(table.d_lut), table.n,
+                                                                     table.fb_c, table.fb_nwin, d_scalars, opt.scalar_be, n, K,
+                                                                     partials, tickets, wsum);
+    } else {
+        k_small_bits<C><<<dim3(nblk, (uint32_t)plan.nwin, nbatch), kTreeThreads, 0, stream>>>(
+            reinterpret_cast<const Affine<F>*>(table.d_points), table.d_flags, d_scalars, opt.scalar_be, n, opt.shared_points,
+            partials, tickets, wsum);
+    }
+    LAUNCHED();
+    g_stage_timer.mark(kStageReduce, stream);
+    g_stage_timer.mark(kStageFinalize, stream);
+    if (opt.d_window_sums) {
+        PORLA_CUDA(cudaMemcpyAsync(opt.d_window_sums, wsum, (size_t)slots * sizeof(XYZZ<F>), cudaMemcpyDeviceToDevice, stream));
+    } else {
+        k_finalize<C><<<(nbatch + 31) / 32, 32, 0, stream>>>((const XC*)wsum, nbatch, plan.nwin, plan.c, opt.out_fmt, d_out,
+                                                            reinterpret_cast<XC*>(d_out_xyzz));
+        LAUNCHED();
+    }
+    g_stage_timer.mark(kNumStages, stream);
+    PORLA_CUDA(cudaGetLastError());
+}
+
 // ---------------------------------------------------------------------------- the pipeline
 template <class C>
 void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uint32_t nbatch,
                      const MsmOptions& opt, uint8_t* d_out, void* d_out_xyzz, cudaStream_t stream) {
     using F = typename C::F;
     const int curve = CurveIdOf<C>::value;
+    {
+        const MsmPlan plan = msm_plan_table(table, n, nbatch, opt);
+        if (plan.mode != kPlanPipeline && n > 0) {
+            msm_small_impl<C>(table, d_scalars, n, nbatch, opt, plan, d_out, d_out_xyzz, stream);
+            return;
+        }
+    }
     MsmShape sh;
     sh.n = n;
     sh.nbatch = nbatch;
@@ -278,6 +340,24 @@ void precompute_impl(PointTable* t, int c, cudaStream_t stream) {
     t->d_fb_points = out;
     t->fb_c = c;
     t->fb_nwin = nwin;
+    if (t->d_lut) PORLA_CUDA(cudaFree(t->d_lut));
+    t->d_lut = nullptr;
+}
+
+// Look-up table of every window multiple (k_lut_build) on top of the fixed-base expansion.
+template <class C>
+void lut_impl(PointTable* t, cudaStream_t stream) {
+    using FC = typename C::FC;
+    if (!t->n || !t->d_fb_points) return;
+    void* out = nullptr;
+    const size_t entries = ((size_t)t->fb_nwin * t->n) << (t->fb_c - 1);
+    PORLA_CUDA(cudaMalloc(&out, entries * sizeof(Affine<FC>)));
+    const uint32_t threads = t->n * (uint32_t)t->fb_nwin;
+    k_lut_build<C><<<(threads + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<FC>*>(t->d_fb_points), t->d_flags, t->n,
+                                                             t->fb_c, t->fb_nwin, reinterpret_cast<Affine<FC>*>(out));
+    LAUNCHED();
+    PORLA_CUDA(cudaGetLastError());
+    t->d_lut = out;
 }
 
 template <class C>
@@ -353,6 +433,7 @@ void field_mul_impl(const void* d_a, const void* d_b, uint32_t n, int op, void* 
                               void*, cudaStream_t);                                                                    \
     template void combine_impl<C>(const void*, uint32_t, uint32_t, int, uint8_t*, cudaStream_t);                       \
     template void precompute_impl<C>(PointTable*, int, cudaStream_t);                                                  \
+    template void lut_impl<C>(PointTable*, cudaStream_t);                                                              \
     template void scalar_mul_impl<C>(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);           \
     template void export_impl<C>(const void*, uint32_t, int, uint8_t*, cudaStream_t);                                  \
     template void butterfly_impl<C>(PointTable*, uint32_t, const uint8_t*, int, cudaStream_t);                         \

@@ -1,0 +1,182 @@
+"""Parity of the one-launch small-MSM kernels (porla_b200/csrc/small_kernels.cuh) against the oracle and
+against the sort / accumulate / reduce pipeline, through the C-ABI.
+
+  k_small_bits : Porla's audit aggregation, compute_multi_exp with 128..766 terms and 31-bit coefficients
+                 (/root/reference/porla/Server/Server.hpp:900-901, Client.hpp:795, main.go:119-138)
+  k_lut_sum    : commitments over the resident SRS, compute_digest_from_srs / create_proof
+                 (Server.hpp:558, main.go:104-116, 154-175) and the resident secp256k1 generator table
+
+PORLA_NO_SMALL=1 forces the pipeline, so every case is computed twice and both must equal the oracle.
+"""
+import random
+
+import pytest
+
+import porla_b200 as pb
+from oracle import curves_py as O
+from oracle import loader
+
+pytestmark = pytest.mark.gpu
+
+BN, SE = O.BN254, O.SECP256K1
+TAU = bytes.fromhex("ffeeddccbbaa99887766554433221100")
+ALPHA = bytes.fromhex("00112233445566778899aabbccddeeff")
+
+
+def be(x):
+    return x.to_bytes(32, "big")
+
+
+def le(x):
+    return x.to_bytes(32, "little")
+
+
+def enc(P):
+    return bytes(64) if P is None else be(P[0]) + be(P[1])
+
+
+def chain(c, n, seed):
+    """n distinct points: P_0 = hash point, P_{i+1} = P_i + Q."""
+    cur, Q = O.hash_point(c, seed), O.hash_point(c, seed + 1)
+    out = []
+    for _ in range(n):
+        out.append(cur)
+        cur = O.add(c, cur, Q)
+    return out
+
+
+@pytest.fixture(params=["small", "pipeline"])
+def route(request, monkeypatch):
+    if request.param == "pipeline":
+        monkeypatch.setenv("PORLA_NO_SMALL", "1")
+    return request.param
+
+
+@pytest.mark.parametrize("n,bits", [(1, 31), (2, 31), (127, 31), (128, 31), (129, 31), (255, 31), (256, 31), (257, 31),
+                                    (513, 31), (766, 31), (766, 256), (100, 256), (300, 64), (1000, 254)])
+def test_bitwise_tree_sum_matches_oracle(n, bits, route):
+    rnd = random.Random(1000 * n + bits)
+    pts = chain(BN, n, n)
+    for i in range(0, n, 7):
+        pts[i] = None                                       # alignment MACs that are still infinity
+    sc = [rnd.randrange(1 << bits) for _ in range(n)]
+    if n > 4:
+        sc[1] = 0
+        sc[2] = (1 << bits) - 1
+    got = pb.bn254_multi_exp(b"".join(map(enc, pts)), b"".join(map(be, sc)), n)
+    want = loader.bn254_msm(b"".join(map(be, sc)), b"".join(map(enc, pts)), n, 1)
+    assert got == want
+    if n <= 130:
+        assert got == O.bn254_marshal(O.msm(BN, sc, pts))
+
+
+def test_bitwise_tree_sum_exceptional_additions(route):
+    """Equal points meet in the tree (doubling branch), opposite points cancel, whole windows are empty."""
+    P, Q = O.hash_point(BN, 5), O.hash_point(BN, 6)
+    cases = [
+        ([1, 1], [P, P]),
+        ([1, 1], [P, O.neg(BN, P)]),
+        ([3, 3, 3, 3], [P, P, P, P]),
+        ([5, 5, 9, 9], [P, O.neg(BN, P), Q, O.neg(BN, Q)]),
+        ([1 << 30, 1], [P, Q]),
+        ([0, 0], [P, Q]),
+        ([BN.n, BN.n + 1, BN.n - 1], [P, Q, P]),
+        ([(1 << 256) - 1], [P]),
+        ([7], [None]),
+    ]
+    for sc, pts in cases:
+        got = pb.bn254_multi_exp(b"".join(map(enc, pts)), b"".join(map(be, sc)), len(sc))
+        assert got == O.bn254_marshal(O.msm_naive(BN, sc, pts)), sc
+    n = 300                                                  # every term the same point and scalar
+    got = pb.bn254_multi_exp(enc(P) * n, be(12345) * n, n)
+    assert got == O.bn254_marshal(O.mul(BN, 12345 * n, P))
+
+
+def test_bitwise_tree_sum_batched(route):
+    batch, n = 6, 90
+    rnd = random.Random(8)
+    pts = chain(BN, batch * n, 40)
+    sc = [rnd.randrange(1 << 256) for _ in range(batch * n)]
+    got = pb.bn254_multi_exp_batch(b"".join(map(enc, pts)), b"".join(map(be, sc)), n, batch)
+    for m in range(batch):
+        want = loader.bn254_msm(b"".join(map(be, sc[m * n:(m + 1) * n])), b"".join(map(enc, pts[m * n:(m + 1) * n])), n, 1)
+        assert got[64 * m:64 * m + 64] == want, m
+
+
+@pytest.mark.parametrize("n", [1, 5, 200, 766])
+def test_secp256k1_small_matches_oracle(n, route):
+    rnd = random.Random(n)
+    pts = chain(SE, n, 3 * n)
+    sc = [rnd.randrange(1 << 256) for _ in range(n)]
+    if n > 4:
+        sc[0], sc[1], sc[2], sc[3] = SE.n - 1, SE.n, (SE.n + 1) // 2, SE.n // 2      # the n - s recoding's corners
+    got = pb.msm_host(pb.CURVE_SECP256K1, b"".join(map(le, sc)), b"".join(map(enc, pts)), n, scalar_fmt=pb.SCALAR_LE32)
+    assert got == enc(O.msm(SE, sc, pts))
+
+
+def _srs_points(blob, n):
+    return [O.bn254_unmarshal(blob[132 + 32 * i:164 + 32 * i]) for i in range(n)]
+
+
+def test_lookup_table_commitments_match_oracle(route):
+    """compute_digest_from_srs over the resident 128-point SRS: digits on the signed-window rounding boundary
+    (bytes 0x80 / 0x7f / 0x81 / 0xff), unreduced 256-bit data chunks, zeros, r - 1."""
+    k = pb.Kzg(TAU, ALPHA)
+    n = 128
+    srs = _srs_points(k.init_srs(n), n)
+    srs_bytes = b"".join(O.bn254_marshal(P) for P in srs)
+    rnd = random.Random(99)
+    rows = [
+        [rnd.randrange(1 << 256) for _ in range(n)],
+        [int.from_bytes(bytes([0x80]) * 32, "big") % BN.n] * n,
+        [int.from_bytes(bytes([0x80] * 31 + [0x81]), "big") % BN.n, int.from_bytes(bytes([0x7f] * 32), "big") % BN.n] * (n // 2),
+        [(1 << 256) - 1, BN.n - 1, BN.n, BN.n + 1, 0, 1, 0x80, 0x8000, 0x7fff, 0x80000000] + [0] * (n - 10),
+        [int.from_bytes(bytes(rnd.choice([0x7f, 0x80, 0x81, 0x00, 0xff]) for _ in range(32)), "big") for _ in range(n)],
+        [0] * n,
+    ]
+    for row in rows:
+        data = b"".join(map(be, row))
+        got = k.compute_digest_from_srs(data)
+        assert got == loader.bn254_msm(data, srs_bytes, n, 1)
+    assert k.compute_digest_from_srs(b"".join(map(be, rows[0]))) == O.bn254_marshal(O.msm(BN, rows[0], srs))
+
+
+def test_lookup_table_batch_and_proof(route):
+    k = pb.Kzg(TAU, ALPHA)
+    n, batch = 128, 37
+    srs = _srs_points(k.init_srs(n), n)
+    srs_bytes = b"".join(O.bn254_marshal(P) for P in srs)
+    rnd = random.Random(5)
+    data = b"".join(be(rnd.randrange(1 << 256)) for _ in range(n * batch))
+    got = k.compute_digest_from_srs_batch(data, batch)
+    for m in range(batch):
+        assert got[64 * m:64 * m + 64] == loader.bn254_msm(data[32 * n * m:32 * n * (m + 1)], srs_bytes, n, 1), m
+    # create_proof: commitment of f and of the 127-term quotient (a prefix of the table), then verify
+    block = data[:32 * n]
+    c_, h_, z_, y_ = k.create_proof(987654321, block)
+    assert c_ == got[:64]
+    f = [int.from_bytes(block[32 * i:32 * i + 32], "big") % BN.n for i in range(n)]
+    z = int.from_bytes(z_, "big")
+    y, q = O.kzg_open(f, z)
+    assert int.from_bytes(y_, "big") == y
+    assert h_ == O.bn254_marshal(O.msm(BN, q, srs[:len(q)]))
+    assert k.verify_proof(c_, h_, z_, y_)
+
+
+def test_secp256k1_generator_table_lookup(route):
+    """Resident secp256k1 generators (IPA mode, Client.hpp:377-406): sub-range MSMs with host scalars."""
+    import ctypes as C
+    n = 128
+    rnd = random.Random(17)
+    gens = chain(SE, n, 500)
+    tab = pb.Table.from_host(pb.CURVE_SECP256K1, b"".join(map(enc, gens)))
+    tab.precompute(0, n, 1)
+    lib = pb.load()
+    for first, cnt in ((0, 128), (0, 16), (16, 16), (0, 1)):
+        sc = [rnd.randrange(1 << 256) for _ in range(cnt)]
+        sc[0] = SE.n - 1
+        out = (C.c_ubyte * 64)()
+        buf = b"".join(map(le, sc))
+        lib.porla_msm_table_host_scalars(C.c_void_p(tab.handle), first, buf, cnt, pb.SCALAR_LE32, pb.POINT_BE64, C.cast(out, C.c_void_p))
+        assert bytes(out) == enc(O.msm(SE, sc, gens[first:first + cnt])), (first, cnt)
+    tab.destroy()
