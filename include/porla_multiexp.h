@@ -205,6 +205,11 @@ int porla_secp256k1_gej_serialize(const porla_secp256k1_gej* a, unsigned char ou
  * field code issues them; 2: 32-bit mad.lo.  Runs at least min_seconds. */
 double porla_measure_pint(int variant, double min_seconds);
 
+/* Latency probe (one block on one SM): cycles and nanoseconds per operation of a dependent chain of field
+ * products (mode 0; 1 / 2: two / four independent chains per thread; 3: squarings) or point operations
+ * (4: XYZZ add, 5: the same with the outlined multiplier, 6: mixed add, 7: doubling), `warps` warps. */
+int porla_debug_latency(int curve, int mode, int warps, int iters, double* cycles_per_op, double* ns_per_op);
+
 /* ---- test hooks (host buffers; GPU kernels underneath) */
 /* out[i] = a[i] (*) b[i], the device field product on raw 8x32 LE limbs: a*b mod p for secp256k1,
  * the Montgomery product a*b*2^-256 mod p for BN254. */

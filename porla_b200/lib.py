@@ -33,7 +33,7 @@ NEW_SYMBOLS = [
     "porla_stage_timing_enable", "porla_stage_timing_read",
     "porla_butterfly_stage_device", "bn254_butterfly_stage", "bn254_align_mac_batch",
     "porla_msm_table_host_scalars", "porla_secp256k1_table_create", "porla_secp256k1_ecmult_multi_table",
-    "porla_debug_pairing_selfcheck",
+    "porla_debug_pairing_selfcheck", "porla_debug_latency",
 ]
 
 
@@ -122,6 +122,7 @@ def load() -> C.CDLL:
         "porla_secp256k1_table_create": (P, [C.POINTER(SecpGe), C.c_size_t]),
         "porla_secp256k1_ecmult_multi_table": (I, [P, C.c_size_t, C.POINTER(SecpScalar), C.c_size_t, C.POINTER(SecpGej)]),
         "porla_debug_pairing_selfcheck": (I, [I]),
+        "porla_debug_latency": (I, [I, I, I, I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "porla_debug_field_mul": (None, [I, P, P, C.c_int64, P]),
         "porla_debug_field_op": (None, [I, I, P, P, C.c_int64, P]),
         "porla_debug_point_add_host": (None, [I, P, P, C.c_int64, I, P]),
