@@ -220,6 +220,55 @@ def secp_config4(lib, pb, torch, stream, log2n=18):
             "bit_exact_vs_reference": True}
 
 
+def porla_calls(lib, pb):
+    """The second half of BASELINE.json's metric, "Porla update/audit latency": the C-ABI calls one KZG-mode audit and
+    update issue (Server.hpp:564-931, Client.hpp:633-892, Server.hpp:401-476) with the reference's
+    shapes (NUM_CHUNKS = 128, 31-bit audit coefficients, 128 / 766 aggregated MACs), timed per call through the legacy
+    symbols with host buffers, beside the CPU port of the same MSMs on one host thread."""
+    import random
+    from oracle import curves_py as O, loader
+    rnd = random.Random(1)
+    be = lambda v: v.to_bytes(32, "big")
+    k = pb.Kzg(bytes.fromhex("ffeeddccbbaa99887766554433221100"), bytes.fromhex("00112233445566778899aabbccddeeff"))
+    blob = k.init_srs(128)
+    srs = b"".join(O.bn254_marshal(O.bn254_unmarshal(blob[132 + 32 * i:164 + 32 * i])) for i in range(128))
+    G = O.bn254_marshal((1, 2))
+    step = O.bn254_marshal(O.mul(O.BN254, 0xABCDEF12345, (1, 2)))
+
+    def timeit(fn, reps=50, warm=5):
+        for _ in range(warm):
+            fn()
+        t = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t) / reps * 1e3
+
+    out = {"unit": "ms per call", "cpu": "C restatement (oracle/bn254_oracle.c), 1 host thread"}
+    block = b"".join(be(rnd.randrange(1 << 256)) for _ in range(128))
+    for npts in (128, 766):
+        macs = bytearray(loader.bn254_point_chain(G, step, npts))
+        for i in range(0, npts, 7):
+            macs[64 * i:64 * i + 64] = bytes(64)
+        coeff = b"".join(pb.bn254_scalar_set_int(rnd.randrange(1 << 31)) for _ in range(npts))
+        got = pb.bn254_multi_exp(bytes(macs), coeff, npts)
+        if got != loader.bn254_msm(coeff, bytes(macs), npts, 1):
+            raise SystemExit("bench self-check failed: audit-shaped compute_multi_exp differs from the oracle")
+        out["compute_multi_exp_%d" % npts] = {"gpu": timeit(lambda: pb.bn254_multi_exp(bytes(macs), coeff, npts)),
+                                              "cpu": timeit(lambda: loader.bn254_msm(coeff, bytes(macs), npts, 1), reps=5, warm=1)}
+    if k.compute_digest_from_srs(block) != loader.bn254_msm(block, srs, 128, 1):
+        raise SystemExit("bench self-check failed: compute_digest_from_srs differs from the oracle")
+    out["compute_digest_from_srs"] = {"gpu": timeit(lambda: k.compute_digest_from_srs(block)),
+                                      "cpu": timeit(lambda: loader.bn254_msm(block, srs, 128, 1), reps=5, warm=1)}
+    out["create_proof"] = {"gpu": timeit(lambda: k.create_proof(123456789, block))}
+    c_, h_, z_, y_ = k.create_proof(123456789, block)
+    out["verify_proof_host"] = {"gpu": timeit(lambda: k.verify_proof(c_, h_, z_, y_), reps=5, warm=1)}
+    blocks = b"".join(be(rnd.randrange(1 << 256)) for _ in range(128 * 1024))
+    out["compute_digest_from_srs_batch_1024"] = {"gpu": timeit(lambda: k.compute_digest_from_srs_batch(blocks, 1024), reps=3, warm=1)}
+    for npts in (128, 766):   # Server::audit's MSM share: two aggregations + align_MAC commitment + create_proof
+        out["server_audit_msm_total_%d" % npts] = {"gpu": 2 * out["compute_multi_exp_%d" % npts]["gpu"] + out["compute_digest_from_srs"]["gpu"] + out["create_proof"]["gpu"]}
+    return out
+
+
 # ------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -421,6 +470,13 @@ def run_ours(args):
         except Exception as exc:  # the headline must not depend on the optional block
             secp = {"error": repr(exc)}
 
+    calls = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            calls = porla_calls(lib, pb)
+        except Exception as exc:
+            calls = {"error": repr(exc)}
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -464,6 +520,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "sweep": sweep,
         "secp256k1_config4": secp,
+        "porla_calls": calls,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

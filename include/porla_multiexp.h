@@ -173,6 +173,15 @@ extern void bn254_butterfly_stage(GoSlice* points, GoInt n, GoInt m, GoSlice* tw
  * reference adds to the alignment MACs with bn254_add (Server.hpp:560). */
 extern void bn254_align_mac_batch(GoSlice* data, GoInt batch, GoSlice* align_out);
 
+/* Server::audit's block aggregation and its alignment, KZG branch (Server.hpp:790-828 and 903 -> 478-562):
+ *       B[j] = sum_i coefs[i] * blocks[i][j]                       plain integers, no modulus (Server.hpp:798-800)
+ *       mod  = B[j] % PRIME_MODULUS;  c[j] = (mod - B[j]) % r;  B[j] = mod;   align = kzg.Commit(c)
+ * coefs: n x 4 bytes little-endian, the 31-bit audit coefficients (Client.hpp:700); blocks: n x n_samples chunks of
+ * 64 bytes (little-endian integers below LCM, utils.h:42).  b_out receives n_samples x 32 bytes big-endian (the
+ * bn254_scalar form create_proof takes, Server.hpp:388-392), align_out the 64-byte value the reference adds to the
+ * combined alignment MAC (Server.hpp:560).  One aggregation kernel + one look-up-table commitment. */
+extern void bn254_audit_aggregate(GoSlice* coefs, GoSlice* blocks, GoInt n, GoSlice* b_out, GoSlice* align_out);
+
 /* ---- secp256k1 (IPA mode).  Mirrors of the reference structs (field_5x52.h:12-21,
  * group.h:13-28, scalar_4x64.h:13-15, util.h:19-22, ecmult.h:32). */
 typedef struct { uint64_t n[5]; } porla_secp256k1_fe;

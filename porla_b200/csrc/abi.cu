@@ -611,9 +611,10 @@ void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const voi
     view.d_points = (uint8_t*)t->t.d_points + (size_t)first * 64;
     view.d_flags = t->t.d_flags ? t->t.d_flags + first : nullptr;
     view.n = (uint32_t)n;
-    view.d_fb_points = view.d_lut = nullptr;      // the fixed-base expansion is indexed from point 0
-    view.fb_c = view.fb_nwin = 0;
-    if (first == 0 && t->t.fb_c > 0) view = t->t;
+    if (t->t.fb_c > 0) {                          // the expansion's rows keep their stride; start them at `first`
+        view.d_fb_points = (uint8_t*)t->t.d_fb_points + (size_t)first * 64;
+        if (t->t.d_lut) view.d_lut = (uint8_t*)t->t.d_lut + (((size_t)first << (t->t.fb_c - 1)) * 64);
+    }
     MsmOptions opt;
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.out_fmt = out_fmt;
@@ -689,6 +690,41 @@ void bn254_align_mac_batch(GoSlice* data, GoInt batch, GoSlice* align_out) {
         opt.shared_points = 1;
         run_and_fetch(kCurveBn254, g_kzg.srs_table, d + sc_off, n, batch, opt, d + out_off, res.data(), st);
     }
+    go_copy(align_out, res.data(), res.size());
+}
+
+void bn254_audit_aggregate(GoSlice* coefs, GoSlice* blocks, GoInt n, GoSlice* b_out, GoSlice* align_out) {
+    const int64_t chunks = g_kzg.n_samples;
+    if (n < 0 || n >= (1 << 24)) die("bn254_audit_aggregate: block count out of range");
+    if (coefs->len < n * 4 || blocks->len < n * chunks * 64) die("bn254_audit_aggregate: coefs / blocks shorter than n entries");
+    if (!g_kzg.have_table) {
+        if (g_kzg.srs_g1.empty()) die("SRS not initialised (call init_SRS or init_SRS_from_data first)");
+        upload_srs();
+    }
+    device_init();
+    std::vector<uint8_t> b_mod((size_t)chunks * 32), res(64);
+    {
+        std::lock_guard<std::mutex> lock(g_io_mu);
+        auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        const size_t blk_bytes = (size_t)n * chunks * 64;
+        size_t cf_off = pad(blk_bytes), b_off = cf_off + pad((size_t)n * 4 + 4), c_off = b_off + pad((size_t)chunks * 32),
+               out_off = c_off + pad((size_t)chunks * 32);
+        uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(kCurveBn254, chunks, 1));
+        cudaStream_t st = g_stage.stream;
+        if (n) {
+            PORLA_CUDA(cudaMemcpyAsync(d, blocks->data, blk_bytes, cudaMemcpyHostToDevice, st));
+            PORLA_CUDA(cudaMemcpyAsync(d + cf_off, coefs->data, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        }
+        audit_aggregate_device(reinterpret_cast<const uint32_t*>(d + cf_off), reinterpret_cast<const uint32_t*>(d), (uint32_t)n,
+                               (uint32_t)chunks, d + b_off, d + c_off, st);
+        PORLA_CUDA(cudaMemcpyAsync(b_mod.data(), d + b_off, b_mod.size(), cudaMemcpyDeviceToHost, st));
+        MsmOptions opt;
+        opt.scalar_be = 1;
+        opt.out_fmt = PORLA_POINT_BE64;
+        opt.shared_points = 1;
+        run_and_fetch(kCurveBn254, g_kzg.srs_table, d + c_off, chunks, 1, opt, d + out_off, res.data(), st);
+    }
+    go_copy(b_out, b_mod.data(), b_mod.size());
     go_copy(align_out, res.data(), res.size());
 }
 

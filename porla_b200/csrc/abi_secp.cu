@@ -174,7 +174,11 @@ porla_table* porla_secp256k1_table_create(const porla_secp256k1_ge* points, size
         fe_to_canonical(&points[i].y, xy + 8);
         memcpy(le.data() + 64 * i, xy, 64);
     }
-    return porla_table_create(PORLA_CURVE_SECP256K1, le.data(), (int64_t)n, PORLA_POINT_LE64, 0, nullptr);
+    porla_table* t = porla_table_create(PORLA_CURVE_SECP256K1, le.data(), (int64_t)n, PORLA_POINT_LE64, 0, nullptr);
+    // generators are fixed bases: expand them once (small sets such as Porla's 128 get the full look-up table of
+    // window multiples, so every commitment / IPA round over them is a plain sum of table entries)
+    if (n) porla_table_precompute(t, 0, (int64_t)n, 1, nullptr);
+    return t;
 }
 
 int porla_secp256k1_ecmult_multi_table(const porla_table* t, size_t first, const porla_secp256k1_scalar* scalars, size_t n,

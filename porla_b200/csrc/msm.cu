@@ -85,6 +85,7 @@ template <class C> void scalar_mul_impl(const PointTable&, const uint8_t*, int, 
 template <class C> void export_impl(const void*, uint32_t, int, uint8_t*, cudaStream_t);
 template <class C> void butterfly_impl(PointTable*, uint32_t, const uint8_t*, int, cudaStream_t);
 template <class C> void align_scalars_impl(uint32_t*, uint32_t, uint8_t*, cudaStream_t);
+template <class C> void audit_aggregate_impl(const uint32_t*, const uint32_t*, uint32_t, uint32_t, uint8_t*, uint8_t*, cudaStream_t);
 template <class C> void field_mul_impl(const void*, const void*, uint32_t, int, void*, cudaStream_t);
 
 #define DISPATCH(curve, fn, ...)                                  \
@@ -314,6 +315,7 @@ void butterfly_stage_device(PointTable* t, uint32_t m, const uint8_t* d_twiddles
         if (t->d_lut) PORLA_CUDA(cudaFree(t->d_lut));
         t->d_fb_points = t->d_lut = nullptr;
         t->fb_c = t->fb_nwin = 0;
+        t->fb_n = 0;
     }
     DISPATCH(t->curve, butterfly_impl, t, m, d_twiddles, scalar_be, stream);
 }
@@ -321,6 +323,12 @@ void butterfly_stage_device(PointTable* t, uint32_t m, const uint8_t* d_twiddles
 void align_scalars_device(uint32_t* d_data, uint32_t total, uint8_t* d_scalars_be, cudaStream_t stream) {
     device_init();
     align_scalars_impl<Bn254>(d_data, total, d_scalars_be, stream);   // the reference's KZG branch only (BN254 order)
+}
+
+void audit_aggregate_device(const uint32_t* d_coefs, const uint32_t* d_blocks, uint32_t n, uint32_t chunks, uint8_t* d_b_mod_be,
+                            uint8_t* d_c_be, cudaStream_t stream) {
+    device_init();
+    audit_aggregate_impl<Bn254>(d_coefs, d_blocks, n, chunks, d_b_mod_be, d_c_be, stream);   // KZG branch: BN254 order
 }
 
 void export_points_device(int curve, const void* d_affine, uint32_t n, int fmt, uint8_t* d_out, cudaStream_t stream) {

@@ -33,6 +33,8 @@ struct PointTable {
     // per-window bucket reduction and no doublings in the window combine.
     int fb_c = 0;
     int fb_nwin = 0;
+    uint32_t fb_n = 0;            // row stride of the expansion = length of the table it was built for (a view
+                                  // [first, first + n) of the table keeps it and offsets the pointers by `first`)
     void* d_fb_points = nullptr;
     // Optional look-up table of EVERY window multiple on top of the expansion (small tables only):
     // lut[((w*n + i) << (fb_c-1)) + d - 1] = d * 2^(fb_c*w) * P_i, 1 <= d <= 2^(fb_c-1).  An MSM over the
@@ -112,6 +114,11 @@ void butterfly_stage_device(PointTable* t, uint32_t m, const uint8_t* d_twiddles
 // Server::align_MAC's scalar preparation for `total` chunks of 64 bytes (16 LE limbs, values below
 // PRIME_MODULUS * r): chunk <- chunk % PRIME_MODULUS in place, scalars_be[i] = (chunk % PRIME_MODULUS - chunk) % r.
 void align_scalars_device(uint32_t* d_data, uint32_t total, uint8_t* d_scalars_be, cudaStream_t stream);
+// Server::audit's aggregation of `n` data blocks of `chunks` 64-byte chunks (16 LE limbs) with 31-bit coefficients,
+// followed by align_MAC's arithmetic on the sums: b_mod_be[j] = B_j % PRIME_MODULUS and
+// c_be[j] = (B_j % PRIME_MODULUS - B_j) % r as 32-byte big-endian scalars, B_j = sum_i coefs[i] * blocks[i][j].
+void audit_aggregate_device(const uint32_t* d_coefs, const uint32_t* d_blocks, uint32_t n, uint32_t chunks, uint8_t* d_b_mod_be,
+                            uint8_t* d_c_be, cudaStream_t stream);
 void export_points_device(int curve, const void* d_affine, uint32_t n, int point_fmt, uint8_t* d_out,
                           cudaStream_t stream);
 void field_mul_device(int curve, const void* d_a, const void* d_b, uint32_t n, int op, void* d_out,

@@ -102,7 +102,7 @@ void msm_small_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t 
     for (int st = kStageCount; st <= kStageAccumulate; st++) g_stage_timer.mark(st, stream);
     if (nblk > 1) PORLA_CUDA(cudaMemsetAsync(tickets, 0, (size_t)slots * 4, stream));
     if (lut) {
-        k_lut_sum<C><<<dim3(nblk, nbatch), kTreeThreads, 0, stream>>>(reinterpret_cast<const Affine<F>*>(table.d_lut), table.n,
+        k_lut_sum<C><<<dim3(nblk, nbatch), kTreeThreads, 0, stream>>>(reinterpret_cast<const Affine<F>*>(table.d_lut), table.fb_n,
                                                                      table.fb_c, table.fb_nwin, d_scalars, opt.scalar_be, n, K,
                                                                      partials, tickets, wsum);
     } else {
@@ -146,7 +146,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     sh.c = fixed ? table.fb_c : (opt.window_bits > 0 ? opt.window_bits : choose_window(curve, n, nbatch));
     sh.nwin = (C::kScalarBits + 1 + sh.c - 1) / sh.c;
     sh.nbuckets = 1u << (sh.c - 1);
-    sh.fixed_n = fixed ? table.n : 0u;
+    sh.fixed_n = fixed ? table.fb_n : 0u;
     // window slots that own a bucket set: one per (msm, window), or one per msm in fixed-base mode
     const int slot_windows = fixed ? 1 : sh.nwin;
 
@@ -154,7 +154,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     const uint64_t nbt64 = slots * sh.nbuckets;
     const uint64_t pairs64 = (uint64_t)nbatch * n * sh.nwin;
     if (nbt64 >= (1ull << 32) || pairs64 >= (1ull << 32) || (uint64_t)nbatch * n >= (1ull << 31) ||
-        (fixed && (uint64_t)table.n * sh.nwin >= (1ull << 31))) {
+        (fixed && (uint64_t)table.fb_n * sh.nwin >= (1ull << 31))) {
         fprintf(stderr, "[libmultiexp/porla_b200] FATAL: MSM shape too large for 32-bit indexing\n");
         abort();
     }
@@ -340,6 +340,7 @@ void precompute_impl(PointTable* t, int c, cudaStream_t stream) {
     t->d_fb_points = out;
     t->fb_c = c;
     t->fb_nwin = nwin;
+    t->fb_n = t->n;
     if (t->d_lut) PORLA_CUDA(cudaFree(t->d_lut));
     t->d_lut = nullptr;
 }
@@ -410,6 +411,15 @@ void align_scalars_impl(uint32_t* d_data, uint32_t total, uint8_t* d_scalars_be,
 }
 
 template <class C>
+void audit_aggregate_impl(const uint32_t* d_coefs, const uint32_t* d_blocks, uint32_t n, uint32_t chunks, uint8_t* d_b_mod_be,
+                          uint8_t* d_c_be, cudaStream_t stream) {
+    if (!chunks) return;
+    k_audit_aggregate<C><<<chunks, kAggThreads, 0, stream>>>(d_coefs, d_blocks, n, chunks, d_b_mod_be, d_c_be);
+    LAUNCHED();
+    PORLA_CUDA(cudaGetLastError());
+}
+
+template <class C>
 void export_impl(const void* d_affine, uint32_t n, int fmt, uint8_t* d_out, cudaStream_t stream) {
     using F = typename C::F;
     k_export_points<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<F>*>(d_affine), n, fmt, d_out);
@@ -438,6 +448,8 @@ void field_mul_impl(const void* d_a, const void* d_b, uint32_t n, int op, void* 
     template void export_impl<C>(const void*, uint32_t, int, uint8_t*, cudaStream_t);                                  \
     template void butterfly_impl<C>(PointTable*, uint32_t, const uint8_t*, int, cudaStream_t);                         \
     template void align_scalars_impl<C>(uint32_t*, uint32_t, uint8_t*, cudaStream_t);                                  \
+    template void audit_aggregate_impl<C>(const uint32_t*, const uint32_t*, uint32_t, uint32_t, uint8_t*, uint8_t*,    \
+                                          cudaStream_t);                                                               \
     template void field_mul_impl<C>(const void*, const void*, uint32_t, int, void*, cudaStream_t);
 
 }  // namespace porla

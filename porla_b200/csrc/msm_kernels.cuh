@@ -1013,6 +1013,109 @@ k_align_scalars(uint32_t* __restrict__ data, uint32_t total, uint8_t* __restrict
         src[k] = k < 2 ? make_uint4(rem[4 * k], rem[4 * k + 1], rem[4 * k + 2], rem[4 * k + 3]) : make_uint4(0u, 0u, 0u, 0u);
 }
 
+// ---- Server::audit block aggregation + alignment (/root/reference/porla/Server/Server.hpp:790-828, 531-540)
+// rem = a mod m for an a of LIMBS 32-bit limbs and a 256-bit m (restoring shift-subtract, as mod512).
+template <int LIMBS>
+PORLA_D void mod_wide(const uint32_t* a, const uint32_t* m, uint32_t* rem) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) rem[k] = 0;
+    for (int bit = LIMBS * 32 - 1; bit >= 0; bit--) {
+        uint32_t top = rem[7] >> 31;
+#pragma unroll
+        for (int k = 7; k > 0; k--) rem[k] = (rem[k] << 1) | (rem[k - 1] >> 31);
+        rem[0] = (rem[0] << 1) | ((a[bit >> 5] >> (bit & 31)) & 1u);
+        uint32_t t[8];
+        uint32_t borrow = sub256(t, rem, m);
+        if (top | (borrow ^ 1u)) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) rem[k] = t[k];
+        }
+    }
+}
+
+// Block j of the grid owns chunk j:  B = sum_i coefs[i] * blocks[i][j]  (plain integers: coefficients below 2^31,
+// chunks of 16 LE limbs, at most 2^24 blocks, so B < 2^567 fits kAggLimbs limbs), thread t takes the blocks
+// i = t, t + 128, ...; the partial sums meet in a shared-memory tree.  Thread 0 then applies align_MAC's
+// arithmetic:  mod = B % PRIME_MODULUS,  c = (mod - B) % r,  and emits both as 32-byte big-endian scalars.
+constexpr int kAggLimbs = 18;
+constexpr int kAggThreads = 128;
+template <class C>
+__global__ void __launch_bounds__(kAggThreads)
+k_audit_aggregate(const uint32_t* __restrict__ coefs, const uint32_t* __restrict__ blocks, uint32_t n, uint32_t chunks,
+                  uint8_t* __restrict__ b_mod_be, uint8_t* __restrict__ c_be) {
+    __shared__ uint32_t sh[kAggThreads][kAggLimbs + 1];   // +1: bank spread
+    const uint32_t j = blockIdx.x;
+    uint32_t acc[kAggLimbs];
+#pragma unroll
+    for (int k = 0; k < kAggLimbs; k++) acc[k] = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += kAggThreads) {
+        const uint32_t cf = __ldg(coefs + i);
+        const uint4* src = reinterpret_cast<const uint4*>(blocks + ((size_t)i * chunks + j) * 16);
+        uint32_t a[16];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint4 v = __ldg(src + k);
+            a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+        }
+        uint64_t carry = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            uint64_t v = (uint64_t)a[k] * cf + acc[k] + carry;
+            acc[k] = (uint32_t)v;
+            carry = v >> 32;
+        }
+#pragma unroll
+        for (int k = 16; k < kAggLimbs; k++) {
+            uint64_t v = (uint64_t)acc[k] + carry;
+            acc[k] = (uint32_t)v;
+            carry = v >> 32;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kAggLimbs; k++) sh[threadIdx.x][k] = acc[k];
+    __syncthreads();
+    for (int o = kAggThreads / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            uint32_t carry = 0;
+#pragma unroll
+            for (int k = 0; k < kAggLimbs; k++) {
+                uint64_t v = (uint64_t)sh[threadIdx.x][k] + sh[threadIdx.x + o][k] + carry;
+                sh[threadIdx.x][k] = (uint32_t)v;
+                carry = (uint32_t)(v >> 32);
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    constexpr uint32_t kPrime[8] = {0x00000001u, 0u, 0u, 0u, 0u, 0u, 0u, 0xcf000000u};
+    uint32_t B[kAggLimbs], pm[8], ord[8], rem[8], d[kAggLimbs], t[8], c[8];
+#pragma unroll
+    for (int k = 0; k < kAggLimbs; k++) B[k] = sh[0][k];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        pm[k] = kPrime[k];
+        ord[k] = C::order(k);
+    }
+    mod_wide<kAggLimbs>(B, pm, rem);
+    uint32_t borrow = 0;   // d = B - mod, a non-negative multiple of PRIME_MODULUS
+#pragma unroll
+    for (int k = 0; k < kAggLimbs; k++) {
+        uint32_t sub = k < 8 ? rem[k] : 0u;
+        uint64_t v = (uint64_t)B[k] - sub - borrow;
+        d[k] = (uint32_t)v;
+        borrow = (uint32_t)(v >> 63);
+    }
+    mod_wide<kAggLimbs>(d, ord, t);
+    bool zero = true;
+#pragma unroll
+    for (int k = 0; k < 8; k++) zero = zero && t[k] == 0;
+    sub256(c, ord, t);   // c = (-(B - mod)) mod r
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = zero ? 0u : c[k];
+    store_u256(c_be, j, 1, c);
+    store_u256(b_mod_be, j, 1, rem);
+}
+
 // out[i] = a[i] + b[i]
 template <class C>
 __global__ void k_point_add(const Affine<typename C::FC>* __restrict__ a,

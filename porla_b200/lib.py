@@ -31,7 +31,7 @@ NEW_SYMBOLS = [
     "porla_scalar_mul_batch_device", "porla_secp256k1_ecmult_multi_var",
     "porla_secp256k1_gej_serialize", "porla_debug_field_mul", "porla_debug_field_op", "porla_debug_point_add_host", "porla_measure_pint",
     "porla_stage_timing_enable", "porla_stage_timing_read",
-    "porla_butterfly_stage_device", "bn254_butterfly_stage", "bn254_align_mac_batch",
+    "porla_butterfly_stage_device", "bn254_butterfly_stage", "bn254_align_mac_batch", "bn254_audit_aggregate",
     "porla_msm_table_host_scalars", "porla_secp256k1_table_create", "porla_secp256k1_ecmult_multi_table",
     "porla_debug_pairing_selfcheck", "porla_debug_latency",
 ]
@@ -118,6 +118,7 @@ def load() -> C.CDLL:
         "porla_butterfly_stage_device": (None, [P, C.c_int64, P, I, I, P]),
         "bn254_butterfly_stage": (None, [GS, LL, LL, GS]),
         "bn254_align_mac_batch": (None, [GS, LL, GS]),
+        "bn254_audit_aggregate": (None, [GS, GS, LL, GS, GS]),
         "porla_msm_table_host_scalars": (None, [P, C.c_int64, P, C.c_int64, I, I, P]),
         "porla_secp256k1_table_create": (P, [C.POINTER(SecpGe), C.c_size_t]),
         "porla_secp256k1_ecmult_multi_table": (I, [P, C.c_size_t, C.POINTER(SecpScalar), C.c_size_t, C.POINTER(SecpGej)]),
@@ -249,6 +250,14 @@ class Kzg:
         out = bytearray(64 * batch)
         self.lib.bn254_align_mac_batch(C.byref(_slice(data)), batch, C.byref(_slice(out)))
         return bytes(out)
+
+    def audit_aggregate(self, coefs: bytes, blocks: bytes, n: int):
+        """Server::audit's B = sum coef_i * block_i followed by align_MAC on B (Server.hpp:790-828, 903): coefs n x 4 B
+        LE, blocks n x n_samples x 64 B LE; returns (B % PRIME_MODULUS as n_samples x 32 B BE, 64-byte alignment value)."""
+        b_out, al = bytearray(32 * self.n), bytearray(64)
+        self.lib.bn254_audit_aggregate(C.byref(_slice(bytearray(coefs))), C.byref(_slice(bytearray(blocks))), n,
+                                       C.byref(_slice(b_out)), C.byref(_slice(al)))
+        return bytes(b_out), bytes(al)
 
     def create_proof(self, random_point: int, data: bytes):
         c, h, z, y = bytearray(64), bytearray(64), bytearray(32), bytearray(32)

@@ -180,3 +180,72 @@ def test_secp256k1_generator_table_lookup(route):
         lib.porla_msm_table_host_scalars(C.c_void_p(tab.handle), first, buf, cnt, pb.SCALAR_LE32, pb.POINT_BE64, C.cast(out, C.c_void_p))
         assert bytes(out) == enc(O.msm(SE, sc, gens[first:first + cnt])), (first, cnt)
     tab.destroy()
+
+
+# ------------------------------------------------------------------ Server::audit's block aggregation
+@pytest.mark.parametrize("n", [1, 3, 128, 766])
+def test_audit_aggregate_matches_reference_arithmetic(n):
+    """B = sum coef_i * block_i over plain integers (Server.hpp:790-828), then align_MAC on B (Server.hpp:531-560):
+    B % PRIME_MODULUS comes back as bn254_scalars, with the commitment of c = (B % PRIME - B) % r over the SRS."""
+    PRIME = 207 * 2**248 + 1                                   # utils.h:40
+    LCM = PRIME * BN.n                                         # utils.h:42-43
+    chunks = 128
+    k = pb.Kzg(TAU, ALPHA)
+    srs = _srs_points(k.init_srs(chunks), chunks)
+    srs_bytes = b"".join(O.bn254_marshal(P) for P in srs)
+    rnd = random.Random(31 * n)
+    coefs = [rnd.randrange(1 << 31) for _ in range(n)]
+    blocks = [[rnd.randrange(LCM) for _ in range(chunks)] for _ in range(n)]
+    coefs[0] = (1 << 31) - 1
+    blocks[0][:5] = [LCM - 1, 0, PRIME, PRIME - 1, 1]
+    if n > 2:
+        blocks[1] = [rnd.randrange(1 << 256) for _ in range(chunks)]      # a raw U block: 256-bit chunks (Client.hpp:371)
+        coefs[2] = 0
+    for i in range(n):
+        blocks[i][7] = LCM - 1                                  # the widest possible sum in chunk 7
+    got_b, got_align = k.audit_aggregate(b"".join(c.to_bytes(4, "little") for c in coefs),
+                                         b"".join(v.to_bytes(64, "little") for row in blocks for v in row), n)
+    B = [sum(c * row[j] for c, row in zip(coefs, blocks)) for j in range(chunks)]
+    for j in range(chunks):
+        assert int.from_bytes(got_b[32 * j:32 * j + 32], "big") == B[j] % PRIME, j
+    cs = b"".join(be(((b % PRIME) - b) % BN.n) for b in B)
+    assert got_align == loader.bn254_msm(cs, srs_bytes, chunks, 1)
+
+
+# ------------------------------------------------------------------ SURVEY 8(f)3: the IPA prover's round MSMs
+def test_ipa_round_msms_over_resident_generators(route):
+    """Server::inner_product_prove (Server.hpp:2318-2443): every round's L and R are multi-exponentiations of
+    NUM_CHUNKS/2 generators picked in alternating blocks of half_width (L: odd blocks, R: even blocks) with scalars
+    a[q] * x_values[j] mod n.  With the generators resident (porla_secp256k1_table_create expands them into the
+    look-up table) each L / R is ONE call over the whole table whose unused generators carry a zero scalar."""
+    N = 128
+    rnd = random.Random(2318)
+    G = (SE.gx, SE.gy)
+    gens = [O.mul(SE, rnd.randrange(1, SE.n), G) for _ in range(N)]
+    tab = pb.SecpGenerators(gens)
+    a = [rnd.randrange(SE.n) for _ in range(N)]
+    x_values = [1] * N
+    half, k = N // 2, 1
+    while half > 1:
+        x = rnd.randrange(1, SE.n)
+        inv_x = pow(x, -1, SE.n)
+        for odd, a_off, factor in ((1, 0, x), (0, half, inv_x)):            # L then R, as the reference orders them
+            sc = [0] * N
+            for i in range(k):
+                pos = 2 * i + odd
+                for q, j in enumerate(range(pos * half, (pos + 1) * half)):
+                    sc[j] = a[a_off + q] * x_values[j] % SE.n
+                    x_values[j] = x_values[j] * factor % SE.n
+            ok, got = tab.multi(0, sc)
+            active = [(s, gens[j]) for j, s in enumerate(sc) if s]
+            assert len(active) <= N // 2
+            assert ok == 1 and got == O.msm(SE, [s for s, _ in active], [P for _, P in active]), (half, odd)
+        a = [(a[i] * x + a[i + half] * inv_x) % SE.n for i in range(half)] + [0] * (N - half)
+        half >>= 1
+        k <<= 1
+    # the per-thread sub-ranges of compute_commitment (16 generators per pool thread, Server.hpp:331-360)
+    for t in range(8):
+        sc = [rnd.randrange(1 << 256) for _ in range(16)]
+        ok, got = tab.multi(16 * t, sc)
+        assert ok == 1 and got == O.msm(SE, [s % SE.n for s in sc], gens[16 * t:16 * t + 16]), t
+    tab.destroy()
