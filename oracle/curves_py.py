@@ -313,3 +313,55 @@ def kzg_open(coeffs, z: int):
         carry = (coeffs[i] + carry * z) % r
         h[i - 1] = carry
     return y, h
+
+
+# ---------------------------------------------------------------------------------------------
+# GLV endomorphism constants (test infrastructure for porla_b200/csrc/ec.cuh: Bn254::glv_*).
+# phi(x, y) = (beta x, y) = lambda (x, y); (a1, b1), (a2, b2) is a reduced basis of the lattice
+# {(x, y): x + y lambda = 0 mod n}; k = k1 + k2 lambda with k1 = k - c1 a1 - c2 a2, k2 = -c1 b1 - c2 b2.
+def glv_constants(c: Curve):
+    import math
+
+    def cube_root_of_unity(m):
+        for g in range(2, 100):
+            w = pow(g, (m - 1) // 3, m)
+            if w != 1:
+                return w
+        raise ValueError
+
+    beta, lam = cube_root_of_unity(c.p), cube_root_of_unity(c.n)
+    G = (c.gx, c.gy)
+    found = None
+    for lm in (lam, lam * lam % c.n):
+        lg = mul(c, lm, G)
+        for bt in (beta, beta * beta % c.p):
+            if lg == (bt * G[0] % c.p, G[1]):
+                found = (bt, lm)
+    # the smaller lambda / its matching beta (the pair the kernels were generated with)
+    beta, lam = found
+    alt = (beta * beta % c.p, lam * lam % c.n)
+    if alt[1] < lam:
+        beta, lam = alt
+    rows, sq = [], math.isqrt(c.n)
+    r0, r1, t0, t1 = c.n, lam, 0, 1
+    while r1:
+        q = r0 // r1
+        r0, r1 = r1, r0 - q * r1
+        t0, t1 = t1, t0 - q * t1
+        rows.append((r0, t0))
+    idx = max(i for i, (r, _) in enumerate(rows) if r >= sq)
+    v1 = (rows[idx + 1][0], -rows[idx + 1][1])
+    ca, cb = (rows[idx][0], -rows[idx][1]), (rows[idx + 2][0], -rows[idx + 2][1])
+    v2 = ca if ca[0] ** 2 + ca[1] ** 2 <= cb[0] ** 2 + cb[1] ** 2 else cb
+    return {"beta": beta, "lambda": lam, "a1": v1[0], "b1": v1[1], "a2": v2[0], "b2": v2[1]}
+
+
+def glv_split(c: Curve, k: int, consts=None):
+    """The device routine glv_split (msm_kernels.cuh) restated: floors instead of roundings."""
+    g = consts or glv_constants(c)
+    g1 = (g["b2"] << 256) // c.n
+    g2 = ((-g["b1"]) << 256) // c.n
+    c1, c2 = (k * g1) >> 256, (k * g2) >> 256
+    k1 = k - c1 * g["a1"] - c2 * g["a2"]
+    k2 = -c1 * g["b1"] - c2 * g["b2"]
+    return k1, k2

@@ -138,7 +138,8 @@ void msm_host_split(int curve, const uint8_t* scalars, const uint8_t* points, in
     const int64_t half[2] = {n / 2, n - n / 2};
     const MsmPlan plan = msm_plan(curve, (uint32_t)half[1], 1, 0);
     const size_t ws_bytes = (size_t)plan.nwin * 128;
-    size_t sc_off = 0, pt_off = pad((size_t)n * 32), tab_off = pt_off + pad((size_t)n * 64), fl_off = tab_off + pad((size_t)n * 64),
+    // table region: every half's points are followed by their endomorphism image (2 * 64 B per point)
+    size_t sc_off = 0, pt_off = pad((size_t)n * 32), tab_off = pt_off + pad((size_t)n * 64), fl_off = tab_off + pad((size_t)n * 128),
            ws_off = fl_off + pad((size_t)n);
     uint8_t* d = g_stage.dev(ws_off + 2 * pad(ws_bytes));
     cudaStream_t st = g_stage.stream, cs = g_stage.copy_stream;
@@ -156,7 +157,7 @@ void msm_host_split(int curve, const uint8_t* scalars, const uint8_t* points, in
         PORLA_CUDA(cudaEventRecord(g_stage.ev[h], cs));
         PORLA_CUDA(cudaStreamWaitEvent(st, g_stage.ev[h], 0));
         PointTable tab;
-        table_import_into(curve, d + pt_off + a * 64, point_fmt, (uint32_t)m, d + tab_off + a * 64, d + fl_off + a, &tab, st);
+        table_import_into(curve, d + pt_off + a * 64, point_fmt, (uint32_t)m, d + tab_off + a * 128, d + fl_off + a, &tab, st);
         opt.d_window_sums = d + ws_off + h * pad(ws_bytes);
         msm_device(curve, tab, d + sc_off + a * 32, (uint32_t)m, 1, opt, nullptr, nullptr, st);
         first += half[h];
@@ -219,7 +220,7 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
     // staging layout: scalars | raw points | imported table | infinity flags | result scratch
     auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t sc_bytes = total * 32, pt_bytes = total * 64;
-    size_t sc_off = 0, pt_off = pad(sc_bytes), tab_off = pt_off + pad(pt_bytes), fl_off = tab_off + pad(pt_bytes),
+    size_t sc_off = 0, pt_off = pad(sc_bytes), tab_off = pt_off + pad(pt_bytes), fl_off = tab_off + pad(2 * pt_bytes),
            out_off = fl_off + pad(total);
     uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(curve, n, nbatch));
     cudaStream_t st = g_stage.stream;

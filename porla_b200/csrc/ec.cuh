@@ -160,6 +160,37 @@ struct Bn254 {
     using FC = Bn254FpCompact;  // same layout, non-inlined multiplier (cold kernels)
     static constexpr int kScalarBits = 254;     // bits the window recoder covers (r < 2^254)
     static constexpr bool kHalveScalar = false;
+    // GLV: phi(x, y) = (beta x, y) = lambda (x, y) with beta^3 = 1 in Fp, lambda^3 = 1 mod r.  A scalar k splits as
+    // k = k1 + k2 lambda with |k1|, |k2| < 2^127 (lattice basis (a1, b1), (a2, b2), a1 b2 - a2 b1 = r; constants
+    // derived and checked in oracle/curves_py.py: glv_constants / tests/test_oracle.py), so an n-term MSM becomes a
+    // 2n-term MSM over (P_i, phi(P_i)) with half as many windows, i.e. half as many buckets to reduce.
+    static constexpr bool kGlv = true;
+    static constexpr int kGlvBits = 127;
+    PORLA_HD static constexpr uint32_t glv_beta_mont(int i) {   // beta * 2^256 mod p
+        constexpr uint32_t m[8] = {0xd782e155u, 0x71930c11u, 0xffbe3323u, 0xa6bb947cu,
+                                   0xd4741444u, 0xaa303344u, 0x26594943u, 0x2c3b3f0du};
+        return m[i];
+    }
+    PORLA_HD static constexpr uint32_t glv_g1(int i) {   // floor(2^256 * b2 / r)
+        constexpr uint32_t m[3] = {0xc7e0b3d7u, 0xd91d232eu, 0x2u};
+        return m[i];
+    }
+    PORLA_HD static constexpr uint32_t glv_g2(int i) {   // floor(2^256 * (-b1) / r)
+        constexpr uint32_t m[5] = {0x391eb18du, 0x7a7bd9d4u, 0xa773d2cfu, 0x4ccef014u, 0x2u};
+        return m[i];
+    }
+    PORLA_HD static constexpr uint32_t glv_a1(int i) {   // a1 = b2
+        constexpr uint32_t m[2] = {0x94d213e3u, 0x89d32568u};
+        return m[i];
+    }
+    PORLA_HD static constexpr uint32_t glv_a2(int i) {
+        constexpr uint32_t m[4] = {0x1221250bu, 0x0be4e154u, 0xeeb859fdu, 0x6f4d8248u};
+        return m[i];
+    }
+    PORLA_HD static constexpr uint32_t glv_nb1(int i) {  // -b1
+        constexpr uint32_t m[4] = {0x7d4f1128u, 0x8211bbebu, 0xeeb859fcu, 0x6f4d8248u};
+        return m[i];
+    }
     // r (scalar field order), little-endian 32-bit limbs
     PORLA_HD static constexpr uint32_t order(int i) {
         constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
@@ -176,6 +207,10 @@ struct Secp256k1 {
     // carry of the signed digits) span exactly 16 windows of 16 bits instead of 17 with a 1-bit top window.
     static constexpr int kScalarBits = 255;
     static constexpr bool kHalveScalar = true;
+    // no GLV here: the split halves of a secp256k1 scalar reach 2^128 (they need 129 bits with the signed digits'
+    // carry), so 2n terms x 9 windows of 16 bits would cost more bucket updates than n terms x 16 windows
+    static constexpr bool kGlv = false;
+    static constexpr int kGlvBits = 0;
     PORLA_HD static constexpr uint32_t order(int i) {
         constexpr uint32_t m[8] = {0xd0364141u, 0xbfd25e8cu, 0xaf48a03bu, 0xbaaedce6u,
                                    0xfffffffeu, 0xffffffffu, 0xffffffffu, 0xffffffffu};

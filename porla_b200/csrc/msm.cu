@@ -107,41 +107,75 @@ static double bucket_cost() {
     return v;
 }
 
-int choose_window(int curve, uint32_t n, uint32_t nbatch) {
+// Cost (in bucket-accumulation mixed additions) of running `terms` terms of `bits`-bit scalars per MSM with
+// window size c; < 0 when c is not usable.
+static double window_cost(int bits, double terms, uint32_t nbatch, int c) {
+    int nwin = (bits + 1 + c - 1) / c;
+    double nb = (double)(1u << (c - 1));
+    // one mixed add per (point, window); ~4 mixed-add equivalents per bucket in the reduction
+    double cost = (double)nwin * (terms + bucket_cost() * nb);
+    double total_buckets = (double)nbatch * nwin * nb;
+    if (total_buckets > 3.0e9) return -1;           // 32-bit bucket ids
+    if (total_buckets * 128.0 > 48.0e9) return -1;  // bucket array budget
+    // A window size that leaves only a few bits for the top window puts n / 2^(t-1) points into each
+    // of its few buckets: contended counters in the sort and long serial stitches in the accumulation
+    // (measured at 2^18: c = 13 -> 1.99 ms, c = 15 -> 1.33 ms; secp256k1 2^18: c = 13 -> 1.38 ms,
+    // c = 16 -> 1.23 ms).  Skip such sizes once the load matters, penalise them mildly below that.  A top
+    // window that still has more than 2^10 buckets spreads the load over enough threads (c = 20).
+    int t_top = bits + 1 - (nwin - 1) * c;
+    if (t_top < c - 1 && t_top <= 10) {
+        uint64_t load_top = (uint64_t)terms >> (t_top > 1 ? t_top - 1 : 0);
+        if (load_top > 1024) return -1;
+        if (load_top > 256) cost *= 1.15;
+    }
+    // Buckets much longer than a slice (64 pairs) are cut into many partial sums that one owner thread
+    // per bucket adds serially while its warp idles (2^26: c = 17 -> 225 ms, c = 20 -> 168 ms).
+    cost *= 1.0 + 0.02 * (terms / nb) / 64.0;
+    return cost;
+}
+
+static bool glv_allowed(int curve) {
+    return curve == kCurveBn254 && Bn254::kGlv && !getenv("PORLA_NO_GLV");
+}
+
+// Window size and whether to split the scalars with the GLV endomorphism (BN254): 2n terms of 127-bit scalars need
+// half as many windows, hence half as many buckets to reduce, for the same number of bucket updates whenever
+// ceil(128/c) * 2 == ceil(255/c) (c = 16: 8 + 8 windows instead of 16).  forced_c > 0 fixes the window size.
+struct WindowChoice {
+    int c;
+    int glv;
+};
+static WindowChoice choose_window_ex(int curve, uint32_t n, uint32_t nbatch, int forced_c) {
     const char* env = getenv("PORLA_WINDOW_BITS");
-    if (env && atoi(env) >= 2 && atoi(env) <= 24) return atoi(env);
+    if (forced_c <= 0 && env && atoi(env) >= 2 && atoi(env) <= 24) forced_c = atoi(env);
     const int bits = scalar_bits(curve);
+    const bool glv_ok = glv_allowed(curve);
+    const char* force_glv = getenv("PORLA_GLV");
     double best = 1e300;
-    int best_c = 4;
+    WindowChoice ch{forced_c > 0 ? forced_c : 4, 0};
     for (int c = 3; c <= 20; c++) {   // 20: the widest window the shared-memory radix partition packs
-        int nwin = (bits + 1 + c - 1) / c;
-        double nb = (double)(1u << (c - 1));
-        // one mixed add per (point, window); ~4 mixed-add equivalents per bucket in the reduction
-        double cost = (double)nwin * ((double)n + bucket_cost() * nb);
-        double total_buckets = (double)nbatch * nwin * nb;
-        if (total_buckets > 3.0e9) continue;           // 32-bit bucket ids
-        if (total_buckets * 128.0 > 48.0e9) continue;  // bucket array budget
-        // A window size that leaves only a few bits for the top window puts n / 2^(t-1) points into each
-        // of its few buckets: contended counters in the sort and long serial stitches in the accumulation
-        // (measured at 2^18: c = 13 -> 1.99 ms, c = 15 -> 1.33 ms; secp256k1 2^18: c = 13 -> 1.38 ms,
-        // c = 16 -> 1.23 ms).  Skip such sizes once the load matters, penalise them mildly below that.  A top
-        // window that still has more than 2^10 buckets spreads the load over enough threads (c = 20).
-        int t_top = bits + 1 - (nwin - 1) * c;
-        if (t_top < c - 1 && t_top <= 10) {
-            uint64_t load_top = (uint64_t)n >> (t_top > 1 ? t_top - 1 : 0);
-            if (load_top > 1024) continue;
-            if (load_top > 256) cost *= 1.15;
+        if (forced_c > 0 && c != forced_c) continue;
+        double plain = window_cost(bits, (double)n, nbatch, c);
+        if (force_glv && force_glv[0] == '1' && glv_ok) plain = -1;
+        if (plain >= 0 && plain < best) {
+            best = plain;
+            ch = WindowChoice{c, 0};
         }
-        // Buckets much longer than a slice (64 pairs) are cut into many partial sums that one owner thread
-        // per bucket adds serially while its warp idles (2^26: c = 17 -> 225 ms, c = 20 -> 168 ms).
-        cost *= 1.0 + 0.02 * ((double)n / nb) / 64.0;
-        if (cost < best) {
-            best = cost;
-            best_c = c;
+        // measured (one B200): 2^16 c = 13 0.77 -> 0.70 ms, 2^18 1.32 -> 1.29 ms, 2^20 c = 16 3.62 -> 3.53 ms; the
+        // wide windows the model would pick at 2^22 (c = 19, 7 windows per half) lose to the plain c = 17
+        // (12.4 against 11.8 ms: 1.8 M buckets to reduce), so the split is offered up to c = 16 only
+        if (glv_ok && (c <= 16 || forced_c > 0)) {
+            double split = window_cost(Bn254::kGlvBits, 2.0 * (double)n, nbatch, c);
+            if (split >= 0 && split < best) {
+                best = split;
+                ch = WindowChoice{c, 1};
+            }
         }
     }
-    return best_c;
+    return ch;
 }
+
+int choose_window(int curve, uint32_t n, uint32_t nbatch) { return choose_window_ex(curve, n, nbatch, 0).c; }
 
 int choose_window_fixed_base(int curve, uint32_t n, uint32_t nbatch) {
     const int bits = scalar_bits(curve);
@@ -197,20 +231,22 @@ MsmPlan msm_plan_table(const PointTable& t, uint32_t n, uint32_t nbatch, const M
     const bool no_small = opt.no_small || (ns && ns[0] == '1') || getenv("PORLA_WINDOW_BITS");
     if (fixed) {
         const bool lut = t.d_lut && !no_small && nbatch <= 65535u && n <= t.n;
-        return MsmPlan{t.fb_c, 1, lut ? kPlanLut : kPlanPipeline};
+        return MsmPlan{t.fb_c, 1, lut ? kPlanLut : kPlanPipeline, 0};
     }
     if (opt.window_bits == 0 && !no_small && n > 0 && nbatch <= 65535u) {
         int bits = scalar_bits(t.curve);
         if (opt.max_scalar_bits > 0 && opt.max_scalar_bits < bits) bits = opt.max_scalar_bits;
-        if ((uint64_t)n * nbatch * (uint64_t)bits <= small_bits_limit()) return MsmPlan{1, bits, kPlanBits};
+        if ((uint64_t)n * nbatch * (uint64_t)bits <= small_bits_limit()) return MsmPlan{1, bits, kPlanBits, 0};
     }
     return msm_plan(t.curve, n, nbatch, opt.window_bits);
 }
 
 MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits) {
     MsmPlan p;
-    p.c = window_bits > 0 ? window_bits : choose_window(curve, n, nbatch);
-    p.nwin = (scalar_bits(curve) + 1 + p.c - 1) / p.c;
+    const WindowChoice ch = choose_window_ex(curve, n, nbatch, window_bits);
+    p.c = ch.c;
+    p.glv = ch.glv;
+    p.nwin = ((ch.glv ? Bn254::kGlvBits : scalar_bits(curve)) + 1 + p.c - 1) / p.c;
     p.mode = kPlanPipeline;
     return p;
 }
@@ -276,6 +312,7 @@ void table_import_into(int curve, const uint8_t* d_bytes, int fmt, uint32_t n, v
     out->n = n;
     out->n_inf = 0;  // unknown (not counted on this path); the flags are always consulted
     out->curve = curve;
+    out->phi_off = curve == kCurveBn254 && Bn254::kGlv ? n : 0u;
 }
 
 void table_free(PointTable* t) {

@@ -40,6 +40,9 @@ struct PointTable {
     // lut[((w*n + i) << (fb_c-1)) + d - 1] = d * 2^(fb_c*w) * P_i, 1 <= d <= 2^(fb_c-1).  An MSM over the
     // table is then a plain sum of n * fb_nwin entries (k_lut_sum): no sort, no buckets, no doublings.
     void* d_lut = nullptr;
+    // GLV (BN254): phi(P_i) = (beta x_i, y_i) is stored behind the table, at entry phi_off + i of d_points
+    // (0 = absent; every import path of a GLV curve writes it, the butterfly kernel refreshes it).
+    uint32_t phi_off = 0;
 };
 
 // Import `n` external 64-byte points that already live on the device.
@@ -53,8 +56,8 @@ void table_free(PointTable* t);
 // per launch).  One-time cost of ~254 doublings + fb_nwin inversions per point; fb_nwin * n * 64 bytes.
 int table_precompute(PointTable* t, int c, uint32_t n_hint, uint32_t batch_hint, cudaStream_t stream);
 int choose_window_fixed_base(int curve, uint32_t n, uint32_t nbatch);
-// Import into caller-provided device buffers (n*64 B points, n B flags): no allocation, no sync.
-// The returned table borrows the buffers (do not table_free it).
+// Import into caller-provided device buffers (2*n*64 B points: the table and its endomorphism image, n B flags):
+// no allocation, no sync.  The returned table borrows the buffers (do not table_free it).
 void table_import_into(int curve, const uint8_t* d_bytes, int point_fmt, uint32_t n, void* d_points_out,
                        uint8_t* d_flags_out, PointTable* out, cudaStream_t stream);
 
@@ -78,6 +81,7 @@ struct MsmPlan {
     int c;      // window bits
     int nwin;   // window sums per MSM handed to the finaliser
     int mode;   // PlanMode
+    int glv;    // pipeline only: scalars split with the GLV endomorphism; nwin then counts the windows of ONE half
 };
 // The sort / accumulate / reduce pipeline's plan for n terms.
 MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits);

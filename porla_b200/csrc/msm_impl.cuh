@@ -35,6 +35,11 @@ void import_into_impl(const uint8_t* d_bytes, int fmt, uint32_t n, void* d_point
     k_import_points<C><<<(n + 127) / 128, 128, 0, stream>>>(d_bytes, fmt, mask, n, reinterpret_cast<Affine<F>*>(d_points_out),
                                                            d_flags_out, nullptr);
     LAUNCHED();
+    if constexpr (C::kGlv) {   // the endomorphism image right behind the table (PointTable::phi_off = n)
+        k_phi_table<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<F>*>(d_points_out), n,
+                                                           reinterpret_cast<Affine<F>*>(d_points_out) + n);
+        LAUNCHED();
+    }
     PORLA_CUDA(cudaGetLastError());
 }
 
@@ -44,7 +49,7 @@ void import_impl(const uint8_t* d_bytes, int fmt, uint32_t n, PointTable* out, c
     Affine<F>* pts = nullptr;
     uint8_t* flags = nullptr;
     uint32_t* d_count = nullptr;
-    PORLA_CUDA(cudaMalloc(&pts, (size_t)(n ? n : 1) * sizeof(Affine<F>)));
+    PORLA_CUDA(cudaMalloc(&pts, (size_t)(n ? n : 1) * sizeof(Affine<F>) * (C::kGlv ? 2 : 1)));
     PORLA_CUDA(cudaMalloc(&flags, (size_t)(n ? n : 1)));
     PORLA_CUDA(cudaMalloc(&d_count, 4));
     PORLA_CUDA(cudaMemsetAsync(d_count, 0, 4, stream));
@@ -52,6 +57,10 @@ void import_impl(const uint8_t* d_bytes, int fmt, uint32_t n, PointTable* out, c
         int mask = C::F::Params::kMontgomery ? 1 : 0;  // BN254: gnark flag bits in byte 0
         k_import_points<C><<<(n + 127) / 128, 128, 0, stream>>>(d_bytes, fmt, mask, n, pts, flags, d_count);
         LAUNCHED();
+        if constexpr (C::kGlv) {
+            k_phi_table<C><<<(n + 127) / 128, 128, 0, stream>>>(pts, n, pts + n);
+            LAUNCHED();
+        }
         PORLA_CUDA(cudaGetLastError());
     }
     uint32_t h_count = 0;
@@ -62,6 +71,7 @@ void import_impl(const uint8_t* d_bytes, int fmt, uint32_t n, PointTable* out, c
     out->n = n;
     out->n_inf = h_count;
     out->curve = CurveIdOf<C>::value;
+    out->phi_off = C::kGlv ? n : 0u;
     if (h_count == 0) {
         PORLA_CUDA(cudaFree(flags));
         out->d_flags = nullptr;
@@ -143,12 +153,21 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     sh.shared = opt.shared_points ? 1u : 0u;
     const bool fixed = table.fb_c > 0 && opt.shared_points && !opt.no_fixed_base &&
                        (opt.window_bits == 0 || opt.window_bits == table.fb_c);
-    sh.c = fixed ? table.fb_c : (opt.window_bits > 0 ? opt.window_bits : choose_window(curve, n, nbatch));
-    sh.nwin = (C::kScalarBits + 1 + sh.c - 1) / sh.c;
+    const MsmPlan wplan = fixed ? MsmPlan{table.fb_c, 1, kPlanPipeline, 0} : msm_plan(curve, n, nbatch, opt.window_bits);
+    const bool glv = wplan.glv != 0;
+    if (glv && !(C::kGlv && table.phi_off)) {
+        fprintf(stderr, "[libmultiexp/porla_b200] FATAL: GLV plan for a table without its endomorphism image\n");
+        abort();
+    }
+    sh.c = wplan.c;
+    sh.nwin = glv ? 2 * wplan.nwin : (C::kScalarBits + 1 + sh.c - 1) / sh.c;
     sh.nbuckets = 1u << (sh.c - 1);
     sh.fixed_n = fixed ? table.fb_n : 0u;
-    // window slots that own a bucket set: one per (msm, window), or one per msm in fixed-base mode
-    const int slot_windows = fixed ? 1 : sh.nwin;
+    sh.glv_wh = glv ? wplan.nwin : 0;
+    sh.phi_off = glv ? table.phi_off : 0u;
+    // window slots that own a bucket set: one per (msm, window) -- with GLV, per window of one half: window w of
+    // k1 and window w of k2 fill the same buckets -- or one per msm in fixed-base mode
+    const int slot_windows = fixed ? 1 : (glv ? wplan.nwin : sh.nwin);
 
     const uint64_t slots = (uint64_t)nbatch * slot_windows;
     const uint64_t nbt64 = slots * sh.nbuckets;
@@ -195,7 +214,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
 
     // sort path: shared-memory radix partition (two MSD passes) for large single MSMs, else one returning
     // global atomic per pair
-    const bool radix = nbatch == 1 && n >= (1u << 19) && sh.nwin <= 30 && sh.c >= 9 && sh.c <= 20 && (sh.nbuckets >> (sh.c / 2)) <= (uint32_t)kPartMaxBins && !getenv("PORLA_ATOMIC_SCATTER");
+    const bool radix = nbatch == 1 && n >= (1u << 19) && sh.nwin <= 28 && sh.c >= 9 && sh.c <= 20 && (sh.nbuckets >> (sh.c / 2)) <= (uint32_t)kPartMaxBins && !getenv("PORLA_ATOMIC_SCATTER");
     const int lb = sh.c / 2;                                   // coarse bin = 2^lb consecutive buckets
     const uint32_t ncoarse = radix ? (nbt >> lb) : 0u;
     std::lock_guard<std::mutex> lock(g_engine_mu);
@@ -235,7 +254,15 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     if (total_scalars) {
         uint32_t grid = (uint32_t)((total_scalars + 255) / 256);
         if (grid > 148u * 32u) grid = 148u * 32u;
-        k_digits<C, false><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, 0, sh.nwin, counters, nullptr);
+        bool launched_glv = false;
+        if constexpr (C::kGlv) {
+            if (glv) {
+                k_digits<C, false, true><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, 0, sh.nwin, counters, nullptr);
+                launched_glv = true;
+            }
+        }
+        if (!launched_glv)
+            k_digits<C, false, false><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, 0, sh.nwin, counters, nullptr);
         LAUNCHED();
         g_stage_timer.mark(kStageScan, stream);
         k_scan_tiles<<<ntiles, kScanThreads, 0, stream>>>(counters, offsets, nbt, tile_sums);
@@ -250,13 +277,24 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
             const size_t smem1 = ((size_t)9 * kPartTile + 2 * kPartMaxBins) * 4 + (size_t)kPartTile * 8;
             const size_t smem2 = (size_t)2 * kFineHist * 4 + (size_t)kFineTile * 8;
             std::call_once(attr_once, [=] {
-                PORLA_CUDA(cudaFuncSetAttribute(k_partition_coarse<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+                PORLA_CUDA(cudaFuncSetAttribute(k_partition_coarse<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+                if constexpr (C::kGlv)
+                    PORLA_CUDA(cudaFuncSetAttribute(k_partition_coarse<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
                 PORLA_CUDA(cudaFuncSetAttribute(k_partition_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
             });
             k_init_coarse<<<(ncoarse + 255) / 256, 256, 0, stream>>>(offsets, nbt, lb, ncoarse, coarse_cursor);
             LAUNCHED();
-            k_partition_coarse<C><<<(n + kPartTile - 1) / kPartTile, kPartThreads, smem1, stream>>>(
-                d_scalars, opt.scalar_be, table.d_flags, sh, lb, coarse_cursor, part);
+            bool coarse_glv = false;
+            if constexpr (C::kGlv) {
+                if (glv) {
+                    k_partition_coarse<C, true><<<(n + kPartTile - 1) / kPartTile, kPartThreads, smem1, stream>>>(
+                        d_scalars, opt.scalar_be, table.d_flags, sh, lb, coarse_cursor, part);
+                    coarse_glv = true;
+                }
+            }
+            if (!coarse_glv)
+                k_partition_coarse<C, false><<<(n + kPartTile - 1) / kPartTile, kPartThreads, smem1, stream>>>(
+                    d_scalars, opt.scalar_be, table.d_flags, sh, lb, coarse_cursor, part);
             LAUNCHED();
             k_partition_fine<<<(uint32_t)((pairs_cap + kFineTile - 1) / kFineTile), kFineThreads, smem2, stream>>>(part, grand, lb,
                                                                                                              counters, sorted);
@@ -272,7 +310,15 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         }
         for (int w0 = 0; w0 < sh.nwin; w0 += wgroup) {
             int w1 = w0 + wgroup < sh.nwin ? w0 + wgroup : sh.nwin;
-            k_digits<C, true><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, w0, w1, counters, sorted);
+            bool scatter_glv = false;
+            if constexpr (C::kGlv) {
+                if (glv) {
+                    k_digits<C, true, true><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, w0, w1, counters, sorted);
+                    scatter_glv = true;
+                }
+            }
+            if (!scatter_glv)
+                k_digits<C, true, false><<<grid, 256, 0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, w0, w1, counters, sorted);
             LAUNCHED();
         }
         }
@@ -399,6 +445,13 @@ void butterfly_impl(PointTable* t, uint32_t m, const uint8_t* d_twiddles, int sc
         k_butterfly<C, typename C::FC><<<(nb + 127) / 128, 128, 0, stream>>>(
             reinterpret_cast<Affine<typename C::FC>*>(t->d_points), t->d_flags, t->n, m, d_twiddles, scalar_be);
     LAUNCHED();
+    if constexpr (C::kGlv) {
+        if (t->phi_off) {   // the points changed: so does their endomorphism image
+            k_phi_table<C><<<(t->n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<typename C::F>*>(t->d_points), t->n,
+                                                                  reinterpret_cast<Affine<typename C::F>*>(t->d_points) + t->phi_off);
+            LAUNCHED();
+        }
+    }
     PORLA_CUDA(cudaGetLastError());
 }
 

@@ -32,6 +32,8 @@ struct MsmShape {
     int nwin;            // windows per scalar
     uint32_t nbuckets;   // buckets per window = 2^(c-1)
     uint32_t fixed_n;    // 0: general.  > 0: fixed-base table of stride fixed_n (windows share buckets)
+    int glv_wh;          // 0: off.  > 0: GLV, windows per half; nwin = 2 * glv_wh, window w and w + glv_wh share buckets
+    uint32_t phi_off;    // GLV: phi(P_i) is the table entry phi_off + i
 };
 
 // ---------------------------------------------------------------------------- small helpers
@@ -94,6 +96,109 @@ PORLA_D void reduce_scalar(uint32_t* s) {
 #pragma unroll
         for (int i = 0; i < 8; i++) s[i] = t[i];
     }
+}
+
+// ---------------------------------------------------------------------------- GLV scalar split (BN254)
+// out = a * b mod 2^(32*NO) on 32-bit limbs (schoolbook; a few dozen IMADs per scalar)
+template <int NA, int NB, int NO>
+PORLA_D void mul_limbs(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+#pragma unroll
+    for (int i = 0; i < NO; i++) out[i] = 0;
+#pragma unroll
+    for (int i = 0; i < NA; i++) {
+        uint64_t carry = 0;
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            if (i + j < NO) {
+                uint64_t v = (uint64_t)a[i] * b[j] + out[i + j] + carry;
+                out[i + j] = (uint32_t)v;
+                carry = v >> 32;
+            }
+        }
+        if (i + NB < NO) out[i + NB] = (uint32_t)carry;
+    }
+}
+
+// k (reduced mod r) -> |k1|, |k2| < 2^127 and their signs, k = k1 + k2 * lambda (mod r).
+//   c1 = floor(k * g1 / 2^256) ~ k b2 / r,  c2 = floor(k * g2 / 2^256) ~ -k b1 / r
+//   k1 = k - c1 a1 - c2 a2,  k2 = -c1 b1 - c2 b2        (exact, evaluated mod 2^192 in two's complement)
+// Any integers c1, c2 give a valid split; the floors instead of roundings only cost one bit of size
+// (bound checked exhaustively on the corners and on 3*10^5 random scalars in tests/test_oracle.py).
+template <class C>
+PORLA_D void glv_split(const uint32_t* k, uint32_t* k1, uint32_t* k2, uint32_t& neg1, uint32_t& neg2) {
+    uint32_t g1[3], g2[5], a1[2], a2[4], nb1[4];
+#pragma unroll
+    for (int i = 0; i < 3; i++) g1[i] = C::glv_g1(i);
+#pragma unroll
+    for (int i = 0; i < 5; i++) g2[i] = C::glv_g2(i);
+#pragma unroll
+    for (int i = 0; i < 2; i++) a1[i] = C::glv_a1(i);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        a2[i] = C::glv_a2(i);
+        nb1[i] = C::glv_nb1(i);
+    }
+    uint32_t t1[11], t2[13];
+    mul_limbs<8, 3, 11>(k, g1, t1);
+    mul_limbs<8, 5, 13>(k, g2, t2);
+    const uint32_t* c1 = t1 + 8;   // 2 limbs (c1 < 2^64)
+    const uint32_t* c2 = t2 + 8;   // 4 limbs (c2 < 2^127)
+    uint32_t p1[6], p2[6], q1[6], q2[6];
+    mul_limbs<2, 2, 6>(c1, a1, p1);
+    mul_limbs<4, 4, 6>(c2, a2, p2);
+    mul_limbs<2, 4, 6>(c1, nb1, q1);
+    mul_limbs<4, 2, 6>(c2, a1, q2);   // b2 = a1
+    uint32_t v1[6], v2[6];
+    uint32_t borrow = 0, borrow2 = 0, borrow3 = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        uint64_t d = (uint64_t)k[i] - p1[i] - borrow;
+        borrow = (uint32_t)(d >> 63);
+        uint64_t e = (uint64_t)(uint32_t)d - p2[i] - borrow2;
+        borrow2 = (uint32_t)(e >> 63);
+        v1[i] = (uint32_t)e;
+        uint64_t f = (uint64_t)q1[i] - q2[i] - borrow3;
+        borrow3 = (uint32_t)(f >> 63);
+        v2[i] = (uint32_t)f;
+    }
+    neg1 = v1[5] >> 31;
+    neg2 = v2[5] >> 31;
+    uint32_t cy1 = neg1, cy2 = neg2;   // two's complement negation where negative
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        uint64_t x = (uint64_t)(neg1 ? ~v1[i] : v1[i]) + cy1;
+        v1[i] = (uint32_t)x;
+        cy1 = (uint32_t)(x >> 32);
+        uint64_t y = (uint64_t)(neg2 ? ~v2[i] : v2[i]) + cy2;
+        v2[i] = (uint32_t)y;
+        cy2 = (uint32_t)(y >> 32);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        k1[i] = v1[i];
+        k2[i] = v2[i];
+    }
+}
+
+// phi[i] = (beta * x_i, y_i): the endomorphism image of every table entry, stored right behind the table
+template <class C>
+__global__ void __launch_bounds__(128)
+k_phi_table(const Affine<typename C::F>* __restrict__ in, uint32_t n, Affine<typename C::F>* __restrict__ out) {
+    using F = typename C::F;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p;
+    {   // plain loads: `in` may have been written earlier on this stream by the butterfly kernel
+        const uint4* s = reinterpret_cast<const uint4*>(in + i);
+        uint4* d = reinterpret_cast<uint4*>(&p);
+#pragma unroll
+        for (int q = 0; q < 4; q++) d[q] = s[q];
+    }
+    F beta;
+#pragma unroll
+    for (int q = 0; q < 8; q++) beta.v[q] = C::glv_beta_mont(q);
+    p.x = p.x * beta;      // infinity (0, 0) stays (0, 0)
+    st16(out + i, p);
 }
 
 // ---------------------------------------------------------------------------- import / export
@@ -202,7 +307,7 @@ k_precompute_windows(const Affine<typename C::FC>* __restrict__ in, uint32_t n, 
 // ---------------------------------------------------------------------------- recoding
 // Signed c-bit digits: d_w in [-2^(c-1), 2^(c-1)], bucket id |d_w| - 1; nwin*c > bits of the
 // order, so the top digit never overflows.
-template <class C, bool SCATTER>
+template <class C, bool SCATTER, bool GLV>
 __global__ void __launch_bounds__(256)
 k_digits(const uint8_t* __restrict__ scalars, int big_endian,
          const uint8_t* __restrict__ inf_flags, MsmShape sh, int w_begin, int w_end,
@@ -214,32 +319,45 @@ k_digits(const uint8_t* __restrict__ scalars, int big_endian,
     const uint32_t half = 1u << (sh.c - 1);
     const uint32_t mask = (1u << sh.c) - 1u;
     constexpr int kBatch = 8;  // independent atomics kept in flight per thread
+    // limbs of the value being recoded: the scalar (s[8] = 0), or with GLV the two halves |k1| in s[0..3],
+    // |k2| in s[5..8] (s[4] = s[9] = 0), window w >= glv_wh reading the second half
+    constexpr int kLimbs = GLV ? 10 : 9;
+    const int wh = GLV ? sh.glv_wh : sh.nwin;
     for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t m = (uint32_t)(idx / sh.n);
         uint32_t i = (uint32_t)(idx - (uint64_t)m * sh.n);
         uint32_t pidx = sh.shared ? i : (uint32_t)idx;
         if (inf_flags && inf_flags[pidx]) continue;
-        uint32_t s[9];
-        load_u256(scalars, idx, big_endian, s);
-        s[8] = 0;
-        reduce_scalar<C>(s);
-        uint32_t flip = 0;   // s > order/2: use order - s and the negated point
-        if (C::kHalveScalar) {
-            uint32_t ord[8], t[8], u[8];
+        uint32_t s[kLimbs];
+        uint32_t flip[2] = {0, 0};   // negate the point (per half with GLV)
+        if constexpr (GLV) {
+            uint32_t k[8];
+            load_u256(scalars, idx, big_endian, k);
+            reduce_scalar<C>(k);
+            glv_split<C>(k, s, s + 5, flip[0], flip[1]);
+            s[4] = 0;
+            s[9] = 0;
+        } else {
+            load_u256(scalars, idx, big_endian, s);
+            s[8] = 0;
+            reduce_scalar<C>(s);
+            if (C::kHalveScalar) {   // s > order/2: use order - s and the negated point
+                uint32_t ord[8], t[8], u[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) ord[k] = C::order(k);
-            sub256(t, ord, s);                 // order - s  (s < order)
-            if (sub256(u, t, s)) {             // order - s < s
-                flip = 1;
+                for (int k = 0; k < 8; k++) ord[k] = C::order(k);
+                sub256(t, ord, s);                 // order - s  (s < order)
+                if (sub256(u, t, s)) {             // order - s < s
+                    flip[0] = 1;
 #pragma unroll
-                for (int k = 0; k < 8; k++) s[k] = t[k];
+                    for (int k = 0; k < 8; k++) s[k] = t[k];
+                }
             }
         }
         uint32_t carry = 0;
         // general: one bucket set per (msm, window); fixed-base: one per msm, the window selects the
-        // pre-multiplied copy 2^(c*w) * P_i of the point instead
-        const uint32_t slot_base = sh.fixed_n ? m * sh.nbuckets : m * (uint32_t)sh.nwin * sh.nbuckets;
+        // pre-multiplied copy 2^(c*w) * P_i of the point instead; GLV: one per (msm, window of a half)
+        const uint32_t slot_base = sh.fixed_n ? m * sh.nbuckets : m * (uint32_t)wh * sh.nbuckets;
         for (int w0 = 0; w0 < w_end; w0 += kBatch) {
             uint32_t bucket[kBatch], val[kBatch];
 #pragma unroll
@@ -248,22 +366,25 @@ k_digits(const uint8_t* __restrict__ scalars, int big_endian,
                 bucket[k] = 0xffffffffu;
                 val[k] = 0;
                 if (w < sh.nwin) {
-                    uint32_t pos = (uint32_t)w * sh.c;
+                    const int h = GLV && w >= wh ? 1 : 0;
+                    const int wl = w - h * wh;
+                    if (GLV && wl == 0) carry = 0;
+                    uint32_t pos = (uint32_t)wl * sh.c + (GLV ? 160u * h : 0u);
                     uint32_t word = pos >> 5, sft = pos & 31;
-                    uint32_t lo = s[word < 8 ? word : 8];
-                    uint32_t hi = s[word < 7 ? word + 1 : 8];
+                    uint32_t lo = s[word < kLimbs - 1 ? word : kLimbs - 1];
+                    uint32_t hi = s[word < kLimbs - 2 ? word + 1 : kLimbs - 1];
                     uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry;
                     uint32_t dneg = d > half;
                     carry = dneg;
                     uint32_t mag = dneg ? ((1u << sh.c) - d) : d;
-                    uint32_t neg = dneg ^ flip;
+                    uint32_t neg = dneg ^ flip[h];
                     if (mag != 0 && w >= w_begin && w < w_end) {
                         if (sh.fixed_n) {
                             bucket[k] = slot_base + (mag - 1);
                             val[k] = ((uint32_t)w * sh.fixed_n + pidx) | (neg << 31);
                         } else {
-                            bucket[k] = slot_base + (uint32_t)w * sh.nbuckets + (mag - 1);
-                            val[k] = pidx | (neg << 31);
+                            bucket[k] = slot_base + (uint32_t)wl * sh.nbuckets + (mag - 1);
+                            val[k] = (pidx + (h ? sh.phi_off : 0u)) | (neg << 31);
                         }
                     }
                 }
@@ -394,7 +515,7 @@ constexpr int kFineThreads = 512;
 constexpr int kFinePerThread = 8;
 constexpr int kFineTile = kFineThreads * kFinePerThread;   // 4096 pairs
 constexpr uint32_t kFineHist = 4096;                       // shared histogram entries of pass 2
-constexpr uint32_t kMetaSkip = 1u << 30, kMetaFlip = 1u << 31;
+constexpr uint32_t kMetaSkip = 1u << 30, kMetaFlip = 1u << 31, kMetaFlip2 = 1u << 29;   // carry bits: 0 .. nwin-1 (<= 28)
 
 static __global__ void k_init_coarse(const uint32_t* __restrict__ offsets, uint32_t nbt, int lb, uint32_t ncoarse,
                                      uint32_t* __restrict__ coarse_cursor) {
@@ -402,7 +523,7 @@ static __global__ void k_init_coarse(const uint32_t* __restrict__ offsets, uint3
     if (g < ncoarse) coarse_cursor[g] = offsets[(size_t)g << lb];
 }
 
-template <class C>
+template <class C, bool GLV>
 __global__ void __launch_bounds__(kPartThreads, 2)
 k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const uint8_t* __restrict__ inf_flags,
                    MsmShape sh, int lb, uint32_t* __restrict__ coarse_cursor, uint2* __restrict__ part) {
@@ -423,28 +544,47 @@ k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const ui
         const uint32_t p = q * kPartThreads + threadIdx.x;
         const uint32_t i = tile0 + p;
         uint32_t m = kMetaSkip;
-        uint32_t s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // GLV: |k1| in s[0..3], |k2| in s[4..7]
         if (i < sh.n && !(inf_flags && inf_flags[i])) {
-            load_u256(scalars, i, big_endian, s);
-            reduce_scalar<C>(s);
             m = 0;
-            if (C::kHalveScalar) {
-                uint32_t ord[8], t[8], u[8];
+            if constexpr (GLV) {
+                uint32_t k[8], n1, n2;
+                load_u256(scalars, i, big_endian, k);
+                reduce_scalar<C>(k);
+                glv_split<C>(k, s, s + 4, n1, n2);
+                m = (n1 ? kMetaFlip : 0u) | (n2 ? kMetaFlip2 : 0u);
+            } else {
+                load_u256(scalars, i, big_endian, s);
+                reduce_scalar<C>(s);
+                if (C::kHalveScalar) {
+                    uint32_t ord[8], t[8], u[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) ord[k] = C::order(k);
-                sub256(t, ord, s);
-                if (sub256(u, t, s)) {
-                    m = kMetaFlip;
+                    for (int k = 0; k < 8; k++) ord[k] = C::order(k);
+                    sub256(t, ord, s);
+                    if (sub256(u, t, s)) {
+                        m = kMetaFlip;
 #pragma unroll
-                    for (int k = 0; k < 8; k++) s[k] = t[k];
+                        for (int k = 0; k < 8; k++) s[k] = t[k];
+                    }
                 }
             }
             uint32_t carry = 0;
             for (int w = 0; w < sh.nwin; w++) {
-                uint32_t pos = (uint32_t)w * sh.c;
-                uint32_t word = pos >> 5, sft = pos & 31;
-                uint32_t lo = s[word < 8 ? word : 8];
-                uint32_t hi = s[word < 7 ? word + 1 : 8];
+                uint32_t lo, hi, sft;
+                if (GLV) {
+                    const int h = w >= sh.glv_wh ? 1 : 0;
+                    const int wl = w - h * sh.glv_wh;
+                    if (wl == 0) carry = 0;
+                    const uint32_t pos = (uint32_t)wl * sh.c, word = pos >> 5;   // word <= 3 inside a 128-bit half
+                    sft = pos & 31;
+                    lo = s[4 * h + word];
+                    hi = word < 3 ? s[4 * h + word + 1] : 0u;
+                } else {
+                    const uint32_t pos = (uint32_t)w * sh.c, word = pos >> 5;
+                    sft = pos & 31;
+                    lo = s[word < 8 ? word : 8];
+                    hi = s[word < 7 ? word + 1 : 8];
+                }
                 m |= carry << w;
                 uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry;
                 carry = d > half;
@@ -459,9 +599,13 @@ k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const ui
     for (int w = 0; w < sh.nwin; w++) {
         for (uint32_t b = threadIdx.x; b < ncw; b += kPartThreads) cnt[b] = 0;
         __syncthreads();
-        const uint32_t pos = (uint32_t)w * sh.c;
-        const uint32_t word = pos >> 5, sft = pos & 31;
-        const uint32_t key0 = sh.fixed_n ? 0u : (uint32_t)w * sh.nbuckets;
+        const int h = GLV && w >= sh.glv_wh ? 1 : 0;          // GLV: second half, phi(P_i), the first half's buckets
+        const int wl = w - h * (GLV ? sh.glv_wh : 0);
+        const uint32_t pos = (uint32_t)wl * sh.c;
+        const uint32_t word = (pos >> 5) + (GLV ? 4u * h : 0u), sft = pos & 31;
+        const uint32_t word_end = GLV ? 4u * h + 4u : 8u;       // first limb past the value being recoded
+        const uint32_t key0 = sh.fixed_n ? 0u : (uint32_t)wl * sh.nbuckets;
+        const uint32_t flip_bit = h ? 29u : 31u;
         // packed per item: bucket (20 bits) | rank within (block, bin) (11 bits) | sign
         uint32_t item[kPartPerThread];
 #pragma unroll
@@ -470,14 +614,14 @@ k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const ui
             const uint32_t m = meta[p];
             item[q] = 0xffffffffu;
             if (!(m & kMetaSkip)) {
-                uint32_t lo = word < 8 ? sw[word * kPartTile + p] : 0u;
-                uint32_t hi = word < 7 ? sw[(word + 1) * kPartTile + p] : 0u;
+                uint32_t lo = word < word_end ? sw[word * kPartTile + p] : 0u;
+                uint32_t hi = word + 1 < word_end ? sw[(word + 1) * kPartTile + p] : 0u;
                 uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + ((m >> w) & 1u);
                 uint32_t dneg = d > half;
                 uint32_t mag = dneg ? ((1u << sh.c) - d) : d;
                 if (mag != 0) {
                     uint32_t r = atomicAdd(&cnt[(mag - 1) >> lb], 1u);     // r < kPartTile = 2^11
-                    item[q] = (mag - 1) | (r << 20) | ((dneg ^ (m >> 31)) << 31);
+                    item[q] = (mag - 1) | (r << 20) | ((dneg ^ ((m >> flip_bit) & 1u)) << 31);
                 }
             }
         }
@@ -504,7 +648,7 @@ k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const ui
         for (int q = 0; q < kPartPerThread; q++) {
             if (item[q] == 0xffffffffu) continue;
             const uint32_t bucket = item[q] & 0xfffffu, r = (item[q] >> 20) & 0x7ffu, neg = item[q] >> 31;
-            const uint32_t pidx = tile0 + q * kPartThreads + threadIdx.x;
+            const uint32_t pidx = tile0 + q * kPartThreads + threadIdx.x + (h ? sh.phi_off : 0u);
             stage[cnt[bucket >> lb] + r] =
                 make_uint2(key0 + bucket, (sh.fixed_n ? (uint32_t)w * sh.fixed_n + pidx : pidx) | (neg << 31));
         }

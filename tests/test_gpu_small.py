@@ -249,3 +249,29 @@ def test_ipa_round_msms_over_resident_generators(route):
         ok, got = tab.multi(16 * t, sc)
         assert ok == 1 and got == O.msm(SE, [s % SE.n for s in sc], gens[16 * t:16 * t + 16]), t
     tab.destroy()
+
+
+# ------------------------------------------------------------------ GLV split in the pipeline (BN254)
+@pytest.mark.parametrize("glv", ["on", "off"])
+@pytest.mark.parametrize("n,window", [(3, 4), (600, 9), (600, 13), (600, 16), (5000, 0), (5000, 11), (40000, 0)])
+def test_glv_pipeline_matches_oracle(n, window, glv, monkeypatch):
+    """k = k1 + k2 lambda, 2n terms over (P_i, phi(P_i)) with half the windows: same bytes as the plain recoding and
+    as the oracle, for window sizes that do and do not divide 128, scalars at the corners of the split, infinities."""
+    monkeypatch.setenv("PORLA_NO_SMALL", "1")
+    monkeypatch.setenv("PORLA_GLV" if glv == "on" else "PORLA_NO_GLV", "1")
+    if window:
+        monkeypatch.setenv("PORLA_WINDOW_BITS", str(window))
+    rnd = random.Random(n * 31 + window)
+    g = O.glv_constants(BN)
+    lam = g["lambda"]
+    pts = chain(BN, min(n, 700), n)
+    pts = (pts * (n // len(pts) + 1))[:n]                    # repeated points: equal operands meet in the buckets
+    for i in range(0, n, 11):
+        pts[i] = None
+    sc = [rnd.randrange(1 << 256) for _ in range(n)]
+    corners = [0, 1, BN.n - 1, BN.n, lam, BN.n - lam, lam + 1, g["a2"], -g["b1"], BN.n // 2, (1 << 253) - 1, (1 << 127) - 1, 1 << 127]
+    for i, v in enumerate(corners[:n]):
+        sc[i] = v
+    pbytes, sbytes = b"".join(map(enc, pts)), b"".join(map(be, sc))
+    got = pb.bn254_multi_exp(pbytes, sbytes, n)
+    assert got == loader.bn254_msm(sbytes, pbytes, n, 4)

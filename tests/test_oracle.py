@@ -148,3 +148,38 @@ def test_reference_build_reproduces_its_own_golden():
     o33 = C.create_string_buffer(33)
     assert lib.ref_secp_msm_prepared(h, n, 8, None, o33) == 1 and o33.raw.hex() == case["sec1"]
     lib.ref_secp_release(h)
+
+
+def test_glv_constants_in_the_kernel_header_and_split_bounds():
+    """Bn254::glv_* in porla_b200/csrc/ec.cuh against an independent derivation (cube roots of unity, extended
+    Euclid on (r, lambda)), and the size bound of the split the recoder relies on (|k1|, |k2| < 2^127)."""
+    import os
+    import random
+    import re
+    from oracle import curves_py as O
+    c = O.BN254
+    g = O.glv_constants(c)
+    assert pow(g["beta"], 3, c.p) == 1 and g["beta"] != 1 and pow(g["lambda"], 3, c.n) == 1 and g["lambda"] != 1
+    P = O.hash_point(c, 7)
+    assert O.mul(c, g["lambda"], P) == (g["beta"] * P[0] % c.p, P[1])
+    assert (g["a1"] + g["b1"] * g["lambda"]) % c.n == 0 and (g["a2"] + g["b2"] * g["lambda"]) % c.n == 0
+    assert g["a1"] * g["b2"] - g["a2"] * g["b1"] == c.n and g["b2"] == g["a1"] and g["b1"] < 0
+    src = open(os.path.join(os.path.dirname(__file__), "..", "porla_b200", "csrc", "ec.cuh")).read()
+
+    def limbs(name):
+        body = re.search(r"%s\(int i\) \{[^}]*?m\[\d+\] = \{([^}]*)\}" % name, src, re.S).group(1)
+        return sum(int(tok.strip().rstrip("u"), 16) << (32 * i) for i, tok in enumerate(body.split(",")))
+
+    assert limbs("glv_beta_mont") == g["beta"] * (1 << 256) % c.p
+    assert limbs("glv_g1") == (g["b2"] << 256) // c.n
+    assert limbs("glv_g2") == ((-g["b1"]) << 256) // c.n
+    assert limbs("glv_a1") == g["a1"] and limbs("glv_a2") == g["a2"] and limbs("glv_nb1") == -g["b1"]
+    rnd = random.Random(127)
+    lam = g["lambda"]
+    ks = [0, 1, 2, c.n - 1, c.n - 2, c.n // 2, c.n // 2 + 1, lam, c.n - lam, lam - 1, lam + 1, (1 << 253) % c.n, (1 << 253) - 1,
+          1 << 128, (1 << 128) - 1, 1 << 127, g["a2"], g["a2"] - 1, c.n - g["a2"], -g["b1"], c.n + g["b1"]]
+    ks += [rnd.randrange(c.n) for _ in range(300000)]
+    for k in ks:
+        k1, k2 = O.glv_split(c, k, g)
+        assert (k1 + k2 * lam - k) % c.n == 0
+        assert abs(k1) < 1 << 127 and abs(k2) < 1 << 127
