@@ -162,7 +162,7 @@ struct Bn254 {
     static constexpr bool kHalveScalar = false;
     // GLV: phi(x, y) = (beta x, y) = lambda (x, y) with beta^3 = 1 in Fp, lambda^3 = 1 mod r.  A scalar k splits as
     // k = k1 + k2 lambda with |k1|, |k2| < 2^127 (lattice basis (a1, b1), (a2, b2), a1 b2 - a2 b1 = r; constants
-    // derived and checked in oracle/curves_py.py: glv_constants / tests/test_oracle.py), so an n-term MSM becomes a
+    // re-derived independently and compared limb by limb in tests/test_oracle.py), so an n-term MSM becomes a
     // 2n-term MSM over (P_i, phi(P_i)) with half as many windows, i.e. half as many buckets to reduce.
     static constexpr bool kGlv = true;
     static constexpr int kGlvBits = 127;
