@@ -34,4 +34,20 @@ rnd = random.Random(1)
 data = bytearray(b"".join(rnd.randrange(1 << 500).to_bytes(64, "little") for _ in range(32 * 3)))
 print("align", k.align_mac_batch(data, 3).hex()[:16])
 print("proof", k.create_proof(77, b"".join(be(rnd.randrange(1 << 256)) for _ in range(32)))[0].hex()[:16])
+# one-launch small paths: bitwise tree sum (1 and several blocks per window, batched), look-up-table sums (single,
+# batch with one scalar per thread), sub-range view of the table, block aggregation of an audit
+coeff = b"".join(pb.bn254_scalar_set_int(rnd.randrange(1 << 31)) for _ in range(700))
+G = O.bn254_marshal((1, 2))
+pts = G * 700
+print("bits", pb.bn254_multi_exp(pts, coeff, 700).hex()[:16], pb.bn254_multi_exp(pts[:64 * 100], coeff[:32 * 100], 100).hex()[:16])
+print("bits batch", pb.bn254_multi_exp_batch(pts[:64 * 120], coeff[:32 * 120], 40, 3).hex()[:16])
+blocks = b"".join(be(rnd.randrange(1 << 256)) for _ in range(32 * 20))
+print("lut", k.compute_digest_from_srs(blocks[:32 * 32]).hex()[:16], k.compute_digest_from_srs_batch(blocks, 20).hex()[:16])
+cf = b"".join(rnd.randrange(1 << 31).to_bytes(4, "little") for _ in range(50))
+bl = b"".join(rnd.randrange(1 << 500).to_bytes(64, "little") for _ in range(50 * 32))
+print("aggregate", k.audit_aggregate(cf, bl, 50)[1].hex()[:16])
+c = O.SECP256K1
+gens = pb.SecpGenerators([(c.gx, c.gy)] * 64)
+print("secp lut", gens.multi(0, [rnd.randrange(c.n) for _ in range(64)])[0], gens.multi(16, [rnd.randrange(c.n) for _ in range(16)])[0])
+gens.destroy()
 print("done")
