@@ -433,17 +433,23 @@ void butterfly_impl(PointTable* t, uint32_t m, const uint8_t* d_twiddles, int sc
         PORLA_CUDA(cudaMalloc(&t->d_flags, t->n));
         PORLA_CUDA(cudaMemsetAsync(t->d_flags, 0, t->n, stream));
     }
-    // Few butterflies (Porla's n = 1024 blocks: 512 threads) are pure latency: the inlined field type runs a
-    // lone warp's dependent multiplications about twice as fast as the outlined multiplier of the compact
-    // type; with the machine full the compact code (no instruction-cache pressure) wins.
+    // Measured per stage (one B200, warm clocks, tools/butterfly_times.py), BN254:
+    //   n = 1024 (512 butterflies, pure latency): plain double-and-add 2.16 ms inlined / 2.69 ms compact field type;
+    //            GLV joint double-and-add (127 doublings, one extra inversion per butterfly) 1.39 / 1.67 ms
+    //   n = 2^20: plain 42.1 / 47.3 ms, GLV 26.6 / 31.3 ms
+    // so BN254 always runs the inlined GLV form; secp256k1 (no GLV) keeps the inlined type for few butterflies and
+    // the compact one when the machine is full.
     const char* force = getenv("PORLA_BUTTERFLY_FIELD");
-    const bool inlined = force ? force[0] == 'i' : nb < 148u * 512u;
-    if (inlined)
-        k_butterfly<C, typename C::F><<<(nb + 127) / 128, 128, 0, stream>>>(
-            reinterpret_cast<Affine<typename C::F>*>(t->d_points), t->d_flags, t->n, m, d_twiddles, scalar_be);
-    else
-        k_butterfly<C, typename C::FC><<<(nb + 127) / 128, 128, 0, stream>>>(
-            reinterpret_cast<Affine<typename C::FC>*>(t->d_points), t->d_flags, t->n, m, d_twiddles, scalar_be);
+    const bool inlined = force ? force[0] == 'i' : (C::kGlv || nb < 148u * 512u);
+    const char* fg = getenv("PORLA_BUTTERFLY_GLV");
+    const bool glv = C::kGlv && (fg ? fg[0] == '1' : true);
+    auto* pf = reinterpret_cast<Affine<typename C::F>*>(t->d_points);
+    auto* pc = reinterpret_cast<Affine<typename C::FC>*>(t->d_points);
+    const dim3 grid((nb + 127) / 128);
+    if (inlined && glv) k_butterfly<C, typename C::F, true><<<grid, 128, 0, stream>>>(pf, t->d_flags, t->n, m, d_twiddles, scalar_be);
+    else if (inlined) k_butterfly<C, typename C::F, false><<<grid, 128, 0, stream>>>(pf, t->d_flags, t->n, m, d_twiddles, scalar_be);
+    else if (glv) k_butterfly<C, typename C::FC, true><<<grid, 128, 0, stream>>>(pc, t->d_flags, t->n, m, d_twiddles, scalar_be);
+    else k_butterfly<C, typename C::FC, false><<<grid, 128, 0, stream>>>(pc, t->d_flags, t->n, m, d_twiddles, scalar_be);
     LAUNCHED();
     if constexpr (C::kGlv) {
         if (t->phi_off) {   // the points changed: so does their endomorphism image
