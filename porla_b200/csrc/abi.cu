@@ -132,10 +132,23 @@ void run_and_fetch(int curve, const PointTable& tab, const uint8_t* d_scalars, i
 // half (PCIe, ~50 GB/s: 96 B per term) runs while the first half is being multiplied, and the two sets of
 // per-window sums are added by the host finaliser exactly as the multi-GPU path does.  Worth it from 2^19
 // terms (below that the second bucket reduction costs more than the copy it hides).  Caller holds g_io_mu.
+constexpr int kSplitPercentSmall = 25, kSplitPercentLarge = 40;
 void msm_host_split(int curve, const uint8_t* scalars, const uint8_t* points, int64_t n, int scalar_fmt, int point_fmt,
                     uint8_t* out) {
     auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const int64_t half[2] = {n / 2, n - n / 2};
+    // The first part's copy is exposed, the second part's hides behind the first MSM: a smaller first part shortens
+    // the exposed copy as long as the second copy still fits under the first MSM (PORLA_SPLIT_PERCENT to tune).
+    // Measured at 2^20 (pinned buffers, one B200): 50 % 5.20 ms, 40 % 5.13, 35 % 4.98, 30 % 4.83, 25 % 4.73, 20 % 4.90,
+    // one pass 5.48.  Above 2^21 the copy of the second part (1.75 ns per term) no longer fits under a quarter-size
+    // MSM (~2.7 ns per term), so the first part grows to 40 %.
+    static const int forced_percent = [] {
+        const char* e = getenv("PORLA_SPLIT_PERCENT");
+        int v = e ? atoi(e) : 0;
+        return v < 5 || v > 95 ? 0 : v;
+    }();
+    const int split_percent = forced_percent ? forced_percent : (n <= (1 << 21) ? kSplitPercentSmall : kSplitPercentLarge);
+    const int64_t first_part = n * split_percent / 100;
+    const int64_t half[2] = {first_part, n - first_part};
     const MsmPlan plan = msm_plan(curve, (uint32_t)half[1], 1, 0);
     const size_t ws_bytes = (size_t)plan.nwin * 128;
     // table region: every half's points are followed by their endomorphism image (2 * 64 B per point)
@@ -148,6 +161,7 @@ void msm_host_split(int curve, const uint8_t* scalars, const uint8_t* points, in
     opt.out_fmt = point_fmt;
     opt.shared_points = 1;
     opt.window_bits = plan.c;
+    opt.glv = plan.glv;           // both parts with the larger part's layout: their window sums are added window by window
     opt.no_fixed_base = 1;
     int64_t first = 0;
     for (int h = 0; h < 2; h++) {

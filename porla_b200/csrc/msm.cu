@@ -153,7 +153,7 @@ struct WindowChoice {
     int c;
     int glv;
 };
-static WindowChoice choose_window_ex(int curve, uint32_t n, uint32_t nbatch, int forced_c) {
+static WindowChoice choose_window_ex(int curve, uint32_t n, uint32_t nbatch, int forced_c, int forced_glv = -1) {
     const char* env = getenv("PORLA_WINDOW_BITS");
     if (forced_c <= 0 && env && atoi(env) >= 2 && atoi(env) <= 24) forced_c = atoi(env);
     const int bits = scalar_bits(curve);
@@ -164,6 +164,8 @@ static WindowChoice choose_window_ex(int curve, uint32_t n, uint32_t nbatch, int
     for (int c = 3; c <= 20; c++) {   // 20: the widest window the shared-memory radix partition packs
         if (forced_c > 0 && c != forced_c) continue;
         double plain = window_cost(bits, (double)n, nbatch, c);
+        if (forced_glv == 1 && glv_ok && forced_c > 0) return WindowChoice{forced_c, 1};
+        if (forced_glv == 0 && forced_c > 0) return WindowChoice{forced_c, 0};
         if (force_glv && force_glv[0] == '1' && glv_ok) plain = -1;
         if (plain >= 0 && plain < best) {
             best = plain;
@@ -246,12 +248,12 @@ MsmPlan msm_plan_table(const PointTable& t, uint32_t n, uint32_t nbatch, const M
         if (opt.max_scalar_bits > 0 && opt.max_scalar_bits < bits) bits = opt.max_scalar_bits;
         if ((uint64_t)n * nbatch * (uint64_t)bits <= small_bits_limit()) return MsmPlan{1, bits, kPlanBits, 0};
     }
-    return msm_plan(t.curve, n, nbatch, opt.window_bits);
+    return msm_plan(t.curve, n, nbatch, opt.window_bits, opt.glv);
 }
 
-MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits) {
+MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits, int glv) {
     MsmPlan p;
-    const WindowChoice ch = choose_window_ex(curve, n, nbatch, window_bits);
+    const WindowChoice ch = choose_window_ex(curve, n, nbatch, window_bits, glv);
     p.c = ch.c;
     p.glv = ch.glv;
     p.nwin = ((ch.glv ? Bn254::kGlvBits : scalar_bits(curve)) + 1 + p.c - 1) / p.c;

@@ -74,6 +74,7 @@ struct MsmOptions {
     // its host buffer: Porla's audit coefficients are 31-bit, utils.h:271-275); 0 = the full order width.
     int max_scalar_bits = 0;
     int no_small = 0;         // always run the sort / accumulate / reduce pipeline
+    int glv = -1;             // -1: decided by the plan; 0 / 1: forced (parts of one MSM must agree on the window layout)
 };
 
 enum PlanMode : int { kPlanPipeline = 0, kPlanBits = 1, kPlanLut = 2 };
@@ -84,7 +85,7 @@ struct MsmPlan {
     int glv;    // pipeline only: scalars split with the GLV endomorphism; nwin then counts the windows of ONE half
 };
 // The sort / accumulate / reduce pipeline's plan for n terms.
-MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits);
+MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits, int glv = -1);
 // Plan for a specific call.  Fixed-base expansion applicable: nwin = 1 (a single shared bucket set or the
 // look-up table, one "window sum" per MSM, no doublings), c = the expansion's window size.  Few terms in
 // total and no explicit window size: one window per scalar bit (k_small_bits), c = 1.

@@ -153,7 +153,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     sh.shared = opt.shared_points ? 1u : 0u;
     const bool fixed = table.fb_c > 0 && opt.shared_points && !opt.no_fixed_base &&
                        (opt.window_bits == 0 || opt.window_bits == table.fb_c);
-    const MsmPlan wplan = fixed ? MsmPlan{table.fb_c, 1, kPlanPipeline, 0} : msm_plan(curve, n, nbatch, opt.window_bits);
+    const MsmPlan wplan = fixed ? MsmPlan{table.fb_c, 1, kPlanPipeline, 0} : msm_plan(curve, n, nbatch, opt.window_bits, opt.glv);
     const bool glv = wplan.glv != 0;
     if (glv && !(C::kGlv && table.phi_off)) {
         fprintf(stderr, "[libmultiexp/porla_b200] FATAL: GLV plan for a table without its endomorphism image\n");
