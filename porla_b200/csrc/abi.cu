@@ -261,6 +261,12 @@ void srs_commit_core(const uint8_t* coeffs_be, int64_t n, int64_t nbatch, uint8_
     if (n > (int64_t)g_kzg.srs_table.n) die("polynomial longer than the SRS");
     device_init();
     std::lock_guard<std::mutex> lock(g_io_mu);
+    // a large batch over a mid-sized SRS (BASELINE config 3) is worth the one-time wide-window look-up table
+    if ((uint64_t)n * (uint64_t)nbatch >= (1ull << 22) && g_kzg.srs_table.n > 2048 && g_kzg.srs_table.n <= 8192 &&
+        !g_kzg.srs_table.d_lut && !getenv("PORLA_NO_LUT")) {
+        table_precompute(&g_kzg.srs_table, 0, (uint32_t)n, (uint32_t)nbatch, g_stage.stream);
+        PORLA_CUDA(cudaStreamSynchronize(g_stage.stream));
+    }
     size_t sc_bytes = (size_t)n * nbatch * 32;
     size_t out_off = (sc_bytes + 255) & ~(size_t)255;
     uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(kCurveBn254, n, nbatch));
@@ -628,7 +634,7 @@ void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const voi
     view.n = (uint32_t)n;
     if (t->t.fb_c > 0) {                          // the expansion's rows keep their stride; start them at `first`
         view.d_fb_points = (uint8_t*)t->t.d_fb_points + (size_t)first * 64;
-        if (t->t.d_lut) view.d_lut = (uint8_t*)t->t.d_lut + (((size_t)first << (t->t.fb_c - 1)) * 64);
+        if (t->t.d_lut) view.d_lut = (uint8_t*)t->t.d_lut + ((((size_t)first * t->t.fb_nwin) << (t->t.fb_c - 1)) * 64);
     }
     MsmOptions opt;
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;

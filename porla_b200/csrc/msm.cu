@@ -87,6 +87,7 @@ template <class C> void msm_impl(const PointTable&, const uint8_t*, uint32_t, ui
 template <class C> void precompute_impl(PointTable*, int, cudaStream_t);
 template <class C> void lut_impl(PointTable*, cudaStream_t);
 constexpr uint32_t kLutMaxBases = 2048;   // 512 MiB of table at most
+constexpr uint32_t kLutMaxBasesBatched = 8192;
 constexpr int kLutWindow = 8;
 template <class C> void combine_impl(const void*, uint32_t, uint32_t, int, uint8_t*, cudaStream_t);
 template <class C> void scalar_mul_impl(const PointTable&, const uint8_t*, int, uint32_t, void*, cudaStream_t);
@@ -209,10 +210,32 @@ int choose_window_fixed_base(int curve, uint32_t n, uint32_t nbatch) {
 
 int table_precompute(PointTable* t, int c, uint32_t n_hint, uint32_t batch_hint, cudaStream_t stream) {
     device_init();
-    // Small tables (Porla's 128-point SRS / generator sets) get the full look-up table: 8-bit windows,
-    // 32 windows x 128 multiples x 64 B = 256 KiB per base.
-    const bool want_lut = c <= 0 && t->n > 0 && t->n <= kLutMaxBases && !getenv("PORLA_NO_LUT");
-    if (want_lut) c = kLutWindow;
+    // Small tables (Porla's 128-point SRS / generator sets) get the full look-up table of window multiples with
+    // 8-bit windows: 32 windows x 128 multiples x 64 B = 256 KiB per base, L2-resident for 128 bases.  A table
+    // shared by a large batch (BASELINE config 3: 4096 commitments over 4096 bases) gets the WIDEST windows whose
+    // table fits the HBM budget (c = 15: 17 windows x 16384 multiples x 4096 bases x 64 B = 73 GB of the B200's
+    // 180 GB): every scalar then costs 17 gathers and mixed additions, with no sort and no bucket reduction.
+    bool want_lut = false;
+    if (c <= 0 && t->n > 0 && t->n <= kLutMaxBasesBatched && (uint64_t)(n_hint ? n_hint : t->n) * (batch_hint ? batch_hint : 1) >= (1ull << 22) &&
+        !getenv("PORLA_NO_LUT")) {
+        const char* e = getenv("PORLA_LUT_BUDGET_GB");
+        double budget = (e && atof(e) > 0 ? atof(e) : 80.0) * 1e9;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (double)free_b * 0.6 < budget) budget = (double)free_b * 0.6;
+        const int bits = scalar_bits(t->curve);
+        for (int cc = 16; cc >= 9; cc--) {
+            const double nwin = (double)((bits + 1 + cc - 1) / cc);
+            if (nwin * (double)t->n * (double)(1u << (cc - 1)) * 64.0 <= budget) {
+                c = cc;
+                want_lut = true;
+                break;
+            }
+        }
+    }
+    if (c <= 0 && t->n > 0 && t->n <= kLutMaxBases && !getenv("PORLA_NO_LUT")) {
+        c = kLutWindow;
+        want_lut = true;
+    }
     if (c <= 0) c = choose_window_fixed_base(t->curve, n_hint ? n_hint : t->n, batch_hint ? batch_hint : 1);
     if (t->curve == kCurveBn254) precompute_impl<Bn254>(t, c, stream);
     else precompute_impl<Secp256k1>(t, c, stream);

@@ -37,7 +37,7 @@ struct PointTable {
                                   // [first, first + n) of the table keeps it and offsets the pointers by `first`)
     void* d_fb_points = nullptr;
     // Optional look-up table of EVERY window multiple on top of the expansion (small tables only):
-    // lut[((w*n + i) << (fb_c-1)) + d - 1] = d * 2^(fb_c*w) * P_i, 1 <= d <= 2^(fb_c-1).  An MSM over the
+    // lut[((i*fb_nwin + w) << (fb_c-1)) + d - 1] = d * 2^(fb_c*w) * P_i, 1 <= d <= 2^(fb_c-1).  An MSM over the
     // table is then a plain sum of n * fb_nwin entries (k_lut_sum): no sort, no buckets, no doublings.
     void* d_lut = nullptr;
     // GLV (BN254): phi(P_i) = (beta x_i, y_i) is stored behind the table, at entry phi_off + i of d_points

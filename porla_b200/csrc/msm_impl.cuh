@@ -94,7 +94,17 @@ void msm_small_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t 
     if (lut) {
         // few MSMs: two table entries per thread, depth = log2 of the term count; many MSMs: one scalar
         // (all its windows) per thread, the machine is full anyway and the tree is 7 levels
-        K = nbatch > 8 ? (uint32_t)table.fb_nwin : 2u;
+        // few MSMs: two table entries per thread; many: whole scalars per thread, several of them once the machine
+        // is full four times over, so that the block tree (7 levels, three of four warps idle) is paid less often
+        uint32_t per_thread = 1;
+        if (nbatch > 8) {
+            const uint64_t want_threads = 148ull * 3 * kTreeThreads * 4;
+            per_thread = (uint32_t)(((uint64_t)n * nbatch) / want_threads);
+            if (per_thread < 1) per_thread = 1;
+            if (per_thread > 16) per_thread = 16;
+            while (per_thread > 1 && n / per_thread < (uint32_t)kTreeThreads) per_thread >>= 1;
+        }
+        K = nbatch > 8 ? (uint32_t)table.fb_nwin * per_thread : 2u;
         const uint32_t threads = (n * (uint32_t)table.fb_nwin + K - 1) / K;
         nblk = (threads + kTreeThreads - 1) / kTreeThreads;
     } else {
@@ -112,9 +122,10 @@ void msm_small_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t 
     for (int st = kStageCount; st <= kStageAccumulate; st++) g_stage_timer.mark(st, stream);
     if (nblk > 1) PORLA_CUDA(cudaMemsetAsync(tickets, 0, (size_t)slots * 4, stream));
     if (lut) {
-        k_lut_sum<C><<<dim3(nblk, nbatch), kTreeThreads, 0, stream>>>(reinterpret_cast<const Affine<F>*>(table.d_lut), table.fb_n,
-                                                                     table.fb_c, table.fb_nwin, d_scalars, opt.scalar_be, n, K,
-                                                                     partials, tickets, wsum);
+        const int m_major = nbatch > 8 ? 1 : 0;
+        k_lut_sum<C><<<m_major ? dim3(nbatch, nblk) : dim3(nblk, nbatch), kTreeThreads, 0, stream>>>(
+            reinterpret_cast<const Affine<F>*>(table.d_lut), table.fb_c, table.fb_nwin, d_scalars, opt.scalar_be, n, K, m_major,
+            partials, tickets, wsum);
     } else {
         k_small_bits<C><<<dim3(nblk, (uint32_t)plan.nwin, nbatch), kTreeThreads, 0, stream>>>(
             reinterpret_cast<const Affine<F>*>(table.d_points), table.d_flags, d_scalars, opt.scalar_be, n, opt.shared_points,

@@ -12,7 +12,10 @@
 //   k_lut_sum     fixed bases (SRS / generator tables).  A look-up table resident in HBM holds EVERY
 //                 multiple d * 2^(c*w) * P_i (1 <= d <= 2^(c-1)); an MSM is the sum of n * nwin table
 //                 entries, no doublings at all.  128 bases, c = 8: 32 windows x 128 multiples x 128 bases
-//                 x 64 B = 32 MiB (L2-resident on a B200).
+//                 x 64 B = 32 MiB (L2-resident on a B200).  Layout [base][window][multiple]: the entries one
+//                 scalar touches lie within nwin * 2^(c-1) * 64 B, and a large batch walks the table one slab
+//                 of 128 bases at a time (blocks of the same bases are adjacent in the grid), which keeps the
+//                 gathers of a 73 GB table (4096 bases, c = 15) inside a 2.3 GB working set.
 //   k_lut_build   fills that table from the fixed-base window expansion (k_precompute_windows).
 //
 // Both sum kernels: a block of 128 threads folds its terms with mixed additions, then a shared-memory
@@ -25,6 +28,16 @@ namespace porla {
 
 constexpr int kTreeThreads = 128;
 
+// ONE copy of the XYZZ addition for the trees below (the kernels already inline the mixed addition of their main
+// loop; a second and third inlined 14-product addition made the batched look-up sums instruction-fetch bound:
+// ncu stall_no_instructions on top, 60 % multiplier-pipe utilisation).
+template <class F>
+__device__ __noinline__ void xyzz_add_shared(XYZZ<F>* a, const XYZZ<F>* b) {
+    XYZZ<F> r = *a;
+    r.add(*b);
+    *a = r;
+}
+
 // Sum of v over the first `count` threads of the block (count <= kTreeThreads); every thread must call.
 // The result is returned to thread 0.
 template <class F>
@@ -35,11 +48,7 @@ PORLA_D XYZZ<F> block_tree_sum(const XYZZ<F>& v, uint32_t count, XYZZ<F>* sh) {
     while (o < count) o <<= 1;
 #pragma unroll 1
     for (o >>= 1; o > 0; o >>= 1) {
-        if (threadIdx.x < o && threadIdx.x + o < count) {
-            XYZZ<F> a = sh[threadIdx.x];
-            a.add(sh[threadIdx.x + o]);
-            sh[threadIdx.x] = a;
-        }
+        if (threadIdx.x < o && threadIdx.x + o < count) xyzz_add_shared(&sh[threadIdx.x], &sh[threadIdx.x + o]);
         __syncthreads();
     }
     XYZZ<F> r = sh[0];
@@ -74,7 +83,7 @@ PORLA_D void fold_blocks(const XYZZ<F>& v, uint32_t slot, uint32_t blk, uint32_t
         for (int q = 0; q < 8; q++) {
             d[q].x = src[k * 8 + q].x; d[q].y = src[k * 8 + q].y; d[q].z = src[k * 8 + q].z; d[q].w = src[k * 8 + q].w;
         }
-        acc.add(p);
+        xyzz_add_shared(&acc, &p);
     }
     XYZZ<F> r = block_tree_sum(acc, nblk < (uint32_t)kTreeThreads ? nblk : (uint32_t)kTreeThreads, sh);
     if (threadIdx.x == 0) st16(out + slot, r);
@@ -130,7 +139,7 @@ k_small_bits(const Affine<typename C::F>* __restrict__ points, const uint8_t* __
 }
 
 // ---------------------------------------------------------------------------- fixed bases, full look-up table
-// lut[((w * n_table + i) << (c-1)) + d - 1] = d * 2^(c*w) * P_i.
+// lut[((i * nwin + w) << (c-1)) + d - 1] = d * 2^(c*w) * P_i.
 // Signed c-bit digits as in k_digits.  The carry into window w is 1 exactly when the low c*w bits of the
 // scalar exceed H_w = sum_{j<w} 2^(c-1) * 2^(c*j) (the value whose every digit sits on the rounding
 // boundary), so a thread can start at any window without walking the lower ones.
@@ -151,20 +160,24 @@ PORLA_D uint32_t carry_into_window(const uint32_t* s, int c, int w) {
     return 0;
 }
 
-// Thread t of MSM m folds the pairs [t*K, (t+1)*K) of the n*nwin (scalar i, window w) pairs, p = i*nwin + w.
-// grid = (blocks per MSM, nbatch); out[m] = the MSM's XYZZ sum.
+// Thread t of MSM m folds the pairs [t*K, (t+1)*K) of the n*nwin (scalar i, window w) pairs, p = i*nwin + w, whose
+// table entry is lut[(p << (c-1)) + |digit| - 1].  Grid: (blocks per MSM, nbatch), or (nbatch, blocks per MSM) when
+// m_major (large batches: concurrently resident blocks then read the same slab of bases).  out[m] = the MSM's sum.
+// The next entry is fetched before the current mixed addition: the loads depend on the digits only.
 template <class C>
 __global__ void __launch_bounds__(kTreeThreads)
-k_lut_sum(const Affine<typename C::F>* __restrict__ lut, uint32_t n_table, int c, int nwin,
-          const uint8_t* __restrict__ scalars, int big_endian, uint32_t n, uint32_t K,
+k_lut_sum(const Affine<typename C::F>* __restrict__ lut, int c, int nwin,
+          const uint8_t* __restrict__ scalars, int big_endian, uint32_t n, uint32_t K, int m_major,
           XYZZ<typename C::F>* __restrict__ partials, uint32_t* __restrict__ tickets,
           XYZZ<typename C::F>* __restrict__ out) {
     using F = typename C::F;
     __shared__ XYZZ<F> sh[kTreeThreads];
-    const uint32_t m = blockIdx.y;
+    const uint32_t m = m_major ? blockIdx.x : blockIdx.y;
+    const uint32_t blk = m_major ? blockIdx.y : blockIdx.x;
+    const uint32_t nblk = m_major ? gridDim.y : gridDim.x;
     const uint32_t total = n * (uint32_t)nwin;
     const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1u;
-    uint32_t p = (blockIdx.x * kTreeThreads + threadIdx.x) * K;
+    uint32_t p = (blk * kTreeThreads + threadIdx.x) * K;
     const uint32_t p_end = p + K < total ? p + K : total;
     XYZZ<F> acc = XYZZ<F>::inf();
     if (p < total) {
@@ -174,35 +187,42 @@ k_lut_sum(const Affine<typename C::F>* __restrict__ lut, uint32_t n_table, int c
         uint32_t flip = canonical_scalar<C>(scalars, (size_t)m * n + i, big_endian, s);
         s[8] = 0;
         uint32_t carry = carry_into_window(s, c, w);
+        Affine<F> cur = Affine<F>::inf();     // entry of the previous pair, added one iteration later
 #pragma unroll 1
-        for (; p < p_end; p++) {
-            const uint32_t pos = (uint32_t)w * c, word = pos >> 5, sft = pos & 31;
-            const uint32_t lo = s[word < 8 ? word : 8], hi = s[word < 7 ? word + 1 : 8];
-            const uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry;
-            const uint32_t dneg = d > half;
-            carry = dneg;
-            const uint32_t mag = dneg ? ((1u << c) - d) : d;
-            if (mag != 0) {
-                Affine<F> q = ld16(lut + ((((size_t)w * n_table + i) << (c - 1)) + (mag - 1)));
-                if (dneg ^ flip) q.y = q.y.neg();
-                acc.madd(q);
-            }
-            if (++w == nwin) {
-                w = 0;
-                carry = 0;
-                if (++i < n && p + 1 < p_end) {
-                    flip = canonical_scalar<C>(scalars, (size_t)m * n + i, big_endian, s);
-                    s[8] = 0;
+        for (; p <= p_end; p++) {             // one extra turn adds the last entry (a single copy of the mixed addition)
+            Affine<F> nxt = Affine<F>::inf();
+            if (p < p_end) {
+                const uint32_t pos = (uint32_t)w * c, word = pos >> 5, sft = pos & 31;
+                const uint32_t lo = s[word < 8 ? word : 8], hi = s[word < 7 ? word + 1 : 8];
+                const uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry;
+                const uint32_t dneg = d > half;
+                carry = dneg;
+                const uint32_t mag = dneg ? ((1u << c) - d) : d;
+                if (mag != 0) {
+                    nxt = ld16(lut + (((size_t)p << (c - 1)) + (mag - 1)));
+                    if (dneg ^ flip) nxt.y = nxt.y.neg();
+                }
+                if (++w == nwin) {
+                    w = 0;
+                    carry = 0;
+                    if (++i < n && p + 1 < p_end) {
+                        flip = canonical_scalar<C>(scalars, (size_t)m * n + i, big_endian, s);
+                        s[8] = 0;
+                    }
                 }
             }
+            acc.madd(cur);
+            cur = nxt;
         }
     }
     XYZZ<F> r = block_tree_sum(acc, kTreeThreads, sh);
-    fold_blocks(r, m, blockIdx.x, gridDim.x, partials, tickets, out, sh);
+    fold_blocks(r, m, blk, nblk, partials, tickets, out, sh);
 }
 
-// One thread per (window, base): the 2^(c-1) multiples of Q = 2^(c*w) * P_i, each normalised to affine.
-// Built once per table (at SRS upload); the inversion per entry is of no consequence there.
+// One thread per (window, base): the 2^(c-1) multiples of Q = 2^(c*w) * P_i, normalised to affine kLutChunk at a
+// time with ONE inversion per chunk (Montgomery's trick on the zzz coordinates): ~36 field products per entry, so
+// the 1.1 * 10^9 entries of a 4096-base, c = 15 table (73 GB) are a fraction of a second of one-time work.
+constexpr int kLutChunk = 16;
 template <class C>
 __global__ void __launch_bounds__(128)
 k_lut_build(const Affine<typename C::FC>* __restrict__ fb_points, const uint8_t* __restrict__ inf_flags, uint32_t n,
@@ -212,7 +232,8 @@ k_lut_build(const Affine<typename C::FC>* __restrict__ fb_points, const uint8_t*
     if (t >= n * (uint32_t)nwin) return;
     const uint32_t i = t % n;
     const uint32_t count = 1u << (c - 1);
-    Affine<F>* dst = lut + ((size_t)t << (c - 1));     // t = w * n + i
+    const uint32_t w = t / n;                          // fb_points is [window][base], the table [base][window][multiple]
+    Affine<F>* dst = lut + (((size_t)i * nwin + w) << (c - 1));
     const Affine<F> q = ld16(fb_points + t);
     if (q.is_inf() || (inf_flags && inf_flags[i])) {
         for (uint32_t d = 0; d < count; d++) st16(dst + d, Affine<F>::inf());
@@ -220,11 +241,27 @@ k_lut_build(const Affine<typename C::FC>* __restrict__ fb_points, const uint8_t*
     }
     st16(dst, q);
     XYZZ<F> r = XYZZ<F>::from_affine(q);
-    for (uint32_t d = 1; d < count; d++) {
-        r.madd(q);
-        Affine<F> a = r.to_affine();
-        st16(dst + d, a);
-        r = XYZZ<F>::from_affine(a);
+    XYZZ<F> buf[kLutChunk];
+    F prefix[kLutChunk];
+    for (uint32_t d0 = 1; d0 < count; d0 += kLutChunk) {
+        const uint32_t m = count - d0 < (uint32_t)kLutChunk ? count - d0 : (uint32_t)kLutChunk;
+        F acc = F::one();
+        for (uint32_t j = 0; j < m; j++) {
+            r.madd(q);                 // (d0 + j + 1) * Q: never infinity below the group order
+            buf[j] = r;
+            acc = acc * r.zzz;
+            prefix[j] = acc;
+        }
+        F inv = acc.inverse();         // 1 / (zzz_0 ... zzz_{m-1})
+        for (uint32_t j = m; j-- > 0;) {
+            const F i3 = j ? prefix[j - 1] * inv : inv;     // 1 / zzz_j
+            inv = inv * buf[j].zzz;
+            const F tt = buf[j].zz * i3;                    // 1 / zz_j = (zz_j / zzz_j)^2
+            Affine<F> a;
+            a.x = buf[j].x * tt.sqr();
+            a.y = buf[j].y * i3;
+            st16(dst + d0 + j, a);
+        }
     }
 }
 

@@ -275,3 +275,33 @@ def test_glv_pipeline_matches_oracle(n, window, glv, monkeypatch):
     pbytes, sbytes = b"".join(map(enc, pts)), b"".join(map(be, sc))
     got = pb.bn254_multi_exp(pbytes, sbytes, n)
     assert got == loader.bn254_msm(sbytes, pbytes, n, 4)
+
+
+def test_wide_window_lookup_table_for_large_batches(monkeypatch):
+    """A table shared by a large batch gets the widest windows whose look-up table fits the budget (BASELINE config 3:
+    4096 commitments over 4096 bases, c = 15, 73 GB); here 300 bases under a 1 GB budget (c = 12), batches and
+    single MSMs against the general path and the closed form."""
+    import torch
+    monkeypatch.setenv("PORLA_LUT_BUDGET_GB", "1")
+    n, nb = 300, 9
+    rnd = random.Random(73)
+    ks = [rnd.randrange(BN.n) for _ in range(n)]
+    ks[5] = 0                                               # an infinity base
+    tab = pb.Table.multiples_of_generator(pb.CURVE_BN254, b"".join(map(le, ks)), n, pb.SCALAR_LE32)
+    ss = [rnd.randrange(1 << 256) for _ in range(nb * n)]
+    ss[0], ss[1], ss[2] = BN.n - 1, int.from_bytes(bytes([0x08, 0x00] * 16), "big"), (1 << 256) - 1
+    d_sc = torch.frombuffer(bytearray(b"".join(map(le, ss))), dtype=torch.uint8).cuda()
+    general = torch.zeros(64 * nb, dtype=torch.uint8, device="cuda")
+    tab.msm_device(d_sc.data_ptr(), n, general.data_ptr(), nbatch=nb, scalar_fmt=pb.SCALAR_LE32, shared_points=True)
+    torch.cuda.synchronize()
+    c = tab.precompute(0, n, 1 << 15)                       # 300 x 32768 scalars per launch: worth a wide table
+    assert 10 <= c <= 13
+    fixed = torch.zeros(64 * nb, dtype=torch.uint8, device="cuda")
+    tab.msm_device(d_sc.data_ptr(), n, fixed.data_ptr(), nbatch=nb, scalar_fmt=pb.SCALAR_LE32, shared_points=True)
+    torch.cuda.synchronize()
+    assert torch.equal(fixed, general)
+    for m in range(nb):
+        want = O.mul(BN, sum(s * k for s, k in zip(ss[m * n:(m + 1) * n], ks)) % BN.n, (1, 2))
+        assert bytes(fixed[64 * m:64 * m + 64].cpu().numpy().tobytes()) == enc(want), m
+    assert tab.msm_resident(d_sc.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32) == bytes(fixed[:64].cpu().numpy().tobytes())
+    tab.destroy()
