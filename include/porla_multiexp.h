@@ -130,7 +130,13 @@ void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const voi
 /* Building blocks of a range-sharded MSM (one process per GPU): every rank runs
  * the pipeline over its point range up to the per-window sums (nwin XYZZ records of 128 B, about
  * 2 KiB), the ranks all-gather them, and one host combines: add the parts window by window, Horner
- * over the windows, normalise.  All ranks must use the same window size (porla_msm_plan). */
+ * over the windows, normalise.  All ranks must use the same window layout: rank 0 (or every rank, with the same n)
+ * calls porla_msm_plan and the returned *c_out is passed back as `window_bits` / `c` of the two calls below.  *c_out
+ * is a plan code: bits 0..7 the window size, bit 8 set = scalars split with the GLV endomorphism (then nwin counts the
+ * windows of one half), bit 9 set = not split.  A plain window size (no bit 8 / 9) lets each call decide by itself. */
+#define PORLA_PLAN_WINDOW(code) ((code) & 0xff)
+#define PORLA_PLAN_GLV_ON 0x100
+#define PORLA_PLAN_GLV_OFF 0x200
 void porla_msm_plan(int curve, int64_t n, int64_t nbatch, int window_bits, int* c_out, int* nwin_out);
 void porla_msm_window_sums_device(const porla_table* t, const void* d_scalars, int64_t n, int scalar_fmt,
                                   int window_bits, void* d_window_sums, void* cuda_stream);

@@ -76,6 +76,12 @@ struct Staging {
 };
 Staging g_stage;
 
+// window_bits argument of the device entry points: a plain window size, or a plan code of porla_msm_plan
+void decode_plan(int code, MsmOptions* opt) {
+    opt->window_bits = PORLA_PLAN_WINDOW(code);
+    opt->glv = (code & PORLA_PLAN_GLV_ON) ? 1 : (code & PORLA_PLAN_GLV_OFF) ? 0 : -1;
+}
+
 [[noreturn]] void die(const char* msg) {
     fprintf(stderr, "[libmultiexp/porla_b200] FATAL: %s\n", msg);
     abort();
@@ -588,7 +594,7 @@ void porla_msm_device(const porla_table* t, const void* d_scalars, int64_t n, in
     int64_t need = shared_points ? n : n * nbatch;
     if (need > (int64_t)t->t.n) die("porla_msm_device: table shorter than the MSM");
     MsmOptions opt;
-    opt.window_bits = window_bits;
+    decode_plan(window_bits, &opt);
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.out_fmt = out_fmt;
     opt.shared_points = shared_points;
@@ -606,7 +612,7 @@ void porla_msm_resident(const porla_table* t, const void* d_scalars, int64_t n, 
     std::lock_guard<std::mutex> lock(g_io_mu);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     MsmOptions opt;
-    opt.window_bits = window_bits;
+    decode_plan(window_bits, &opt);
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.out_fmt = out_fmt;
     opt.shared_points = 1;
@@ -644,8 +650,10 @@ void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const voi
 }
 
 void porla_msm_plan(int curve, int64_t n, int64_t nbatch, int window_bits, int* c_out, int* nwin_out) {
-    MsmPlan p = msm_plan(curve, (uint32_t)n, (uint32_t)nbatch, window_bits);
-    *c_out = p.c;
+    MsmOptions o;
+    decode_plan(window_bits, &o);
+    MsmPlan p = msm_plan(curve, (uint32_t)n, (uint32_t)nbatch, o.window_bits, o.glv);
+    *c_out = p.c | (p.glv ? PORLA_PLAN_GLV_ON : PORLA_PLAN_GLV_OFF);
     *nwin_out = p.nwin;
 }
 
@@ -653,7 +661,10 @@ void porla_msm_window_sums_device(const porla_table* t, const void* d_scalars, i
                                   void* d_window_sums, void* cuda_stream) {
     if (n > (int64_t)t->t.n) die("porla_msm_window_sums_device: table shorter than the MSM");
     MsmOptions opt;
-    opt.window_bits = msm_plan(t->t.curve, (uint32_t)n, 1, window_bits).c;
+    decode_plan(window_bits, &opt);
+    const MsmPlan plan = msm_plan(t->t.curve, (uint32_t)n, 1, opt.window_bits, opt.glv);
+    opt.window_bits = plan.c;
+    opt.glv = plan.glv;
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.shared_points = 1;
     opt.no_fixed_base = 1;  // the sharded protocol exchanges nwin window sums per rank
@@ -662,7 +673,7 @@ void porla_msm_window_sums_device(const porla_table* t, const void* d_scalars, i
 }
 
 void porla_msm_finalize_host(int curve, const void* h_window_sums, int64_t nparts, int nwin, int c, int out_fmt, void* out64) {
-    finalize_host_parts(curve, h_window_sums, (int)nparts, nwin, c, out_fmt, (uint8_t*)out64);
+    finalize_host_parts(curve, h_window_sums, (int)nparts, nwin, PORLA_PLAN_WINDOW(c), out_fmt, (uint8_t*)out64);
 }
 
 void porla_msm_combine_device(int curve, const void* d_parts, int64_t count, int64_t nbatch, int out_fmt, void* d_out,

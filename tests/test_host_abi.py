@@ -96,3 +96,23 @@ def test_pairing_selfcheck_and_tampered_proofs():
     assert not k.verify_proof(c, other, z, y)
     assert not k.verify_proof(c, h, be(g["z"] + 1), y)
     assert not k.verify_proof(c, bytes(64), z, y)               # H = infinity
+
+
+def test_msm_plan_codes_carry_the_window_layout():
+    """porla_msm_plan needs no GPU: the plan code (window size | GLV on/off) that all ranks of a sharded MSM pass back,
+    and the number of window sums it implies."""
+    import ctypes as C
+    import porla_b200 as pb
+    lib = pb.load()
+    c, nwin = C.c_int(0), C.c_int(0)
+    lib.porla_msm_plan(pb.CURVE_BN254, 1 << 20, 1, 0, C.byref(c), C.byref(nwin))
+    assert c.value & 0xFF == 16 and c.value & 0x100 and nwin.value == 8          # GLV: 8 windows per 127-bit half
+    code = c.value
+    lib.porla_msm_plan(pb.CURVE_BN254, (1 << 20) - 12345, 1, code, C.byref(c), C.byref(nwin))
+    assert c.value == code and nwin.value == 8                                   # a rank with another n keeps the layout
+    lib.porla_msm_plan(pb.CURVE_BN254, 1 << 20, 1, 16 | 0x200, C.byref(c), C.byref(nwin))
+    assert c.value == 16 | 0x200 and nwin.value == 16
+    lib.porla_msm_plan(pb.CURVE_BN254, 1 << 24, 1, 0, C.byref(c), C.byref(nwin))
+    assert c.value == 20 | 0x200 and nwin.value == 13
+    lib.porla_msm_plan(pb.CURVE_SECP256K1, 1 << 18, 1, 0, C.byref(c), C.byref(nwin))
+    assert c.value == 16 | 0x200 and nwin.value == 16
