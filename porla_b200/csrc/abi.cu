@@ -76,6 +76,56 @@ struct Staging {
 };
 Staging g_stage;
 
+// Small calls (Porla's 16..766-term MSMs and 128-term commitments) lease one of a few persistent staging slots (device
+// buffer, pinned buffer, stream, scratch block) and do not take g_io_mu: the pool threads of Server.hpp:1077-1078 /
+// Client.hpp:377-406 then overlap on the device instead of queueing behind one another.  The slots outlive the calling
+// threads (Porla builds a fresh ThreadPool inside align_MAC, Server.hpp:487).  Larger calls, and small ones when every
+// slot is taken, share g_stage under the mutex.
+constexpr int kStageSlots = 16;
+constexpr int64_t kSlotTerms = 4096, kSlotBatch = 4;
+constexpr size_t kSlotScratch = 4u << 20;
+struct StagePool {
+    std::mutex mu;
+    Staging slots[kStageSlots];
+    bool busy[kStageSlots] = {};
+};
+StagePool g_pool;
+struct StageLease {
+    Staging* s = nullptr;
+    std::unique_lock<std::mutex> lk;   // held for the shared staging area only
+    int slot = -1;
+    bool local() const { return slot >= 0; }
+    StageLease() = default;
+    StageLease(StageLease&& o) noexcept : s(o.s), lk(std::move(o.lk)), slot(o.slot) { o.slot = -1; }
+    StageLease(const StageLease&) = delete;
+    ~StageLease() {
+        if (slot >= 0) {
+            std::lock_guard<std::mutex> g(g_pool.mu);
+            g_pool.busy[slot] = false;
+        }
+    }
+};
+StageLease lease_stage(int64_t n, int64_t nbatch) {
+    StageLease l;
+    if (n * nbatch <= kSlotTerms && nbatch <= kSlotBatch && !getenv("PORLA_SERIAL_CALLS")) {
+        std::lock_guard<std::mutex> g(g_pool.mu);
+        for (int i = 0; i < kStageSlots; i++) {
+            if (!g_pool.busy[i]) {
+                g_pool.busy[i] = true;
+                l.slot = i;
+                l.s = &g_pool.slots[i];
+                break;
+            }
+        }
+    }
+    if (l.slot < 0) {
+        l.s = &g_stage;
+        l.lk = std::unique_lock<std::mutex>(g_io_mu);
+    }
+    l.s->init();
+    return l;
+}
+
 // window_bits argument of the device entry points: a plain window size, or a plan code of porla_msm_plan
 void decode_plan(int code, MsmOptions* opt) {
     opt->window_bits = PORLA_PLAN_WINDOW(code);
@@ -113,7 +163,7 @@ size_t result_scratch_bytes(int curve, int64_t n, int64_t nbatch) {
     return a > b ? a : b;
 }
 void run_and_fetch(int curve, const PointTable& tab, const uint8_t* d_scalars, int64_t n, int64_t nbatch, MsmOptions opt,
-                   uint8_t* d_scratch_out, uint8_t* out, cudaStream_t st) {
+                   uint8_t* d_scratch_out, uint8_t* out, cudaStream_t st, Staging& sg = g_stage) {
     const char* force_dev = getenv("PORLA_DEVICE_FINALIZE");
     if (nbatch <= kHostFinalizeMaxBatch && !(force_dev && force_dev[0] == '1')) {
         MsmPlan p = msm_plan_table(tab, (uint32_t)n, (uint32_t)nbatch, opt);
@@ -121,14 +171,14 @@ void run_and_fetch(int curve, const PointTable& tab, const uint8_t* d_scalars, i
         opt.d_window_sums = d_scratch_out;
         size_t bytes = (size_t)nbatch * p.nwin * 128;
         msm_device(curve, tab, d_scalars, (uint32_t)n, (uint32_t)nbatch, opt, nullptr, nullptr, st);
-        uint8_t* h = g_stage.pinned(bytes);
+        uint8_t* h = sg.pinned(bytes);
         PORLA_CUDA(cudaMemcpyAsync(h, d_scratch_out, bytes, cudaMemcpyDeviceToHost, st));
         PORLA_CUDA(cudaStreamSynchronize(st));
         for (int64_t m = 0; m < nbatch; m++) finalize_host(curve, h + (size_t)m * p.nwin * 128, p.nwin, p.c, opt.out_fmt, out + 64 * m);
         return;
     }
     msm_device(curve, tab, d_scalars, (uint32_t)n, (uint32_t)nbatch, opt, d_scratch_out, nullptr, st);
-    uint8_t* h = g_stage.pinned((size_t)nbatch * 64);
+    uint8_t* h = sg.pinned((size_t)nbatch * 64);
     PORLA_CUDA(cudaMemcpyAsync(h, d_scratch_out, (size_t)nbatch * 64, cudaMemcpyDeviceToHost, st));
     PORLA_CUDA(cudaStreamSynchronize(st));
     memcpy(out, h, (size_t)nbatch * 64);
@@ -230,20 +280,20 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
         return;
     }
     device_init();
-    std::lock_guard<std::mutex> lock(g_io_mu);
-    g_stage.init();
+    StageLease lease = lease_stage(n, nbatch);
+    Staging& sg = *lease.s;
     if (nbatch == 1 && n >= (1 << 19) && !getenv("PORLA_NO_SPLIT")) {
         msm_host_split(curve, scalars, points, n, scalar_fmt, point_fmt, out);
         return;
     }
     const size_t total = (size_t)n * (size_t)nbatch;
-    // staging layout: scalars | raw points | imported table | infinity flags | result scratch
+    // staging layout: scalars | raw points | imported table + endomorphism image | infinity flags | result scratch | small-path scratch
     auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t sc_bytes = total * 32, pt_bytes = total * 64;
     size_t sc_off = 0, pt_off = pad(sc_bytes), tab_off = pt_off + pad(pt_bytes), fl_off = tab_off + pad(2 * pt_bytes),
-           out_off = fl_off + pad(total);
-    uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(curve, n, nbatch));
-    cudaStream_t st = g_stage.stream;
+           out_off = fl_off + pad(total), scr_off = out_off + pad(result_scratch_bytes(curve, n, nbatch));
+    uint8_t* d = sg.dev(scr_off + (lease.local() ? kSlotScratch : 0));
+    cudaStream_t st = sg.stream;
     PORLA_CUDA(cudaMemcpyAsync(d + sc_off, scalars, sc_bytes, cudaMemcpyHostToDevice, st));
     PORLA_CUDA(cudaMemcpyAsync(d + pt_off, points, pt_bytes, cudaMemcpyHostToDevice, st));
     PointTable tab;
@@ -252,37 +302,51 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.out_fmt = point_fmt;
     opt.shared_points = 0;
+    if (lease.local()) {
+        opt.d_scratch = d + scr_off;
+        opt.scratch_bytes = kSlotScratch;
+    }
     if (total <= 4096) opt.max_scalar_bits = host_max_scalar_bits(curve, scalars, total, opt.scalar_be);
-    run_and_fetch(curve, tab, d + sc_off, n, nbatch, opt, d + out_off, out, st);
+    run_and_fetch(curve, tab, d + sc_off, n, nbatch, opt, d + out_off, out, st, sg);
 }
 
 void upload_srs();
 
 // nbatch commitments over the resident SRS
 void srs_commit_core(const uint8_t* coeffs_be, int64_t n, int64_t nbatch, uint8_t* out) {
-    if (!g_kzg.have_table) {
-        if (g_kzg.srs_g1.empty()) die("SRS not initialised (call init_SRS or init_SRS_from_data first)");
-        upload_srs();
+    {
+        static std::mutex upload_mu;   // a first commitment may arrive from several pool threads at once
+        std::lock_guard<std::mutex> up(upload_mu);
+        if (!g_kzg.have_table) {
+            if (g_kzg.srs_g1.empty()) die("SRS not initialised (call init_SRS or init_SRS_from_data first)");
+            upload_srs();
+        }
     }
     if (n > (int64_t)g_kzg.srs_table.n) die("polynomial longer than the SRS");
     device_init();
-    std::lock_guard<std::mutex> lock(g_io_mu);
+    StageLease lease = lease_stage(n, nbatch);
+    Staging& sg = *lease.s;
     // a large batch over a mid-sized SRS (BASELINE config 3) is worth the one-time wide-window look-up table
     if ((uint64_t)n * (uint64_t)nbatch >= (1ull << 22) && g_kzg.srs_table.n > 2048 && g_kzg.srs_table.n <= 8192 &&
-        !g_kzg.srs_table.d_lut && !getenv("PORLA_NO_LUT")) {
-        table_precompute(&g_kzg.srs_table, 0, (uint32_t)n, (uint32_t)nbatch, g_stage.stream);
-        PORLA_CUDA(cudaStreamSynchronize(g_stage.stream));
+        !g_kzg.srs_table.d_lut && !getenv("PORLA_NO_LUT")) {   // (large call: the lease holds g_io_mu)
+        table_precompute(&g_kzg.srs_table, 0, (uint32_t)n, (uint32_t)nbatch, sg.stream);
+        PORLA_CUDA(cudaStreamSynchronize(sg.stream));
     }
+    auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t sc_bytes = (size_t)n * nbatch * 32;
-    size_t out_off = (sc_bytes + 255) & ~(size_t)255;
-    uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(kCurveBn254, n, nbatch));
-    cudaStream_t st = g_stage.stream;
+    size_t out_off = pad(sc_bytes), scr_off = out_off + pad(result_scratch_bytes(kCurveBn254, n, nbatch));
+    uint8_t* d = sg.dev(scr_off + (lease.local() ? kSlotScratch : 0));
+    cudaStream_t st = sg.stream;
     PORLA_CUDA(cudaMemcpyAsync(d, coeffs_be, sc_bytes, cudaMemcpyHostToDevice, st));
     MsmOptions opt;
     opt.scalar_be = 1;
     opt.out_fmt = PORLA_POINT_BE64;
     opt.shared_points = 1;
-    run_and_fetch(kCurveBn254, g_kzg.srs_table, d, n, nbatch, opt, d + out_off, out, st);
+    if (lease.local()) {
+        opt.d_scratch = d + scr_off;
+        opt.scratch_bytes = kSlotScratch;
+    }
+    run_and_fetch(kCurveBn254, g_kzg.srs_table, d, n, nbatch, opt, d + out_off, out, st, sg);
 }
 
 // SRS bases go to HBM once, at init when a device is present (otherwise on the first commit,
@@ -629,10 +693,12 @@ void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const voi
         return;
     }
     device_init();
-    std::lock_guard<std::mutex> lock(g_io_mu);
-    size_t sc_bytes = (size_t)n * 32, out_off = (sc_bytes + 255) & ~(size_t)255;
-    uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(t->t.curve, n, 1));
-    cudaStream_t st = g_stage.stream;
+    StageLease lease = lease_stage(n, 1);
+    Staging& sg = *lease.s;
+    auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t sc_bytes = (size_t)n * 32, out_off = pad(sc_bytes), scr_off = out_off + pad(result_scratch_bytes(t->t.curve, n, 1));
+    uint8_t* d = sg.dev(scr_off + (lease.local() ? kSlotScratch : 0));
+    cudaStream_t st = sg.stream;
     PORLA_CUDA(cudaMemcpyAsync(d, scalars, sc_bytes, cudaMemcpyHostToDevice, st));
     PointTable view = t->t;                       // a window [first, first + n) of the resident table
     view.d_points = (uint8_t*)t->t.d_points + (size_t)first * 64;
@@ -646,7 +712,11 @@ void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const voi
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.out_fmt = out_fmt;
     opt.shared_points = 1;
-    run_and_fetch(t->t.curve, view, d, n, 1, opt, d + out_off, (uint8_t*)out64, st);
+    if (lease.local()) {
+        opt.d_scratch = d + scr_off;
+        opt.scratch_bytes = kSlotScratch;
+    }
+    run_and_fetch(t->t.curve, view, d, n, 1, opt, d + out_off, (uint8_t*)out64, st, sg);
 }
 
 void porla_msm_plan(int curve, int64_t n, int64_t nbatch, int window_bits, int* c_out, int* nwin_out) {

@@ -75,6 +75,11 @@ struct MsmOptions {
     int max_scalar_bits = 0;
     int no_small = 0;         // always run the sort / accumulate / reduce pipeline
     int glv = -1;             // -1: decided by the plan; 0 / 1: forced (parts of one MSM must agree on the window layout)
+    // Caller-owned device scratch for the one-launch small paths: when it is large enough the call takes neither the
+    // engine's arena nor its mutex, so small MSMs issued from several host threads (Porla's pool of 8,
+    // Server.hpp:1077-1078) run concurrently on their own streams.
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
 };
 
 enum PlanMode : int { kPlanPipeline = 0, kPlanBits = 1, kPlanLut = 2 };

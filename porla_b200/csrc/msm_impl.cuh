@@ -111,14 +111,27 @@ void msm_small_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t 
         nblk = (n + 2 * kTreeThreads - 1) / (2 * kTreeThreads);
     }
     if (!nblk) nblk = 1;
-    std::lock_guard<std::mutex> lock(g_engine_mu);
     const size_t need = Arena::padded((size_t)slots * nblk, sizeof(XYZZ<F>)) + Arena::padded(slots, 4) +
                         Arena::padded(slots, sizeof(XYZZ<F>)) + 1024;
-    g_arena.reserve(need, stream);
-    g_arena.reset();
-    XYZZ<F>* partials = g_arena.take<XYZZ<F>>((size_t)slots * nblk);
-    uint32_t* tickets = g_arena.take<uint32_t>(slots);
-    XYZZ<F>* wsum = g_arena.take<XYZZ<F>>(slots);
+    std::unique_lock<std::mutex> lock(g_engine_mu, std::defer_lock);
+    XYZZ<F>* partials;
+    uint32_t* tickets;
+    XYZZ<F>* wsum;
+    if (opt.d_scratch && need <= opt.scratch_bytes) {   // caller's scratch: no shared state, no lock
+        uint8_t* b = reinterpret_cast<uint8_t*>(opt.d_scratch);
+        partials = reinterpret_cast<XYZZ<F>*>(b);
+        b += Arena::padded((size_t)slots * nblk, sizeof(XYZZ<F>));
+        tickets = reinterpret_cast<uint32_t*>(b);
+        b += Arena::padded(slots, 4);
+        wsum = reinterpret_cast<XYZZ<F>*>(b);
+    } else {
+        lock.lock();
+        g_arena.reserve(need, stream);
+        g_arena.reset();
+        partials = g_arena.take<XYZZ<F>>((size_t)slots * nblk);
+        tickets = g_arena.take<uint32_t>(slots);
+        wsum = g_arena.take<XYZZ<F>>(slots);
+    }
     for (int st = kStageCount; st <= kStageAccumulate; st++) g_stage_timer.mark(st, stream);
     if (nblk > 1) PORLA_CUDA(cudaMemsetAsync(tickets, 0, (size_t)slots * 4, stream));
     if (lut) {

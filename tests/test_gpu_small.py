@@ -305,3 +305,44 @@ def test_wide_window_lookup_table_for_large_batches(monkeypatch):
         assert bytes(fixed[64 * m:64 * m + 64].cpu().numpy().tobytes()) == enc(want), m
     assert tab.msm_resident(d_sc.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32) == bytes(fixed[:64].cpu().numpy().tobytes())
     tab.destroy()
+
+
+def test_more_concurrent_callers_than_staging_slots():
+    """24 host threads of short-lived pools (Porla builds a ThreadPool inside align_MAC, Server.hpp:487) issue small
+    commitments, audit-sized MSMs and secp256k1 generator sub-range MSMs at once: 16 lease a staging slot, the rest
+    fall back to the shared staging area; every result equals the sequential one and the oracle."""
+    import threading
+    n = 128
+    k = pb.Kzg(TAU, ALPHA)
+    srs = _srs_points(k.init_srs(n), n)
+    srs_bytes = b"".join(O.bn254_marshal(P) for P in srs)
+    rnd = random.Random(2424)
+    T = 24
+    blocks = [b"".join(be(rnd.randrange(1 << 256)) for _ in range(n)) for _ in range(T)]
+    pts = b"".join(map(enc, chain(BN, 200, 9)))
+    scs = [b"".join(pb.bn254_scalar_set_int(rnd.randrange(1 << 31)) for _ in range(200)) for _ in range(T)]
+    want_c = [loader.bn254_msm(b, srs_bytes, n, 1) for b in blocks]
+    want_m = [loader.bn254_msm(s, pts, 200, 1) for s in scs]
+    gens_pts = chain(SE, 64, 77)
+    gens = pb.SecpGenerators(gens_pts)
+    sec_sc = [[rnd.randrange(SE.n) for _ in range(16)] for _ in range(T)]
+    want_s = [O.msm(SE, sc, gens_pts[16 * (t % 4):16 * (t % 4) + 16]) for t, sc in enumerate(sec_sc)]
+    errors = []
+
+    def worker(t):
+        for _ in range(3):                                   # three generations of fresh threads
+            def body():
+                if k.compute_digest_from_srs(blocks[t]) != want_c[t]:
+                    errors.append(("commit", t))
+                if pb.bn254_multi_exp(pts, scs[t], 200) != want_m[t]:
+                    errors.append(("msm", t))
+                if gens.multi(16 * (t % 4), sec_sc[t]) != (1, want_s[t]):
+                    errors.append(("secp", t))
+            inner = threading.Thread(target=body)
+            inner.start()
+            inner.join()
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    gens.destroy()
+    assert not errors, errors[:6]
