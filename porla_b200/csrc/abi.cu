@@ -29,6 +29,7 @@ struct KzgState {
     int64_t n_samples = 0;
     std::vector<G1A> srs_g1;        // host copy (internal form)
     G2A g2[2];                      // [1]G2, [tau]G2
+    G2Lines g2_lines[2];            // their Miller-loop lines, precomputed once per SRS (verify_proof)
     bool have_g2 = false;
     G1A h_mac = G1A::inf();
     PointTable srs_table;           // resident in HBM
@@ -391,6 +392,7 @@ void init_SRS(GoInt SRS_size, GoSlice* out, GoInt64* out_len) {
     }
     g_kzg.g2[0] = g2_generator();
     g_kzg.g2[1] = g2_mul(g_kzg.g2[0], g_kzg.tau);
+    for (int i = 0; i < 2; i++) g_kzg.g2_lines[i] = g2_precompute_lines(g_kzg.g2[i]);
     g_kzg.have_g2 = true;
     // SRS.WriteTo: compressed encoder over &G2[0], &G2[1], G1 (uint32 BE length prefix)
     std::vector<uint8_t> blob(128 + 4 + (size_t)SRS_size * 32);
@@ -422,6 +424,7 @@ void init_SRS_from_data(GoInt SRS_size, GoSlice* in) {
     if (in->len < 132) die("init_SRS_from_data: blob too short");
     g_kzg.n_samples = SRS_size;
     if (!g2_decompress(b, &g_kzg.g2[0]) || !g2_decompress(b + 64, &g_kzg.g2[1])) die("init_SRS_from_data: bad G2 point");
+    for (int i = 0; i < 2; i++) g_kzg.g2_lines[i] = g2_precompute_lines(g_kzg.g2[i]);
     g_kzg.have_g2 = true;
     uint32_t cnt = ((uint32_t)b[128] << 24) | ((uint32_t)b[129] << 16) | ((uint32_t)b[130] << 8) | b[131];
     if ((GoInt)in->len < 132 + (GoInt)cnt * 32) die("init_SRS_from_data: blob truncated");
@@ -511,7 +514,9 @@ GoUint8 verify_proof(GoSlice* commitment_in, GoSlice* proof_H, GoSlice* proof_po
     G1A lhs = g1_add(g1_add(c, yg.neg()), g1_mul(hq, z));
     G1A ps[2] = {lhs, hq.neg()};
     G2A qs[2] = {g_kzg.g2[0], g_kzg.g2[1]};
-    if (!pairing_product_is_one(ps, qs, 2)) {
+    const G2Lines* ls[2] = {&g_kzg.g2_lines[0], &g_kzg.g2_lines[1]};
+    const bool fixed = ls[0]->valid && ls[1]->valid && !getenv("PORLA_PAIRING_GENERIC");
+    if (!(fixed ? pairing_product_is_one_fixed(ps, ls, 2) : pairing_product_is_one(ps, qs, 2))) {
         printf("Verifying is wrong\n");
         return 0;
     }
@@ -893,6 +898,13 @@ int porla_debug_pairing_selfcheck(int rounds) {
             bool chain2 = hard_part_chain(c2).is_one(), plain2 = hard_part_plain(c2).is_one();
             bool expect = wrong == 0;
             if (chain1 != expect || plain1 != expect || chain2 != expect || plain2 != expect) bad++;
+            // the fixed-argument loop (precomputed lines of qb and g2) must give the very same Fp12 value
+            G2Lines la = g2_precompute_lines(qb), lb = g2_precompute_lines(g2);
+            const G2Lines* ls[2] = {&la, &lb};
+            Fq12 mf = miller_loop_fixed(ps, ls, 2);
+            bool same = la.valid && lb.valid;
+            for (int k = 0; k < 6 && same; k++) same = mf.c[k] == m.c[k];
+            if (!same) bad++;
         }
     }
     return bad;

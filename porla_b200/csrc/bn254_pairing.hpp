@@ -7,6 +7,7 @@
 // Tower: Fp2 = Fp[i]/(i^2+1), Fp12 = Fp2[w]/(w^6 - xi), xi = 9 + i.  Twist E': y^2 = x^3 + 3/xi,
 // untwist (x', y') -> (x' w^2, y' w^3).
 #pragma once
+#include <vector>
 #include "host_bn254.hpp"
 
 namespace porla {
@@ -429,6 +430,97 @@ inline Fq12 miller_loop_multi(const G1A* ps, const G2A* qs, int n) {
 
 inline Fq12 miller_loop(const G1A& p, const G2A& q) { return miller_loop_multi(&p, &q, 1); }
 
+// ---------------------------------------------------------------------------- fixed second arguments
+// kzg.Verify pairs against the two G2 points of the SRS, [1]G2 and [tau]G2, in every call.  Everything the Miller
+// loop does on the G2 side (tangent / chord slopes, the Fp2 inversions, the point updates) depends on Q alone, so
+// it is done once per SRS: per step the slope lam and the constant lam * x_T - y_T.  A pairing evaluation then
+// costs one line evaluation (two Fp products), one sparse Fp12 product per step and pair, and the squarings.
+struct G2Lines {
+    std::vector<Fq2> lam, c3;
+    bool valid = false;
+};
+inline G2Lines g2_precompute_lines(const G2A& q) {
+    G2Lines out;
+    if (q.inf) return out;
+    const PairingConsts& pc = pairing_consts();
+    G2A q1, q2, t = q;
+    q1.x = q.x.conj() * pc.g2;
+    q1.y = q.y.conj() * pc.g3;
+    q1.inf = false;
+    q2.x = q.x.scale(pc.n[2]);
+    q2.y = q.y.scale(pc.n[3]).neg();
+    q2.inf = false;
+    auto step = [&](bool doubling, const G2A& addend) {
+        Fq2 den = doubling ? t.y.dbl() : addend.x - t.x;
+        if (den.is_zero()) return false;                  // impossible for points of prime order r
+        Fq2 lam;
+        if (doubling) {
+            Fq2 xx = t.x.sqr();
+            lam = (xx.dbl() + xx) * den.inverse();
+        } else {
+            lam = (addend.y - t.y) * den.inverse();
+        }
+        out.lam.push_back(lam);
+        out.c3.push_back(lam * t.x - t.y);
+        const Fq2& ox = doubling ? t.x : addend.x;
+        G2A r;
+        r.x = lam.sqr() - t.x - ox;
+        r.y = lam * (t.x - r.x) - t.y;
+        r.inf = false;
+        t = r;
+        return true;
+    };
+    const uint64_t lo = 0x9d797039be763ba8ull;
+    bool ok = true;
+    for (int i = 63; i >= 0 && ok; i--) {
+        ok = step(true, q);
+        if (ok && ((lo >> i) & 1ull)) ok = step(false, q);
+    }
+    ok = ok && step(false, q1) && step(false, q2);
+    out.valid = ok;
+    return out;
+}
+
+// f *= yp + b w + c w^3  (w^6 = xi): twelve Fp2 products and six scalings instead of a dense product
+inline void fq12_mul_line(Fq12& f, const Fq& yp, const Fq2& b, const Fq2& c) {
+    const Fq2 f5x = f.c[5].mul_xi(), f3x = f.c[3].mul_xi(), f4x = f.c[4].mul_xi();
+    Fq12 r;
+    r.c[0] = f.c[0].scale(yp) + b * f5x + c * f3x;
+    r.c[1] = f.c[1].scale(yp) + b * f.c[0] + c * f4x;
+    r.c[2] = f.c[2].scale(yp) + b * f.c[1] + c * f5x;
+    r.c[3] = f.c[3].scale(yp) + b * f.c[2] + c * f.c[0];
+    r.c[4] = f.c[4].scale(yp) + b * f.c[3] + c * f.c[1];
+    r.c[5] = f.c[5].scale(yp) + b * f.c[4] + c * f.c[2];
+    f = r;
+}
+
+// Product of the Miller loops of (ps[i], Q_i) for precomputed Q_i; pairs with an infinite first argument contribute 1.
+inline Fq12 miller_loop_fixed(const G1A* ps, const G2Lines* const* lines, int n) {
+    Fq2 negx[4];
+    bool live[4];
+    if (n > 4) n = 4;
+    for (int i = 0; i < n; i++) {
+        live[i] = !ps[i].is_inf() && lines[i]->valid;
+        negx[i] = Fq2{ps[i].x.neg(), Fq::zero()};
+    }
+    const uint64_t lo = 0x9d797039be763ba8ull;
+    Fq12 f = Fq12::one();
+    size_t k = 0;
+    auto apply = [&]() {
+        for (int i = 0; i < n; i++)
+            if (live[i]) fq12_mul_line(f, ps[i].y, lines[i]->lam[k].scale(negx[i].a0), lines[i]->c3[k]);
+        k++;
+    };
+    for (int i = 63; i >= 0; i--) {
+        f = f.sqr();
+        apply();
+        if ((lo >> i) & 1ull) apply();
+    }
+    apply();
+    apply();
+    return f;
+}
+
 inline Fq12 fq12_pow_u(const Fq12& a) {   // u = 4965661367192848881 (BN254 curve parameter, 63 bits)
     const uint64_t u = 4965661367192848881ull;
     Fq12 r = a;
@@ -485,6 +577,9 @@ inline Fq12 final_exponentiation(const Fq12& f) {
 
 inline bool pairing_product_is_one(const G1A* ps, const G2A* qs, int n) {
     return final_exponentiation(miller_loop_multi(ps, qs, n)).is_one();
+}
+inline bool pairing_product_is_one_fixed(const G1A* ps, const G2Lines* const* lines, int n) {
+    return final_exponentiation(miller_loop_fixed(ps, lines, n)).is_one();
 }
 
 }  // namespace host
