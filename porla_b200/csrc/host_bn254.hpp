@@ -180,24 +180,104 @@ inline G1A g1_add(const G1A& a, const G1A& b) {
     r.madd(b);
     return r.to_affine();
 }
-// k * p, k an Fr element (internal form): fixed 4-bit windows over the canonical scalar, leading
-// zero windows skipped (audit coefficients are 31-bit, utils.h:271-275).
+// out = a * b mod 2^(32*no) on 32-bit limbs (host twin of mul_limbs in msm_kernels.cuh)
+inline void mul_limbs_host(const uint32_t* a, int na, const uint32_t* b, int nb, uint32_t* out, int no) {
+    for (int i = 0; i < no; i++) out[i] = 0;
+    for (int i = 0; i < na; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < nb && i + j < no; j++) {
+            uint64_t v = (uint64_t)a[i] * b[j] + out[i + j] + carry;
+            out[i + j] = (uint32_t)v;
+            carry = v >> 32;
+        }
+        if (i + nb < no) out[i + nb] = (uint32_t)carry;
+    }
+}
+// k (canonical, < r) -> |k1|, |k2| < 2^127 and their signs with k = k1 + k2 * lambda mod r: the device routine
+// glv_split (msm_kernels.cuh) on the host, same constants (Bn254::glv_*, pinned in tests/test_oracle.py).
+inline void glv_split_host(const uint32_t* k, uint32_t* k1, uint32_t* k2, bool* neg1, bool* neg2) {
+    uint32_t g1[3], g2[5], a1[2], a2[4], nb1[4];
+    for (int i = 0; i < 3; i++) g1[i] = Bn254::glv_g1(i);
+    for (int i = 0; i < 5; i++) g2[i] = Bn254::glv_g2(i);
+    for (int i = 0; i < 2; i++) a1[i] = Bn254::glv_a1(i);
+    for (int i = 0; i < 4; i++) {
+        a2[i] = Bn254::glv_a2(i);
+        nb1[i] = Bn254::glv_nb1(i);
+    }
+    uint32_t t1[11], t2[13], p1[6], p2[6], q1[6], q2[6], v1[6], v2[6];
+    mul_limbs_host(k, 8, g1, 3, t1, 11);
+    mul_limbs_host(k, 8, g2, 5, t2, 13);
+    const uint32_t *c1 = t1 + 8, *c2 = t2 + 8;
+    mul_limbs_host(c1, 2, a1, 2, p1, 6);
+    mul_limbs_host(c2, 4, a2, 4, p2, 6);
+    mul_limbs_host(c1, 2, nb1, 4, q1, 6);
+    mul_limbs_host(c2, 4, a1, 2, q2, 6);
+    uint32_t b1 = 0, b2 = 0, b3 = 0;
+    for (int i = 0; i < 6; i++) {
+        uint64_t d = (uint64_t)k[i] - p1[i] - b1;
+        b1 = (uint32_t)(d >> 63);
+        uint64_t e = (uint64_t)(uint32_t)d - p2[i] - b2;
+        b2 = (uint32_t)(e >> 63);
+        v1[i] = (uint32_t)e;
+        uint64_t f = (uint64_t)q1[i] - q2[i] - b3;
+        b3 = (uint32_t)(f >> 63);
+        v2[i] = (uint32_t)f;
+    }
+    *neg1 = (v1[5] >> 31) != 0;
+    *neg2 = (v2[5] >> 31) != 0;
+    uint32_t cy1 = *neg1 ? 1u : 0u, cy2 = *neg2 ? 1u : 0u;
+    for (int i = 0; i < 6; i++) {
+        uint64_t x = (uint64_t)(*neg1 ? ~v1[i] : v1[i]) + cy1;
+        v1[i] = (uint32_t)x;
+        cy1 = (uint32_t)(x >> 32);
+        uint64_t y = (uint64_t)(*neg2 ? ~v2[i] : v2[i]) + cy2;
+        v2[i] = (uint32_t)y;
+        cy2 = (uint32_t)(y >> 32);
+    }
+    for (int i = 0; i < 4; i++) {
+        k1[i] = v1[i];
+        k2[i] = v2[i];
+    }
+}
+
+// k * p, k an Fr element (internal form).  GLV: k = k1 + k2 lambda, phi(p) = (beta x, y) = lambda p, then joint
+// 2 + 2-bit windows over (k1, k2): 15 precomputed combinations i p + j phi(p), 64 steps of two doublings and at
+// most one addition -- 128 doublings instead of 252 (mult_point is called O(n log n) times per rebuild by an
+// unchanged Porla, Server.hpp:1548-1687).  Short scalars (31-bit audit coefficients, utils.h:271-275) skip the
+// leading zero windows.
 inline G1A g1_mul(const G1A& p, const Fr& k_internal) {
     Fr k = k_internal.from_internal();
     if (p.is_inf() || k.is_zero()) return G1A::inf();
+    uint32_t k1[4], k2[4];
+    bool n1, n2;
+    glv_split_host(k.v, k1, k2, &n1, &n2);
+    G1A p1 = p, p2 = p;
+    Fq beta;
+    for (int i = 0; i < 4; i++) beta.v[i] = (uint64_t)Bn254::glv_beta_mont(2 * i) | ((uint64_t)Bn254::glv_beta_mont(2 * i + 1) << 32);
+    p2.x = p.x * beta;
+    if (n1) p1.y = p1.y.neg();
+    if (n2) p2.y = p2.y.neg();
+    // tab[4 j + i] = i p1 + j p2
     G1X tab[16];
     tab[0] = G1X::inf();
-    tab[1] = G1X::from_affine(p);
-    for (int i = 2; i < 16; i++) {
+    for (int i = 1; i < 4; i++) {
         tab[i] = tab[i - 1];
-        tab[i].madd(p);
+        tab[i].madd(p1);
     }
+    for (int j = 1; j < 4; j++)
+        for (int i = 0; i < 4; i++) {
+            tab[4 * j + i] = tab[4 * (j - 1) + i];
+            tab[4 * j + i].madd(p2);
+        }
+    auto digit = [&](int w) {   // 2 bits of k1 and of k2 at bit 2w
+        return ((k1[w >> 4] >> (2 * (w & 15))) & 3u) | (((k2[w >> 4] >> (2 * (w & 15))) & 3u) << 2);
+    };
     int top = 63;
-    while (top > 0 && ((k.v[top >> 3] >> (4 * (top & 7))) & 15u) == 0) top--;
-    G1X r = tab[(k.v[top >> 3] >> (4 * (top & 7))) & 15u];
-    for (int i = top - 1; i >= 0; i--) {
-        r = r.dbl().dbl().dbl().dbl();
-        uint32_t d = (k.v[i >> 3] >> (4 * (i & 7))) & 15u;
+    while (top > 0 && digit(top) == 0) top--;
+    G1X r = tab[digit(top)];
+    for (int w = top - 1; w >= 0; w--) {
+        r = r.dbl().dbl();
+        uint32_t d = digit(w);
         if (d) r.add(tab[d]);
     }
     return r.to_affine();

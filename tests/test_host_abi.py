@@ -116,3 +116,25 @@ def test_msm_plan_codes_carry_the_window_layout():
     assert c.value == 20 | 0x200 and nwin.value == 13
     lib.porla_msm_plan(pb.CURVE_SECP256K1, 1 << 18, 1, 0, C.byref(c), C.byref(nwin))
     assert c.value == 16 | 0x200 and nwin.value == 16
+
+
+def test_mult_point_glv_corners():
+    """mult_point (main.go:205-214) runs a GLV joint double-and-add on the host: corners of the scalar split, short
+    audit coefficients, unreduced scalars, negated halves, the point at infinity."""
+    import random
+    import porla_b200 as pb
+    from oracle import curves_py as O
+    BN = O.BN254
+    g = O.glv_constants(BN)
+    lam = g["lambda"]
+    rnd = random.Random(205)
+    P = O.hash_point(BN, 11)
+    ks = [0, 1, 2, 3, BN.n - 1, BN.n, BN.n + 7, lam, lam - 1, lam + 1, BN.n - lam, g["a2"], -g["b1"], (1 << 127) - 1, 1 << 127,
+          (1 << 31) - 1, (1 << 256) - 1, BN.n // 2, BN.n // 2 + 1] + [rnd.randrange(1 << 256) for _ in range(40)]
+    for k in ks:
+        buf = bytearray(O.bn254_marshal(P))
+        pb.bn254_mult(buf, k.to_bytes(32, "big"))
+        assert bytes(buf) == O.bn254_marshal(O.mul(BN, k % BN.n, P)), hex(k)
+    buf = bytearray(64)
+    pb.bn254_mult(buf, (12345).to_bytes(32, "big"))
+    assert bytes(buf) == bytes(64)
