@@ -297,8 +297,6 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
     cudaStream_t st = sg.stream;
     PORLA_CUDA(cudaMemcpyAsync(d + sc_off, scalars, sc_bytes, cudaMemcpyHostToDevice, st));
     PORLA_CUDA(cudaMemcpyAsync(d + pt_off, points, pt_bytes, cudaMemcpyHostToDevice, st));
-    PointTable tab;
-    table_import_into(curve, d + pt_off, point_fmt, (uint32_t)total, d + tab_off, d + fl_off, &tab, st);
     MsmOptions opt;
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.out_fmt = point_fmt;
@@ -308,6 +306,11 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
         opt.scratch_bytes = kSlotScratch;
     }
     if (total <= 4096) opt.max_scalar_bits = host_max_scalar_bits(curve, scalars, total, opt.scalar_be);
+    PointTable tab;
+    tab.curve = curve;
+    // the one-launch tree sum does not use the endomorphism image: skip that launch for Porla-sized calls
+    const bool bits_plan = msm_plan_table(tab, (uint32_t)n, (uint32_t)nbatch, opt).mode == kPlanBits;
+    table_import_into(curve, d + pt_off, point_fmt, (uint32_t)total, d + tab_off, d + fl_off, &tab, st, !bits_plan);
     run_and_fetch(curve, tab, d + sc_off, n, nbatch, opt, d + out_off, out, st, sg);
 }
 

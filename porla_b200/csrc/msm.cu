@@ -82,7 +82,7 @@ int stage_timing_read(float* ms_out) {
 }
 
 template <class C> void import_impl(const uint8_t*, int, uint32_t, PointTable*, cudaStream_t);
-template <class C> void import_into_impl(const uint8_t*, int, uint32_t, void*, uint8_t*, cudaStream_t);
+template <class C> void import_into_impl(const uint8_t*, int, uint32_t, void*, uint8_t*, cudaStream_t, bool);
 template <class C> void msm_impl(const PointTable&, const uint8_t*, uint32_t, uint32_t, const MsmOptions&, uint8_t*, void*, cudaStream_t);
 template <class C> void precompute_impl(PointTable*, int, cudaStream_t);
 template <class C> void lut_impl(PointTable*, cudaStream_t);
@@ -337,15 +337,15 @@ void table_import_host(int curve, const uint8_t* h_bytes, int fmt, uint32_t n, P
 }
 
 void table_import_into(int curve, const uint8_t* d_bytes, int fmt, uint32_t n, void* d_points_out, uint8_t* d_flags_out,
-                       PointTable* out, cudaStream_t stream) {
+                       PointTable* out, cudaStream_t stream, bool with_phi) {
     device_init();
-    DISPATCH(curve, import_into_impl, d_bytes, fmt, n, d_points_out, d_flags_out, stream);
+    DISPATCH(curve, import_into_impl, d_bytes, fmt, n, d_points_out, d_flags_out, stream, with_phi);
     out->d_points = d_points_out;
     out->d_flags = d_flags_out;
     out->n = n;
     out->n_inf = 0;  // unknown (not counted on this path); the flags are always consulted
     out->curve = curve;
-    out->phi_off = curve == kCurveBn254 && Bn254::kGlv ? n : 0u;
+    out->phi_off = with_phi && curve == kCurveBn254 && Bn254::kGlv ? n : 0u;
 }
 
 void table_free(PointTable* t) {

@@ -59,7 +59,7 @@ int choose_window_fixed_base(int curve, uint32_t n, uint32_t nbatch);
 // Import into caller-provided device buffers (2*n*64 B points: the table and its endomorphism image, n B flags):
 // no allocation, no sync.  The returned table borrows the buffers (do not table_free it).
 void table_import_into(int curve, const uint8_t* d_bytes, int point_fmt, uint32_t n, void* d_points_out,
-                       uint8_t* d_flags_out, PointTable* out, cudaStream_t stream);
+                       uint8_t* d_flags_out, PointTable* out, cudaStream_t stream, bool with_phi = true);
 
 struct MsmOptions {
     int window_bits = 0;      // 0 = choose from n

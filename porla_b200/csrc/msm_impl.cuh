@@ -28,7 +28,7 @@ template <> struct CurveIdOf<Secp256k1> { static constexpr int value = kCurveSec
 // ---------------------------------------------------------------------------- tables
 template <class C>
 void import_into_impl(const uint8_t* d_bytes, int fmt, uint32_t n, void* d_points_out, uint8_t* d_flags_out,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, bool with_phi) {
     using F = typename C::F;
     if (!n) return;
     int mask = C::F::Params::kMontgomery ? 1 : 0;
@@ -36,9 +36,11 @@ void import_into_impl(const uint8_t* d_bytes, int fmt, uint32_t n, void* d_point
                                                            d_flags_out, nullptr);
     LAUNCHED();
     if constexpr (C::kGlv) {   // the endomorphism image right behind the table (PointTable::phi_off = n)
-        k_phi_table<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<F>*>(d_points_out), n,
-                                                           reinterpret_cast<Affine<F>*>(d_points_out) + n);
-        LAUNCHED();
+        if (with_phi) {
+            k_phi_table<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<F>*>(d_points_out), n,
+                                                               reinterpret_cast<Affine<F>*>(d_points_out) + n);
+            LAUNCHED();
+        }
     }
     PORLA_CUDA(cudaGetLastError());
 }
@@ -528,7 +530,7 @@ void field_mul_impl(const void* d_a, const void* d_b, uint32_t n, int op, void* 
 
 #define PORLA_INSTANTIATE_CURVE(C)                                                                                     \
     template void import_impl<C>(const uint8_t*, int, uint32_t, PointTable*, cudaStream_t);                            \
-    template void import_into_impl<C>(const uint8_t*, int, uint32_t, void*, uint8_t*, cudaStream_t);                   \
+    template void import_into_impl<C>(const uint8_t*, int, uint32_t, void*, uint8_t*, cudaStream_t, bool);             \
     template void msm_impl<C>(const PointTable&, const uint8_t*, uint32_t, uint32_t, const MsmOptions&, uint8_t*,      \
                               void*, cudaStream_t);                                                                    \
     template void combine_impl<C>(const void*, uint32_t, uint32_t, int, uint8_t*, cudaStream_t);                       \
