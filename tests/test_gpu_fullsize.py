@@ -68,3 +68,32 @@ def test_closed_form_at_full_size(curve, log2n):
         lib.compute_multi_exp(C.byref(gs[0]), C.byref(gs[1]), n, C.byref(gs[2]))
         assert bytes(out) == want
     tab.destroy()
+
+
+def test_config3_shape_lookup_table_batch(monkeypatch):
+    """BASELINE config 3 in shape (4096 bases shared by a batch of commitments; 512 of the 4096 MSMs to keep the run
+    short): the wide-window look-up table (here under an 8 GB budget: c = 11, 6.4 GB) with several scalars per thread
+    and four blocks per MSM against the general batched path for every MSM, and the closed form for a few."""
+    import torch
+    monkeypatch.setenv("PORLA_LUT_BUDGET_GB", "8")
+    n, nb = 1 << 12, 512
+    rnd = random.Random(3)
+    ks = torch.zeros((n, 8), dtype=torch.int32, device="cuda")
+    ks[:, 0] = torch.arange(1, n + 1, dtype=torch.int64, device="cuda").to(torch.int32)
+    tab = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks.data_ptr(), n, pb.SCALAR_LE32, on_device=True)
+    coef = [(rnd.getrandbits(240) | 1, rnd.getrandbits(255)) for _ in range(nb)]
+    ss = torch.cat([_affine_scalars(torch, n, a, b) for a, b in coef])          # MSM m: s_i = a_m i + b_m
+    general = torch.zeros(64 * nb, dtype=torch.uint8, device="cuda")
+    tab.msm_device(ss.data_ptr(), n, general.data_ptr(), nbatch=nb, scalar_fmt=pb.SCALAR_LE32, shared_points=True)
+    torch.cuda.synchronize()
+    c = tab.precompute(0, n, 4096)
+    assert c == 11
+    fixed = torch.zeros(64 * nb, dtype=torch.uint8, device="cuda")
+    tab.msm_device(ss.data_ptr(), n, fixed.data_ptr(), nbatch=nb, scalar_fmt=pb.SCALAR_LE32, shared_points=True)
+    torch.cuda.synchronize()
+    assert torch.equal(fixed, general)
+    for m in (0, 1, nb // 2, nb - 1):
+        a, b = coef[m]
+        total = (a * ((n - 1) * n * (n + 1) // 3) + b * (n * (n + 1) // 2)) % BN.n
+        assert bytes(fixed[64 * m:64 * m + 64].cpu().numpy().tobytes()) == O.bn254_marshal(O.mul(BN, total, (1, 2))), m
+    tab.destroy()
