@@ -39,6 +39,22 @@ struct Arena {
         return p;
     }
     static size_t padded(size_t count, size_t elt) { return (count * elt + 255) & ~(size_t)255; }
+
+    // The block is shared by consecutive calls; a call on ANOTHER stream must not start before the previous user's
+    // kernels have finished with it.  acquire() at the start of a call (engine mutex held), release() after its last
+    // launch.
+    cudaEvent_t done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool in_use = false;
+    void acquire(cudaStream_t stream) {
+        if (in_use && stream != last_stream) PORLA_CUDA(cudaStreamWaitEvent(stream, done, 0));
+    }
+    void release(cudaStream_t stream) {
+        if (!done) PORLA_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        PORLA_CUDA(cudaEventRecord(done, stream));
+        last_stream = stream;
+        in_use = true;
+    }
 };
 
 // Optional per-stage CUDA-event timing of the most recent MSM (bench.py's live roofline figure).

@@ -128,6 +128,7 @@ void msm_small_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t 
         wsum = reinterpret_cast<XYZZ<F>*>(b);
     } else {
         lock.lock();
+        g_arena.acquire(stream);
         g_arena.reserve(need, stream);
         g_arena.reset();
         partials = g_arena.take<XYZZ<F>>((size_t)slots * nblk);
@@ -157,6 +158,7 @@ void msm_small_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t 
         LAUNCHED();
     }
     g_stage_timer.mark(kNumStages, stream);
+    if (lock.owns_lock()) g_arena.release(stream);
     PORLA_CUDA(cudaGetLastError());
 }
 
@@ -255,6 +257,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
                   Arena::padded(pairs_cap, 8) + Arena::padded(nbt, sizeof(XYZZ<F>)) +
                   2 * Arena::padded(nslices_cap, sizeof(XYZZ<F>)) + Arena::padded(long_cap, 8) +
                   Arena::padded(slots * blocks_per_slot, sizeof(XYZZ<F>)) + Arena::padded(slots, sizeof(XYZZ<F>));
+    g_arena.acquire(stream);
     g_arena.reserve(need, stream);
     g_arena.reset();
     uint32_t* counters = g_arena.take<uint32_t>(nbt);
@@ -400,6 +403,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         LAUNCHED();
     }
     g_stage_timer.mark(kNumStages, stream);
+    g_arena.release(stream);
     PORLA_CUDA(cudaGetLastError());
 }
 

@@ -346,3 +346,30 @@ def test_more_concurrent_callers_than_staging_slots():
     [x.join() for x in th]
     gens.destroy()
     assert not errors, errors[:6]
+
+
+def test_device_entry_on_alternating_streams():
+    """porla_msm_device is asynchronous and all calls share one scratch arena: launches issued back to back on two
+    different streams must not overlap on it (the engine orders them with an event)."""
+    import torch
+    n = 1 << 15
+    g = torch.Generator(device="cuda")
+    g.manual_seed(515)
+    ks = torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda", generator=g)
+    tab = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks.data_ptr(), n, pb.SCALAR_LE32, on_device=True)
+    scs = [torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda", generator=g) for _ in range(6)]
+    ref = []
+    for s in scs:
+        o = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        tab.msm_device(s.data_ptr(), n, o.data_ptr(), scalar_fmt=pb.SCALAR_LE32)
+        torch.cuda.synchronize()
+        ref.append(o.clone())
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    outs = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in scs]
+    for i, s in enumerate(scs):                                  # no synchronisation between the calls
+        tab.msm_device(s.data_ptr(), n, outs[i].data_ptr(), scalar_fmt=pb.SCALAR_LE32, stream=streams[i % 2].cuda_stream)
+    torch.cuda.synchronize()
+    for i in range(len(scs)):
+        assert torch.equal(outs[i], ref[i]), i
+    tab.destroy()
