@@ -456,6 +456,29 @@ def run_ours(args):
                                   "whole_msm_frac_of_imad_peak": n2 * MAC32_PER_POINT / (ms2 * 1e-3) / p_int}
             t2.destroy()
 
+    # ---- the same MSM when the resident table is treated as a fixed base (an SRS): its window expansion 2^(20 w) P_i is
+    # built once (13 x 64 MiB), all windows then share one bucket set and 13 instead of 16 windows are enough.  Reported
+    # beside the headline, which keeps the general path (arbitrary points, nothing precomputed from them).
+    fixed_base = None
+    if world == 1 and args.log2n == 20:
+        try:
+            step(table, scalars, n, 0)
+            barrier()
+            ref_out = bytes(out_host)                       # general path, scalar set 0
+            t0 = time.perf_counter()
+            cfb = table.precompute(20, n, 1)
+            torch.cuda.synchronize()
+            t_pre = time.perf_counter() - t0
+            ms_fb, _, _ = timed(table, scalars, n, max(3, min(args.steps, 10)), 3)
+            step(table, scalars, n, 0)
+            barrier()
+            if bytes(out_host) != ref_out:
+                raise SystemExit("bench self-check failed: fixed-base and general results differ")
+            fixed_base = {"window_bits": cfb, "ms_per_step": ms_fb, "points_per_s": n / (ms_fb * 1e-3), "precompute_ms_once": t_pre * 1e3,
+                          "table_bytes": 13 * n * 64}
+        except Exception as exc:
+            fixed_base = {"error": repr(exc)}
+
     # ---- CPU baseline beside it (bounded sample, host cores of this box)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -524,6 +547,7 @@ def run_ours(args):
         },
         "cpu_baseline": cpu,
         "sweep": sweep,
+        "resident_fixed_base": fixed_base,
         "secp256k1_config4": secp,
         "porla_calls": calls,
     }
