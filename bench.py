@@ -513,7 +513,7 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     traffic = None
     try:   # DRAM bytes of one k_accumulate launch at this size, from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01e_traffic.json")))["k_accumulate<Bn254>"].get(str(args.log2n))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01g_traffic.json")))["k_accumulate<Bn254>"].get(str(args.log2n))
     except Exception:
         pass
     macs = n * MAC32_PER_POINT

@@ -712,6 +712,10 @@ void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const voi
     view.d_points = (uint8_t*)t->t.d_points + (size_t)first * 64;
     view.d_flags = t->t.d_flags ? t->t.d_flags + first : nullptr;
     view.n = (uint32_t)n;
+    if (t->t.d_phi_x) {                           // image of entry first + i: same index arithmetic on the beta*x array
+        view.d_phi_x = (uint8_t*)t->t.d_phi_x + (size_t)first * 32;
+        view.phi_off = (uint32_t)n;
+    }
     if (t->t.fb_c > 0) {                          // the expansion's rows keep their stride; start them at `first`
         view.d_fb_points = (uint8_t*)t->t.d_fb_points + (size_t)first * 64;
         if (t->t.d_lut) view.d_lut = (uint8_t*)t->t.d_lut + ((((size_t)first * t->t.fb_nwin) << (t->t.fb_c - 1)) * 64);

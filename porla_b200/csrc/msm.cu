@@ -346,6 +346,7 @@ void table_import_into(int curve, const uint8_t* d_bytes, int fmt, uint32_t n, v
     out->n_inf = 0;  // unknown (not counted on this path); the flags are always consulted
     out->curve = curve;
     out->phi_off = with_phi && curve == kCurveBn254 && Bn254::kGlv ? n : 0u;
+    out->d_phi_x = out->phi_off ? static_cast<void*>(static_cast<uint8_t*>(d_points_out) + (size_t)n * 64) : nullptr;
 }
 
 void table_free(PointTable* t) {

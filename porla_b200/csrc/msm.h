@@ -40,9 +40,12 @@ struct PointTable {
     // lut[((i*fb_nwin + w) << (fb_c-1)) + d - 1] = d * 2^(fb_c*w) * P_i, 1 <= d <= 2^(fb_c-1).  An MSM over the
     // table is then a plain sum of n * fb_nwin entries (k_lut_sum): no sort, no buckets, no doublings.
     void* d_lut = nullptr;
-    // GLV (BN254): phi(P_i) = (beta x_i, y_i) is stored behind the table, at entry phi_off + i of d_points
-    // (0 = absent; every import path of a GLV curve writes it, the butterfly kernel refreshes it).
+    // GLV (BN254): the endomorphism image phi(P_i) = (beta x_i, y_i) of every entry.  Only beta x_i is stored (32 B per
+    // point, d_phi_x, right behind the table; y_i is read from the table itself), so table + image are 96 B per point.
+    // A (point, window) pair addresses phi(P_i) as index phi_off + i (0 = image absent; every import path of a GLV
+    // curve writes it, the butterfly kernel refreshes it).
     uint32_t phi_off = 0;
+    void* d_phi_x = nullptr;
 };
 
 // Import `n` external 64-byte points that already live on the device.

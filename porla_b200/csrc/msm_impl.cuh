@@ -38,7 +38,7 @@ void import_into_impl(const uint8_t* d_bytes, int fmt, uint32_t n, void* d_point
     if constexpr (C::kGlv) {   // the endomorphism image right behind the table (PointTable::phi_off = n)
         if (with_phi) {
             k_phi_table<C><<<(n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<F>*>(d_points_out), n,
-                                                               reinterpret_cast<Affine<F>*>(d_points_out) + n);
+                                                               reinterpret_cast<F*>(reinterpret_cast<Affine<F>*>(d_points_out) + n));
             LAUNCHED();
         }
     }
@@ -51,7 +51,7 @@ void import_impl(const uint8_t* d_bytes, int fmt, uint32_t n, PointTable* out, c
     Affine<F>* pts = nullptr;
     uint8_t* flags = nullptr;
     uint32_t* d_count = nullptr;
-    PORLA_CUDA(cudaMalloc(&pts, (size_t)(n ? n : 1) * sizeof(Affine<F>) * (C::kGlv ? 2 : 1)));
+    PORLA_CUDA(cudaMalloc(&pts, (size_t)(n ? n : 1) * (sizeof(Affine<F>) + (C::kGlv ? sizeof(F) : 0))));
     PORLA_CUDA(cudaMalloc(&flags, (size_t)(n ? n : 1)));
     PORLA_CUDA(cudaMalloc(&d_count, 4));
     PORLA_CUDA(cudaMemsetAsync(d_count, 0, 4, stream));
@@ -60,7 +60,7 @@ void import_impl(const uint8_t* d_bytes, int fmt, uint32_t n, PointTable* out, c
         k_import_points<C><<<(n + 127) / 128, 128, 0, stream>>>(d_bytes, fmt, mask, n, pts, flags, d_count);
         LAUNCHED();
         if constexpr (C::kGlv) {
-            k_phi_table<C><<<(n + 127) / 128, 128, 0, stream>>>(pts, n, pts + n);
+            k_phi_table<C><<<(n + 127) / 128, 128, 0, stream>>>(pts, n, reinterpret_cast<F*>(pts + n));
             LAUNCHED();
         }
         PORLA_CUDA(cudaGetLastError());
@@ -74,6 +74,7 @@ void import_impl(const uint8_t* d_bytes, int fmt, uint32_t n, PointTable* out, c
     out->n_inf = h_count;
     out->curve = CurveIdOf<C>::value;
     out->phi_off = C::kGlv ? n : 0u;
+    out->d_phi_x = C::kGlv ? static_cast<void*>(pts + n) : nullptr;
     if (h_count == 0) {
         PORLA_CUDA(cudaFree(flags));
         out->d_flags = nullptr;
@@ -183,7 +184,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
                        (opt.window_bits == 0 || opt.window_bits == table.fb_c);
     const MsmPlan wplan = fixed ? MsmPlan{table.fb_c, 1, kPlanPipeline, 0} : msm_plan(curve, n, nbatch, opt.window_bits, opt.glv);
     const bool glv = wplan.glv != 0;
-    if (glv && !(C::kGlv && table.phi_off)) {
+    if (glv && !(C::kGlv && table.phi_off && table.d_phi_x)) {
         fprintf(stderr, "[libmultiexp/porla_b200] FATAL: GLV plan for a table without its endomorphism image\n");
         abort();
     }
@@ -360,7 +361,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         }
         g_stage_timer.mark(kStageAccumulate, stream);
         k_accumulate<C><<<(nslices_cap + kAccThreads - 1) / kAccThreads, kAccThreads, 0, stream>>>(
-            points, sorted, grand, L, buckets, part_head, part_tail);
+            points, reinterpret_cast<const F*>(table.d_phi_x), sh.phi_off, sorted, grand, L, buckets, part_head, part_tail);
         LAUNCHED();
         if (getenv("PORLA_STITCH_COMPACT"))
             k_stitch<C, FC><<<(nslices_cap + 63) / 64, 64, 0, stream>>>(sorted, grand, L, (XC*)buckets, (const XC*)part_head,
@@ -491,7 +492,7 @@ void butterfly_impl(PointTable* t, uint32_t m, const uint8_t* d_twiddles, int sc
     if constexpr (C::kGlv) {
         if (t->phi_off) {   // the points changed: so does their endomorphism image
             k_phi_table<C><<<(t->n + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const Affine<typename C::F>*>(t->d_points), t->n,
-                                                                  reinterpret_cast<Affine<typename C::F>*>(t->d_points) + t->phi_off);
+                                                                  reinterpret_cast<typename C::F*>(t->d_phi_x));
             LAUNCHED();
         }
     }

@@ -180,10 +180,10 @@ PORLA_D void glv_split(const uint32_t* k, uint32_t* k1, uint32_t* k2, uint32_t& 
     }
 }
 
-// phi[i] = (beta * x_i, y_i): the endomorphism image of every table entry, stored right behind the table
+// out[i] = beta * x_i: the x coordinate of the endomorphism image (beta x_i, y_i) of every table entry
 template <class C>
 __global__ void __launch_bounds__(128)
-k_phi_table(const Affine<typename C::F>* __restrict__ in, uint32_t n, Affine<typename C::F>* __restrict__ out) {
+k_phi_table(const Affine<typename C::F>* __restrict__ in, uint32_t n, typename C::F* __restrict__ out) {
     using F = typename C::F;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -197,8 +197,7 @@ k_phi_table(const Affine<typename C::F>* __restrict__ in, uint32_t n, Affine<typ
     F beta;
 #pragma unroll
     for (int q = 0; q < 8; q++) beta.v[q] = C::glv_beta_mont(q);
-    p.x = p.x * beta;      // infinity (0, 0) stays (0, 0)
-    st16(out + i, p);
+    st16(out + i, p.x * beta);      // infinity (0, 0) stays (0, 0)
 }
 
 // ---------------------------------------------------------------------------- import / export
@@ -736,18 +735,31 @@ constexpr int kAccThreads = 128;
 #define PORLA_ACC_MIN_BLOCKS 4
 #endif
 
+// e = point index | sign << 31.  Indices from phi_off on (phi_off != 0) address the endomorphism image of entry
+// index - phi_off: x from the beta*x array, y from the table record.
 template <class C>
 PORLA_D Affine<typename C::F> load_signed_point(const Affine<typename C::F>* __restrict__ points,
-                                                uint32_t e) {
-    Affine<typename C::F> p = ld16(points + (e & 0x7fffffffu));
+                                                const typename C::F* __restrict__ phi_x, uint32_t phi_off, uint32_t e) {
+    using F = typename C::F;
+    const uint32_t idx = e & 0x7fffffffu;
+    const bool image = C::kGlv && phi_off != 0 && idx >= phi_off;
+    const uint32_t j = image ? idx - phi_off : idx;
+    const uint4* sx = image ? reinterpret_cast<const uint4*>(phi_x + j) : reinterpret_cast<const uint4*>(points + j);
+    const uint4* sy = reinterpret_cast<const uint4*>(points + j) + 2;
+    Affine<F> p;
+    uint4* d = reinterpret_cast<uint4*>(&p);
+    d[0] = __ldg(sx);
+    d[1] = __ldg(sx + 1);
+    d[2] = __ldg(sy);
+    d[3] = __ldg(sy + 1);
     if (e >> 31) p.y = p.y.neg();
     return p;
 }
 
 template <class C>
 __global__ void __launch_bounds__(kAccThreads, PORLA_ACC_MIN_BLOCKS)
-k_accumulate(const Affine<typename C::F>* __restrict__ points, const uint2* __restrict__ sorted,
-             const uint32_t* __restrict__ total_pairs, uint32_t L,
+k_accumulate(const Affine<typename C::F>* __restrict__ points, const typename C::F* __restrict__ phi_x, uint32_t phi_off,
+             const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_pairs, uint32_t L,
              XYZZ<typename C::F>* __restrict__ buckets, XYZZ<typename C::F>* __restrict__ part_head,
              XYZZ<typename C::F>* __restrict__ part_tail) {
     using F = typename C::F;
@@ -763,11 +775,11 @@ k_accumulate(const Affine<typename C::F>* __restrict__ points, const uint2* __re
     uint2 e = __ldg(&sorted[start]);
     uint32_t key = e.x;
     bool first = true;  // still inside the first bucket of this slice
-    Affine<F> p = load_signed_point<C>(points, e.y);
+    Affine<F> p = load_signed_point<C>(points, phi_x, phi_off, e.y);
     XYZZ<F> acc{p.x, p.y, F::one(), F::one()};
     for (uint32_t pos = start + 1; pos < end; ++pos) {
         e = __ldg(&sorted[pos]);
-        Affine<F> q = load_signed_point<C>(points, e.y);
+        Affine<F> q = load_signed_point<C>(points, phi_x, phi_off, e.y);
         if (e.x != key) {
             if (first && prev_key == key) st16(part_head + t, acc);
             else st16(buckets + key, acc);
