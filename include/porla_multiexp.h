@@ -212,6 +212,15 @@ int porla_secp256k1_ecmult_multi_var(const porla_secp256k1_callback* error_callb
 porla_table* porla_secp256k1_table_create(const porla_secp256k1_ge* points, size_t n);
 int porla_secp256k1_ecmult_multi_table(const porla_table* t, size_t first, const porla_secp256k1_scalar* scalars,
                                        size_t n, porla_secp256k1_gej* r);
+/* Server::inner_product_prove (Server.hpp:2279-2443) over a resident table: entries 0 .. n-1 are the
+ * generators (n = NUM_CHUNKS, a power of two >= 4) and entry n is the point u (Server.hpp:2376).  a, b: n scalars of 32
+ * bytes, little-endian (convert_ZZ_to_arr, utils.h:353-364), any value below 2^256.  Each round's L and R are one
+ * look-up-table multi-exponentiation over the whole table; the Fiat-Shamir object (one secp256k1_sha256 finalized again
+ * and again, hash_impl.h:151-165), the inner products and the folding of a, b run on the host.  Writes the proof --
+ * <a, b> (32 B) | per round L, R (33 B SEC1 each) | a0 b0 a1 b1 (32 B each): 32 + (log2 n - 1) * 66 + 128 bytes
+ * (Server.hpp:856) -- and returns its length (0: bad arguments). */
+size_t porla_secp256k1_inner_product_prove(const porla_table* gens_and_u, size_t n, const unsigned char* a_le32,
+                                           const unsigned char* b_le32, unsigned char* proof);
 /* 33-byte SEC1 compressed form of a gej/ge result (eckey_impl.h:36-52); returns 0 for infinity. */
 int porla_secp256k1_gej_serialize(const porla_secp256k1_gej* a, unsigned char out33[33]);
 

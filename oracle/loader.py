@@ -70,6 +70,8 @@ def secp_ref():
         lib.ref_secp_kat.argtypes = [P, P]
         lib.ref_secp_kat.restype = C.c_size_t
         lib.ref_secp_point_chain.argtypes = [P, C.c_size_t, P]
+        if hasattr(lib, "ref_sha256_sequence"):
+            lib.ref_sha256_sequence.argtypes = [P, C.POINTER(C.c_uint32), C.c_int, P]
         for f in ("ref_secp_sizeof_ge", "ref_secp_sizeof_gej", "ref_secp_sizeof_scalar"):
             getattr(lib, f).restype = C.c_size_t
         _secp = lib
@@ -82,3 +84,15 @@ def secp_ref_msm(scalars_le: bytes, points_be: bytes, n: int):
     o64, o33 = C.create_string_buffer(64), C.create_string_buffer(33)
     ok = lib.ref_secp_msm(scalars_le, points_be, n, o64, o33)
     return ok, o64.raw, o33.raw
+
+
+def secp_ref_sha256_sequence(segments):
+    """Digests of the reference's re-finalized SHA-256 object after each segment (see secp_ref.c); None if the
+    reference build is not available."""
+    lib = secp_ref()
+    if lib is None or not hasattr(lib, "ref_sha256_sequence"):
+        return None
+    lens = (C.c_uint32 * len(segments))(*[len(s) for s in segments])
+    outs = C.create_string_buffer(32 * len(segments))
+    lib.ref_sha256_sequence(b"".join(segments), lens, len(segments), outs)
+    return [outs.raw[32 * i:32 * i + 32] for i in range(len(segments))]

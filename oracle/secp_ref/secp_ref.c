@@ -280,3 +280,19 @@ void ref_secp_point_chain(const uint8_t* q_le32, size_t n, uint8_t* out) {
     free(js);
     free(as);
 }
+
+/* The reference's SHA-256 object as inner_product_prove / inner_product_verify drive it (Server.hpp:2306-2310, 2386-2387,
+ * 2429-2430): ONE secp256k1_sha256 that is written to and finalized again and again without re-initialisation.
+ * finalize() zeroes the state words but keeps the byte counter, so the digests are not plain SHA-256 of anything.
+ * data = the concatenated segments, lens[i] = length of segment i; after each segment the object is finalized and the
+ * 32-byte digest stored at outs + 32 i. */
+void ref_sha256_sequence(const uint8_t* data, const uint32_t* lens, int nseg, uint8_t* outs) {
+    secp256k1_sha256 h;
+    int i;
+    secp256k1_sha256_initialize(&h);
+    for (i = 0; i < nseg; i++) {
+        secp256k1_sha256_write(&h, data, lens[i]);
+        data += lens[i];
+        secp256k1_sha256_finalize(&h, outs + 32 * i);
+    }
+}

@@ -112,6 +112,167 @@ void point_add_host(const uint8_t* a, const uint8_t* b, int64_t n, int fmt, uint
 
 }  // namespace
 
+namespace {
+// ---------------------------------------------------------------------------- IPA prover support
+// Arithmetic modulo the secp256k1 group order n = 2^256 - C (C has 129 bits): 4 x 64 limbs, products folded with
+// hi * C + lo as libsecp256k1's scalar_4x64 does.  Only the prover's scalar bookkeeping runs here (a few hundred
+// products per proof, NTL ZZ arithmetic in the reference: Server.hpp:2326-2334, 2344, 2435-2440).
+struct Sn {
+    uint64_t v[4];
+};
+const uint64_t kSnN[4] = {0xBFD25E8CD0364141ull, 0xBAAEDCE6AF48A03Bull, 0xFFFFFFFFFFFFFFFEull, 0xFFFFFFFFFFFFFFFFull};
+const uint64_t kSnC[3] = {0x402DA1732FC9BEBFull, 0x4551231950B75FC4ull, 0x1ull};
+
+bool sn_geq_n(const uint64_t* a) {
+    for (int i = 3; i >= 0; i--)
+        if (a[i] != kSnN[i]) return a[i] > kSnN[i];
+    return true;
+}
+void sn_sub_n(uint64_t* a) {
+    u128 borrow = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 d = (u128)a[i] - kSnN[i] - (uint64_t)borrow;
+        a[i] = (uint64_t)d;
+        borrow = (d >> 64) & 1;
+    }
+}
+// t (len limbs, len <= 8) -> t mod n
+Sn sn_reduce(const uint64_t* t, int len) {
+    uint64_t cur[9] = {0};
+    for (int i = 0; i < len; i++) cur[i] = t[i];
+    int n = len;
+    while (n > 4) {   // cur = lo + hi * C
+        uint64_t nxt[9] = {0};
+        for (int i = 0; i < 4; i++) nxt[i] = cur[i];
+        const int hl = n - 4;
+        for (int i = 0; i < hl; i++) {
+            u128 carry = 0;
+            for (int j = 0; j < 3; j++) {
+                u128 p = (u128)cur[4 + i] * kSnC[j] + nxt[i + j] + (uint64_t)carry;
+                nxt[i + j] = (uint64_t)p;
+                carry = p >> 64;
+            }
+            for (int k = i + 3; carry && k < 9; k++) {
+                u128 p = (u128)nxt[k] + (uint64_t)carry;
+                nxt[k] = (uint64_t)p;
+                carry = p >> 64;
+            }
+        }
+        n = 9;
+        while (n > 4 && nxt[n - 1] == 0) n--;
+        for (int i = 0; i < 9; i++) cur[i] = nxt[i];
+    }
+    Sn r;
+    for (int i = 0; i < 4; i++) r.v[i] = cur[i];
+    while (sn_geq_n(r.v)) sn_sub_n(r.v);
+    return r;
+}
+Sn sn_mul(const Sn& a, const Sn& b) {
+    uint64_t t[8] = {0};
+    for (int i = 0; i < 4; i++) {
+        u128 carry = 0;
+        for (int j = 0; j < 4; j++) {
+            u128 p = (u128)a.v[i] * b.v[j] + t[i + j] + (uint64_t)carry;
+            t[i + j] = (uint64_t)p;
+            carry = p >> 64;
+        }
+        t[i + 4] = (uint64_t)carry;
+    }
+    return sn_reduce(t, 8);
+}
+Sn sn_add(const Sn& a, const Sn& b) {
+    uint64_t t[5];
+    u128 carry = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 p = (u128)a.v[i] + b.v[i] + (uint64_t)carry;
+        t[i] = (uint64_t)p;
+        carry = p >> 64;
+    }
+    t[4] = (uint64_t)carry;
+    return sn_reduce(t, 5);
+}
+Sn sn_from_le32(const unsigned char* b) {   // any 256-bit value, reduced
+    uint64_t t[4];
+    memcpy(t, b, 32);
+    return sn_reduce(t, 4);
+}
+Sn sn_one() { return Sn{{1, 0, 0, 0}}; }
+Sn sn_inverse(const Sn& a) {   // a^(n-2)
+    uint64_t e[4] = {kSnN[0] - 2, kSnN[1], kSnN[2], kSnN[3]};
+    Sn r = sn_one();
+    for (int i = 255; i >= 0; i--) {
+        r = sn_mul(r, r);
+        if ((e[i >> 6] >> (i & 63)) & 1) r = sn_mul(r, a);
+    }
+    return r;
+}
+
+// The reference's Fiat-Shamir object: ONE secp256k1_sha256 written to and finalized repeatedly without
+// re-initialisation (Server.hpp:2306-2310, 2386-2387, 2429-2430); finalize wipes the state words and keeps the byte
+// counter (hash_impl.h:151-165), which this class reproduces.
+struct TranscriptSha256 {
+    uint32_t s[8];
+    unsigned char buf[64];
+    uint64_t bytes = 0;
+    TranscriptSha256() {
+        static const uint32_t iv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+        memcpy(s, iv, sizeof(s));
+    }
+    static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+    void transform(const unsigned char* blk) {
+        static const uint32_t K[64] = {
+            0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u, 0xd807aa98u, 0x12835b01u, 0x243185beu,
+            0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u, 0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau,
+            0x5cb0a9dcu, 0x76f988dau, 0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u, 0x27b70a85u,
+            0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u, 0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u,
+            0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u, 0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu,
+            0x682e6ff3u, 0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+        uint32_t w[64];
+        for (int i = 0; i < 16; i++)
+            w[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) | blk[4 * i + 3];
+        for (int i = 16; i < 64; i++) {
+            uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+            uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+        }
+        uint32_t a = s[0], b = s[1], c = s[2], d = s[3], e = s[4], f = s[5], g = s[6], h = s[7];
+        for (int i = 0; i < 64; i++) {
+            uint32_t t1 = h + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
+            uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+            h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        s[0] += a; s[1] += b; s[2] += c; s[3] += d; s[4] += e; s[5] += f; s[6] += g; s[7] += h;
+    }
+    void write(const unsigned char* data, size_t len) {
+        size_t fill = (size_t)(bytes & 63);
+        bytes += len;
+        while (len >= 64 - fill) {
+            memcpy(buf + fill, data, 64 - fill);
+            data += 64 - fill;
+            len -= 64 - fill;
+            transform(buf);
+            fill = 0;
+        }
+        if (len) memcpy(buf + fill, data, len);
+    }
+    void finalize(unsigned char out[32]) {
+        unsigned char pad[64] = {0x80};
+        unsigned char size[8];
+        const uint64_t bits = bytes << 3;
+        for (int i = 0; i < 8; i++) size[i] = (unsigned char)(bits >> (8 * (7 - i)));
+        write(pad, 1 + ((119 - (size_t)(bytes % 64)) % 64));
+        write(size, 8);
+        for (int i = 0; i < 8; i++) {
+            out[4 * i] = (unsigned char)(s[i] >> 24);
+            out[4 * i + 1] = (unsigned char)(s[i] >> 16);
+            out[4 * i + 2] = (unsigned char)(s[i] >> 8);
+            out[4 * i + 3] = (unsigned char)s[i];
+            s[i] = 0;
+        }
+    }
+};
+}  // namespace
+
 extern "C" {
 
 int porla_secp256k1_ecmult_multi_var(const porla_secp256k1_callback* error_callback, void* scratch,
@@ -199,6 +360,79 @@ int porla_secp256k1_ecmult_multi_table(const porla_table* t, size_t first, const
     r->z.n[0] = 1;
     r->infinity = 0;
     return 1;
+}
+
+size_t porla_secp256k1_inner_product_prove(const porla_table* gens_and_u, size_t n, const unsigned char* a_le32,
+                                           const unsigned char* b_le32, unsigned char* proof) {
+    // Server::inner_product_prove (Server.hpp:2279-2443) with the generators resident: every L and R is ONE call over
+    // the whole table, table entry n holds u and carries the cross term c_L / c_R (the reference adds u^c with
+    // secp256k1_ecmult_const, :2376-2378), generators outside the round's blocks carry a zero scalar.
+    if (n < 4 || (n & (n - 1)) || (int64_t)(n + 1) != porla_table_len(gens_and_u)) return 0;
+    std::vector<Sn> a(n), b(n), xv(n, sn_one());
+    for (size_t i = 0; i < n; i++) {
+        a[i] = sn_from_le32(a_le32 + 32 * i);
+        b[i] = sn_from_le32(b_le32 + 32 * i);
+    }
+    unsigned char* out = proof;
+    Sn ip{{0, 0, 0, 0}};
+    for (size_t i = 0; i < n; i++) ip = sn_add(ip, sn_mul(a[i], b[i]));
+    memcpy(out, ip.v, 32);   // convert_ZZ_to_arr: eight 32-bit words, least significant first (utils.h:353-364)
+    out += 32;
+    static const char seed[] = "hash of P, c, etc. all that jazz";
+    unsigned char random_str[32];
+    TranscriptSha256 sha;
+    sha.write((const unsigned char*)seed, 32);
+    sha.write(proof, 32);
+    sha.finalize(random_str);
+    std::vector<Sn> sc(n + 1);
+    size_t k = 1;
+    for (size_t half = n / 2; half > 1; half >>= 1, k <<= 1) {
+        const Sn x = sn_from_le32(random_str);   // convert_arr_to_ZZ_p (utils.h:384-393), reduced mod n
+        const Sn inv_x = sn_inverse(x);
+        Sn cL{{0, 0, 0, 0}}, cR{{0, 0, 0, 0}};
+        for (size_t i = 0; i < half; i++) {
+            cL = sn_add(cL, sn_mul(a[i], b[half + i]));
+            cR = sn_add(cR, sn_mul(a[half + i], b[i]));
+        }
+        for (int side = 0; side < 2; side++) {   // 0: L (odd blocks, a[q], x), 1: R (even blocks, a[half + q], 1/x)
+            for (size_t j = 0; j <= n; j++) sc[j] = Sn{{0, 0, 0, 0}};
+            for (size_t i = 0; i < k; i++) {
+                const size_t pos = 2 * i + (side == 0 ? 1 : 0);
+                for (size_t j = pos * half, q = 0; j < (pos + 1) * half; j++, q++) {
+                    sc[j] = sn_mul(a[(side == 0 ? 0 : half) + q], xv[j]);
+                    xv[j] = sn_mul(xv[j], side == 0 ? x : inv_x);
+                }
+            }
+            sc[n] = side == 0 ? cL : cR;
+            uint8_t res[64];
+            porla_msm_table_host_scalars(gens_and_u, 0, sc.data(), (int64_t)(n + 1), PORLA_SCALAR_LE32, PORLA_POINT_LE64, res);
+            uint32_t xy[16];
+            memcpy(xy, res, 64);
+            bool inf = true;
+            for (int i = 0; i < 16; i++) inf = inf && xy[i] == 0;
+            size_t size = 0;
+            if (!inf) {   // secp256k1_eckey_pubkey_serialize, compressed (eckey_impl.h:36-52); infinity serialises to nothing
+                out[0] = (xy[8] & 1u) ? 0x03 : 0x02;
+                host::limbs_to_be32(xy, out + 1);
+                size = 33;
+            }
+            sha.write(out, size);
+            sha.finalize(random_str);
+            out += size;
+        }
+        for (size_t i = 0; i < half; i++) {
+            const Sn na = sn_add(sn_mul(a[i], x), sn_mul(a[i + half], inv_x));
+            const Sn nb = sn_add(sn_mul(b[i], inv_x), sn_mul(b[i + half], x));
+            a[i] = na;
+            b[i] = nb;
+        }
+    }
+    for (int i = 0; i < 2; i++) {
+        memcpy(out, a[i].v, 32);
+        memcpy(out + 32, b[i].v, 32);
+        out += 64;
+    }
+    return (size_t)(out - proof);
 }
 
 int porla_secp256k1_gej_serialize(const porla_secp256k1_gej* a, unsigned char out33[33]) {

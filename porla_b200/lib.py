@@ -33,7 +33,7 @@ NEW_SYMBOLS = [
     "porla_stage_timing_enable", "porla_stage_timing_read",
     "porla_butterfly_stage_device", "bn254_butterfly_stage", "bn254_align_mac_batch", "bn254_audit_aggregate",
     "porla_msm_table_host_scalars", "porla_secp256k1_table_create", "porla_secp256k1_ecmult_multi_table",
-    "porla_debug_pairing_selfcheck", "porla_debug_latency",
+    "porla_debug_pairing_selfcheck", "porla_debug_latency", "porla_secp256k1_inner_product_prove",
 ]
 
 
@@ -123,6 +123,7 @@ def load() -> C.CDLL:
         "porla_secp256k1_table_create": (P, [C.POINTER(SecpGe), C.c_size_t]),
         "porla_secp256k1_ecmult_multi_table": (I, [P, C.c_size_t, C.POINTER(SecpScalar), C.c_size_t, C.POINTER(SecpGej)]),
         "porla_debug_pairing_selfcheck": (I, [I]),
+        "porla_secp256k1_inner_product_prove": (C.c_size_t, [P, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p]),
         "porla_debug_latency": (I, [I, I, I, I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "porla_debug_field_mul": (None, [I, P, P, C.c_int64, P]),
         "porla_debug_field_op": (None, [I, I, P, P, C.c_int64, P]),
@@ -391,6 +392,15 @@ class SecpGenerators:
         if r.infinity:
             return ok, None
         return ok, (_fe_to_int(r.x), _fe_to_int(r.y))
+
+    def inner_product_prove(self, a: Sequence[int], b: Sequence[int]) -> bytes:
+        """Server::inner_product_prove (Server.hpp:2279-2443); the table must hold the generators followed by u."""
+        n = self.n - 1
+        buf = C.create_string_buffer(32 + 66 * max(0, n.bit_length() - 2) + 128)
+        ln = load().porla_secp256k1_inner_product_prove(C.c_void_p(self.handle), n,
+                                                        b"".join((x % (1 << 256)).to_bytes(32, "little") for x in a),
+                                                        b"".join((x % (1 << 256)).to_bytes(32, "little") for x in b), buf)
+        return buf.raw[:ln]
 
     def destroy(self) -> None:
         if self.handle:

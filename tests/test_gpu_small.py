@@ -373,3 +373,26 @@ def test_device_entry_on_alternating_streams():
     for i in range(len(scs)):
         assert torch.equal(outs[i], ref[i]), i
     tab.destroy()
+
+
+@pytest.mark.parametrize("n", [128, 16, 4])
+def test_inner_product_prove_matches_oracle(n, route):
+    """porla_secp256k1_inner_product_prove (Server::inner_product_prove, Server.hpp:2279-2443) byte for byte against the
+    oracle's restatement: inner product, the L / R points of every round (33-byte SEC1), the re-finalized SHA-256
+    transcript, the folded a and b."""
+    from oracle import ipa_py
+    rnd = random.Random(2279 + n)
+    G = (SE.gx, SE.gy)
+    gens = [O.mul(SE, rnd.randrange(1, SE.n), G) for _ in range(n)]
+    u = O.mul(SE, rnd.randrange(1, SE.n), G)
+    tab = pb.SecpGenerators(gens + [u])
+    for trial in range(2):
+        a = [rnd.randrange(1 << 256) for _ in range(n)]          # data chunks: any 256-bit value (Client.hpp:371)
+        b = [rnd.randrange(SE.n) for _ in range(n)]
+        if trial == 1:
+            a[0], a[1], b[0] = SE.n - 1, 0, SE.n + 5
+        got = tab.inner_product_prove(a, b)
+        want = ipa_py.inner_product_prove(gens, u, a, b)
+        assert len(got) == 32 + 66 * (n.bit_length() - 2) + 128
+        assert got == want, trial
+    tab.destroy()

@@ -183,3 +183,22 @@ def test_glv_constants_in_the_kernel_header_and_split_bounds():
         k1, k2 = O.glv_split(c, k, g)
         assert (k1 + k2 * lam - k) % c.n == 0
         assert abs(k1) < 1 << 127 and abs(k2) < 1 << 127
+
+
+def test_ipa_transcript_sha_matches_the_reference_object():
+    """Porla's IPA prover keeps ONE secp256k1_sha256 and finalizes it again and again (Server.hpp:2306-2310, 2386-2387):
+    the oracle's restatement of that object against the reference's own hash_impl.h compiled into oracle/_ref."""
+    import random
+    import pytest
+    from oracle import ipa_py, loader
+    rnd = random.Random(2306)
+    segs = [bytes(rnd.getrandbits(8) for _ in range(ln)) for ln in (64, 33, 33, 0, 1, 55, 56, 63, 64, 65, 119, 120, 200, 33, 33)]
+    ref = loader.secp_ref_sha256_sequence(segs)
+    if ref is None:
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    t = ipa_py.TranscriptSha256()
+    for s, want in zip(segs, ref):
+        t.write(s)
+        assert t.finalize() == want
+    import hashlib
+    assert ref[0] == hashlib.sha256(segs[0]).digest() and ref[1] != hashlib.sha256(segs[1]).digest()

@@ -55,3 +55,17 @@ for batch in (8, 64, 1024):
     blocks = b"".join(be(rnd.randrange(1 << 256)) for _ in range(128 * batch))
     w, d = timeit(lambda: k.compute_digest_from_srs_batch(blocks, batch), reps=20, warm=3)
     print("compute_digest_from_srs_batch %d: %.3f ms per call, %.3f ms on the device" % (batch, w, d), flush=True)
+# IPA mode: one inner-product proof over 128 resident generators + u (Server::inner_product_prove, Server.hpp:2279-2443)
+c = O.SECP256K1
+gens = [O.mul(c, rnd.randrange(1, c.n), (c.gx, c.gy)) for _ in range(129)]
+tab = pb.SecpGenerators(gens)
+a = [rnd.randrange(1 << 256) for _ in range(128)]
+b = [rnd.randrange(c.n) for _ in range(128)]
+lib.porla_measure_pint(1, 0.2)
+for _ in range(3):
+    tab.inner_product_prove(a, b)
+t0 = time.perf_counter()
+for _ in range(20):
+    tab.inner_product_prove(a, b)
+print("inner_product_prove (128 generators, 6 rounds, 12 multi-exponentiations): %.3f ms per proof" % ((time.perf_counter() - t0) / 20 * 1e3), flush=True)
+tab.destroy()
