@@ -127,6 +127,10 @@ void porla_msm_resident(const porla_table* t, const void* d_scalars, int64_t n, 
  * memory: the resident-generator form of compute_multi_exp (only the scalars cross PCIe). */
 void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const void* scalars, int64_t n,
                                   int scalar_fmt, int out_fmt, void* out64);
+/* The same for `nbatch` scalar vectors over the same range in one launch (scalars nbatch*n*32 B, out nbatch*64 B):
+ * the L and R of one inner-product round, which depend on the same challenge. */
+void porla_msm_table_host_scalars_batch(const porla_table* t, int64_t first, const void* scalars, int64_t n,
+                                        int64_t nbatch, int scalar_fmt, int out_fmt, void* out);
 /* Building blocks of a range-sharded MSM (one process per GPU): every rank runs
  * the pipeline over its point range up to the per-window sums (nwin XYZZ records of 128 B, about
  * 2 KiB), the ranks all-gather them, and one host combines: add the parts window by window, Horner

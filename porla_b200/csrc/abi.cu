@@ -693,18 +693,19 @@ void porla_msm_resident(const porla_table* t, const void* d_scalars, int64_t n, 
     run_and_fetch(t->t.curve, t->t, (const uint8_t*)d_scalars, n, 1, opt, d_ws, (uint8_t*)h_out64, st);
 }
 
-void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const void* scalars, int64_t n, int scalar_fmt,
-                                  int out_fmt, void* out64) {
-    if (first < 0 || n < 0 || first + n > (int64_t)t->t.n) die("porla_msm_table_host_scalars: range outside the table");
+void porla_msm_table_host_scalars_batch(const porla_table* t, int64_t first, const void* scalars, int64_t n, int64_t nbatch,
+                                        int scalar_fmt, int out_fmt, void* out) {
+    if (first < 0 || n < 0 || nbatch < 0 || first + n > (int64_t)t->t.n) die("porla_msm_table_host_scalars: range outside the table");
+    if (nbatch == 0) return;
     if (n == 0) {
-        memset(out64, 0, 64);
+        memset(out, 0, 64 * (size_t)nbatch);
         return;
     }
     device_init();
-    StageLease lease = lease_stage(n, 1);
+    StageLease lease = lease_stage(n, nbatch);
     Staging& sg = *lease.s;
     auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    size_t sc_bytes = (size_t)n * 32, out_off = pad(sc_bytes), scr_off = out_off + pad(result_scratch_bytes(t->t.curve, n, 1));
+    size_t sc_bytes = (size_t)n * nbatch * 32, out_off = pad(sc_bytes), scr_off = out_off + pad(result_scratch_bytes(t->t.curve, n, nbatch));
     uint8_t* d = sg.dev(scr_off + (lease.local() ? kSlotScratch : 0));
     cudaStream_t st = sg.stream;
     PORLA_CUDA(cudaMemcpyAsync(d, scalars, sc_bytes, cudaMemcpyHostToDevice, st));
@@ -728,7 +729,12 @@ void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const voi
         opt.d_scratch = d + scr_off;
         opt.scratch_bytes = kSlotScratch;
     }
-    run_and_fetch(t->t.curve, view, d, n, 1, opt, d + out_off, (uint8_t*)out64, st, sg);
+    run_and_fetch(t->t.curve, view, d, n, nbatch, opt, d + out_off, (uint8_t*)out, st, sg);
+}
+
+void porla_msm_table_host_scalars(const porla_table* t, int64_t first, const void* scalars, int64_t n, int scalar_fmt,
+                                  int out_fmt, void* out64) {
+    porla_msm_table_host_scalars_batch(t, first, scalars, n, 1, scalar_fmt, out_fmt, out64);
 }
 
 void porla_msm_plan(int curve, int64_t n, int64_t nbatch, int window_bits, int* c_out, int* nwin_out) {

@@ -384,7 +384,7 @@ size_t porla_secp256k1_inner_product_prove(const porla_table* gens_and_u, size_t
     sha.write((const unsigned char*)seed, 32);
     sha.write(proof, 32);
     sha.finalize(random_str);
-    std::vector<Sn> sc(n + 1);
+    std::vector<Sn> sc(2 * (n + 1));
     size_t k = 1;
     for (size_t half = n / 2; half > 1; half >>= 1, k <<= 1) {
         const Sn x = sn_from_le32(random_str);   // convert_arr_to_ZZ_p (utils.h:384-393), reduced mod n
@@ -394,20 +394,25 @@ size_t porla_secp256k1_inner_product_prove(const porla_table* gens_and_u, size_t
             cL = sn_add(cL, sn_mul(a[i], b[half + i]));
             cR = sn_add(cR, sn_mul(a[half + i], b[i]));
         }
-        for (int side = 0; side < 2; side++) {   // 0: L (odd blocks, a[q], x), 1: R (even blocks, a[half + q], 1/x)
-            for (size_t j = 0; j <= n; j++) sc[j] = Sn{{0, 0, 0, 0}};
+        // L (odd blocks, a[q], x) and R (even blocks, a[half + q], 1/x) depend on the same challenge: both
+        // multi-exponentiations go out as ONE batch of two; their serialisations then enter the transcript in order
+        for (int side = 0; side < 2; side++) {
+            Sn* v = sc.data() + (size_t)side * (n + 1);
+            for (size_t j = 0; j <= n; j++) v[j] = Sn{{0, 0, 0, 0}};
             for (size_t i = 0; i < k; i++) {
                 const size_t pos = 2 * i + (side == 0 ? 1 : 0);
                 for (size_t j = pos * half, q = 0; j < (pos + 1) * half; j++, q++) {
-                    sc[j] = sn_mul(a[(side == 0 ? 0 : half) + q], xv[j]);
+                    v[j] = sn_mul(a[(side == 0 ? 0 : half) + q], xv[j]);
                     xv[j] = sn_mul(xv[j], side == 0 ? x : inv_x);
                 }
             }
-            sc[n] = side == 0 ? cL : cR;
-            uint8_t res[64];
-            porla_msm_table_host_scalars(gens_and_u, 0, sc.data(), (int64_t)(n + 1), PORLA_SCALAR_LE32, PORLA_POINT_LE64, res);
+            v[n] = side == 0 ? cL : cR;
+        }
+        uint8_t res[128];
+        porla_msm_table_host_scalars_batch(gens_and_u, 0, sc.data(), (int64_t)(n + 1), 2, PORLA_SCALAR_LE32, PORLA_POINT_LE64, res);
+        for (int side = 0; side < 2; side++) {
             uint32_t xy[16];
-            memcpy(xy, res, 64);
+            memcpy(xy, res + 64 * side, 64);
             bool inf = true;
             for (int i = 0; i < 16; i++) inf = inf && xy[i] == 0;
             size_t size = 0;

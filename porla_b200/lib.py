@@ -32,7 +32,7 @@ NEW_SYMBOLS = [
     "porla_secp256k1_gej_serialize", "porla_debug_field_mul", "porla_debug_field_op", "porla_debug_point_add_host", "porla_measure_pint",
     "porla_stage_timing_enable", "porla_stage_timing_read",
     "porla_butterfly_stage_device", "bn254_butterfly_stage", "bn254_align_mac_batch", "bn254_audit_aggregate",
-    "porla_msm_table_host_scalars", "porla_secp256k1_table_create", "porla_secp256k1_ecmult_multi_table",
+    "porla_msm_table_host_scalars", "porla_msm_table_host_scalars_batch", "porla_secp256k1_table_create", "porla_secp256k1_ecmult_multi_table",
     "porla_debug_pairing_selfcheck", "porla_debug_latency", "porla_secp256k1_inner_product_prove",
 ]
 
@@ -120,6 +120,7 @@ def load() -> C.CDLL:
         "bn254_align_mac_batch": (None, [GS, LL, GS]),
         "bn254_audit_aggregate": (None, [GS, GS, LL, GS, GS]),
         "porla_msm_table_host_scalars": (None, [P, C.c_int64, P, C.c_int64, I, I, P]),
+        "porla_msm_table_host_scalars_batch": (None, [P, C.c_int64, P, C.c_int64, C.c_int64, I, I, P]),
         "porla_secp256k1_table_create": (P, [C.POINTER(SecpGe), C.c_size_t]),
         "porla_secp256k1_ecmult_multi_table": (I, [P, C.c_size_t, C.POINTER(SecpScalar), C.c_size_t, C.POINTER(SecpGej)]),
         "porla_debug_pairing_selfcheck": (I, [I]),
