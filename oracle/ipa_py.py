@@ -120,3 +120,50 @@ def inner_product_prove(generators, u, a, b):
     for i in range(2):                                                          # :2443-2449
         proof += _le_words(a[i]) + _le_words(b[i])
     return bytes(proof)
+
+
+def inner_product_verify(generators, u, commitment, proof) -> bool:
+    """Client::inner_product_verify (Client.hpp:1465-1630): True when the two sides the reference compares with
+    ge_equals_ge are the same point.  commitment: the affine point sum a_i g_i (or None for infinity)."""
+    c = O.SECP256K1
+    n = c.n
+    N = len(generators)
+    pos_ = 32
+    ip = _from_le_words(proof[:32])                                           # :1479 convert_arr_to_scalar
+    lhs = O.add(c, commitment, O.mul(c, ip % n, u))                           # :1481-1482
+    x_values = [1] * N
+    sha = TranscriptSha256()                                                  # :1493-1497
+    sha.write(SEED[:32])
+    sha.write(bytes(proof[:32]))
+    random_str = sha.finalize()
+    half, k = N // 2, 1
+    while half > 1:                                                           # :1504
+        x = _from_le_words(random_str) % n
+        inv_x = pow(x, -1, n)
+        for i in range(k):                                                    # :1511-1523
+            for j in range((2 * i + 1) * half, (2 * i + 2) * half):
+                x_values[j] = x_values[j] * x % n
+            for j in range(2 * i * half, (2 * i + 1) * half):
+                x_values[j] = x_values[j] * inv_x % n
+        x2 = x * x % n                                                        # :1525-1528
+        inv_x2 = pow(x2, -1, n)
+        for factor in (x2, inv_x2):                                           # L :1534-1545, R :1547-1558
+            ser = bytes(proof[pos_:pos_ + 33])
+            px = int.from_bytes(ser[1:], "big")
+            py = O.sqrt_mod(c, (px * px * px + c.b) % c.p)
+            if py is None or ser[0] not in (2, 3):
+                return False
+            if (py & 1) != (ser[0] & 1):
+                py = c.p - py
+            sha.write(ser)
+            random_str = sha.finalize()
+            pos_ += 33
+            lhs = O.add(c, lhs, O.mul(c, factor, (px, py)))                    # :1560-1561
+        half >>= 1
+        k <<= 1
+    a0, b0, a1, b1 = (_from_le_words(proof[pos_ + 32 * i:pos_ + 32 * i + 32]) for i in range(4))   # :1567-1574
+    ab = (a0 * b0 + a1 * b1) % n
+    sc = [a0 * x_values[j] % n for j in range(0, N, 2)] + [a1 * x_values[j] % n for j in range(1, N, 2)]   # :1586-1603
+    pts = [generators[j] for j in range(0, N, 2)] + [generators[j] for j in range(1, N, 2)]
+    rhs = O.add(c, O.mul(c, ab, u), O.msm(c, sc, pts))                        # :1583, :1609-1626
+    return lhs == rhs                                                         # :1628-1630 ge_equals_ge

@@ -395,4 +395,7 @@ def test_inner_product_prove_matches_oracle(n, route):
         want = ipa_py.inner_product_prove(gens, u, a, b)
         assert len(got) == 32 + 66 * (n.bit_length() - 2) + 128
         assert got == want, trial
+    # ... and the proof satisfies the verifier's point equation (Client.hpp:1465-1630, restated in the oracle)
+    if n <= 16:
+        assert ipa_py.inner_product_verify(gens, u, O.msm(SE, [x % SE.n for x in a], gens), got)
     tab.destroy()

@@ -202,3 +202,27 @@ def test_ipa_transcript_sha_matches_the_reference_object():
         assert t.finalize() == want
     import hashlib
     assert ref[0] == hashlib.sha256(segs[0]).digest() and ref[1] != hashlib.sha256(segs[1]).digest()
+
+
+def test_ipa_oracle_prover_and_verifier_close_the_loop():
+    """The restatements of Server::inner_product_prove (Server.hpp:2279-2443) and Client::inner_product_verify
+    (Client.hpp:1465-1630) are two different algebraic statements of the same protocol: a proof of the first must satisfy
+    the point equation of the second, and a flipped bit must not."""
+    import random
+    from oracle import curves_py as O, ipa_py
+    c = O.SECP256K1
+    rnd = random.Random(1465)
+    G = (c.gx, c.gy)
+    for n in (4, 16):
+        gens = [O.mul(c, rnd.randrange(1, c.n), G) for _ in range(n)]
+        u = O.mul(c, rnd.randrange(1, c.n), G)
+        a = [rnd.randrange(1 << 256) for _ in range(n)]
+        b = [rnd.randrange(c.n) for _ in range(n)]
+        proof = ipa_py.inner_product_prove(gens, u, a, b)
+        assert len(proof) == 32 + 66 * (n.bit_length() - 2) + 128
+        commitment = O.msm(c, [x % c.n for x in a], gens)
+        assert ipa_py.inner_product_verify(gens, u, commitment, proof)
+        for flip in (0, 35, len(proof) - 1):
+            bad = bytearray(proof)
+            bad[flip] ^= 1
+            assert not ipa_py.inner_product_verify(gens, u, commitment, bytes(bad))
