@@ -225,6 +225,12 @@ int porla_secp256k1_ecmult_multi_table(const porla_table* t, size_t first, const
  * (Server.hpp:856) -- and returns its length (0: bad arguments). */
 size_t porla_secp256k1_inner_product_prove(const porla_table* gens_and_u, size_t n, const unsigned char* a_le32,
                                            const unsigned char* b_le32, unsigned char* proof);
+/* Client::inner_product_verify (Client.hpp:1465-1630) over the same table (generators followed by u): returns 1 when the
+ * two points the reference compares are equal, 0 otherwise (also for a malformed proof: bad SEC1 tag, x not on the
+ * curve).  `commitment` is the Jacobian MAC_Block the client holds.  One variable-base multi-exponentiation over the
+ * proof's L / R points and one look-up-table multi-exponentiation over the table. */
+int porla_secp256k1_inner_product_verify(const porla_table* gens_and_u, size_t n, const porla_secp256k1_gej* commitment,
+                                         const unsigned char* proof);
 /* 33-byte SEC1 compressed form of a gej/ge result (eckey_impl.h:36-52); returns 0 for infinity. */
 int porla_secp256k1_gej_serialize(const porla_secp256k1_gej* a, unsigned char out33[33]);
 

@@ -440,6 +440,108 @@ size_t porla_secp256k1_inner_product_prove(const porla_table* gens_and_u, size_t
     return (size_t)(out - proof);
 }
 
+int porla_secp256k1_inner_product_verify(const porla_table* gens_and_u, size_t n, const porla_secp256k1_gej* commitment,
+                                         const unsigned char* proof) {
+    // Client::inner_product_verify (Client.hpp:1465-1630).  The reference compares
+    //     commitment + c u + sum_rounds (x^2 L + x^-2 R)   with   (a0 b0 + a1 b1) u + sum_even a0 xv_j g_j + sum_odd a1 xv_j g_j ;
+    // here the c u term moves to the right, so the left side is the commitment plus ONE variable-base multi-exponentiation
+    // over the proof's points and the right side ONE look-up-table multi-exponentiation over the resident table.
+    using SF = host::Fp64<host::SecpFq64Params>;
+    if (n < 4 || (n & (n - 1)) || (int64_t)(n + 1) != porla_table_len(gens_and_u)) return 0;
+    size_t rounds = 0;
+    for (size_t h = n / 2; h > 1; h >>= 1) rounds++;
+    const unsigned char* p = proof;
+    const Sn c = sn_from_le32(p);
+    p += 32;
+    unsigned char random_str[32];
+    static const char seed[] = "hash of P, c, etc. all that jazz";
+    TranscriptSha256 sha;
+    sha.write((const unsigned char*)seed, 32);
+    sha.write(proof, 32);
+    sha.finalize(random_str);
+    std::vector<Sn> xv(n, sn_one()), lr_sc(2 * rounds);
+    std::vector<uint8_t> lr_pts(2 * rounds * 64);
+    size_t k = 1, r = 0;
+    for (size_t half = n / 2; half > 1; half >>= 1, k <<= 1, r++) {
+        const Sn x = sn_from_le32(random_str), inv_x = sn_inverse(x);
+        for (size_t i = 0; i < k; i++) {
+            for (size_t j = (2 * i + 1) * half; j < (2 * i + 2) * half; j++) xv[j] = sn_mul(xv[j], x);
+            for (size_t j = 2 * i * half; j < (2 * i + 1) * half; j++) xv[j] = sn_mul(xv[j], inv_x);
+        }
+        lr_sc[2 * r] = sn_mul(x, x);
+        lr_sc[2 * r + 1] = sn_mul(inv_x, inv_x);
+        for (int side = 0; side < 2; side++) {   // secp256k1_eckey_pubkey_parse of a compressed point (eckey_impl.h:17-34)
+            if (p[0] != 0x02 && p[0] != 0x03) return 0;
+            uint32_t xl[8];
+            host::be32_to_limbs(p + 1, xl);
+            uint32_t pm[8], tmp[8];
+            for (int i = 0; i < 8; i++) pm[i] = Secp256k1FpParams::mod(i);
+            if (!sub256(tmp, xl, pm)) return 0;                      // x >= p: not a field element
+            SF x_;
+            memcpy(x_.v, xl, 32);
+            SF seven = SF::zero();
+            seven.v[0] = 7;
+            const SF rhs = x_.sqr() * x_ + seven;
+            // y = rhs^((p+1)/4), (p+1)/4 = 2^254 - 2^30 - 244
+            static const uint64_t e[4] = {0xffffffffbfffff0cull, 0xffffffffffffffffull, 0xffffffffffffffffull, 0x3fffffffffffffffull};
+            SF y = SF::one();
+            for (int i = 253; i >= 0; i--) {
+                y = y.sqr();
+                if ((e[i >> 6] >> (i & 63)) & 1) y = y * rhs;
+            }
+            if (y.sqr() != rhs) return 0;                            // x is not on the curve
+            if ((y.v[0] & 1) != (uint64_t)(p[0] & 1)) y = y.neg();
+            memcpy(lr_pts.data() + 64 * (2 * r + side), x_.v, 32);
+            memcpy(lr_pts.data() + 64 * (2 * r + side) + 32, y.v, 32);
+            sha.write(p, 33);
+            sha.finalize(random_str);
+            p += 33;
+        }
+    }
+    Sn ab[4];
+    for (int i = 0; i < 4; i++) ab[i] = sn_from_le32(p + 32 * i);    // a0 b0 a1 b1
+    // right side over the table: a0 xv_j on even generators, a1 xv_j on odd ones, (a0 b0 + a1 b1 - c) on u
+    std::vector<Sn> sc(n + 1);
+    for (size_t j = 0; j < n; j++) sc[j] = sn_mul(ab[(j & 1) ? 2 : 0], xv[j]);
+    Sn neg_c{{0, 0, 0, 0}};
+    if (c.v[0] | c.v[1] | c.v[2] | c.v[3]) {
+        u128 borrow = 0;
+        for (int i = 0; i < 4; i++) {
+            u128 d = (u128)kSnN[i] - c.v[i] - (uint64_t)borrow;
+            neg_c.v[i] = (uint64_t)d;
+            borrow = (d >> 64) & 1;
+        }
+    }
+    sc[n] = sn_add(sn_add(sn_mul(ab[0], ab[1]), sn_mul(ab[2], ab[3])), neg_c);
+    uint8_t rhs64[64], lr64[64];
+    porla_msm_table_host_scalars(gens_and_u, 0, sc.data(), (int64_t)(n + 1), PORLA_SCALAR_LE32, PORLA_POINT_LE64, rhs64);
+    porla_msm_host(PORLA_CURVE_SECP256K1, lr_sc.data(), lr_pts.data(), (int64_t)(2 * rounds), 1, PORLA_SCALAR_LE32, PORLA_POINT_LE64, lr64);
+    // left side: commitment (Jacobian, any field magnitude) + the L / R combination, on the host
+    auto load_affine = [](const uint8_t* b) {
+        Affine<SF> a;
+        memcpy(a.x.v, b, 32);
+        memcpy(a.y.v, b + 32, 32);
+        return a;
+    };
+    XYZZ<SF> lhs = XYZZ<SF>::inf();
+    if (!commitment->infinity) {
+        SecpFp cx, cy, cz;
+        fe_to_canonical(&commitment->x, cx.v);
+        fe_to_canonical(&commitment->y, cy.v);
+        fe_to_canonical(&commitment->z, cz.v);
+        const SecpFp zi = cz.inverse(), zi2 = zi.sqr();
+        cx = cx * zi2;
+        cy = cy * zi2 * zi;
+        Affine<SF> ca;
+        memcpy(ca.x.v, cx.v, 32);
+        memcpy(ca.y.v, cy.v, 32);
+        lhs = XYZZ<SF>::from_affine(ca);
+    }
+    lhs.madd(load_affine(lr64));             // all-zero bytes = infinity: madd ignores it
+    const Affine<SF> l = lhs.to_affine(), rr = load_affine(rhs64);
+    return l.x == rr.x && l.y == rr.y ? 1 : 0;
+}
+
 int porla_secp256k1_gej_serialize(const porla_secp256k1_gej* a, unsigned char out33[33]) {
     if (a->infinity) return 0;
     SecpFp x, y, z;

@@ -33,7 +33,7 @@ NEW_SYMBOLS = [
     "porla_stage_timing_enable", "porla_stage_timing_read",
     "porla_butterfly_stage_device", "bn254_butterfly_stage", "bn254_align_mac_batch", "bn254_audit_aggregate",
     "porla_msm_table_host_scalars", "porla_msm_table_host_scalars_batch", "porla_secp256k1_table_create", "porla_secp256k1_ecmult_multi_table",
-    "porla_debug_pairing_selfcheck", "porla_debug_latency", "porla_secp256k1_inner_product_prove",
+    "porla_debug_pairing_selfcheck", "porla_debug_latency", "porla_secp256k1_inner_product_prove", "porla_secp256k1_inner_product_verify",
 ]
 
 
@@ -125,6 +125,7 @@ def load() -> C.CDLL:
         "porla_secp256k1_ecmult_multi_table": (I, [P, C.c_size_t, C.POINTER(SecpScalar), C.c_size_t, C.POINTER(SecpGej)]),
         "porla_debug_pairing_selfcheck": (I, [I]),
         "porla_secp256k1_inner_product_prove": (C.c_size_t, [P, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p]),
+        "porla_secp256k1_inner_product_verify": (I, [P, C.c_size_t, C.POINTER(SecpGej), C.c_char_p]),
         "porla_debug_latency": (I, [I, I, I, I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "porla_debug_field_mul": (None, [I, P, P, C.c_int64, P]),
         "porla_debug_field_op": (None, [I, I, P, P, C.c_int64, P]),
@@ -402,6 +403,16 @@ class SecpGenerators:
                                                         b"".join((x % (1 << 256)).to_bytes(32, "little") for x in a),
                                                         b"".join((x % (1 << 256)).to_bytes(32, "little") for x in b), buf)
         return buf.raw[:ln]
+
+    def inner_product_verify(self, commitment, proof: bytes) -> bool:
+        """Client::inner_product_verify (Client.hpp:1465-1630); commitment: affine point or None."""
+        g = SecpGej()
+        if commitment is None:
+            g.infinity = 1
+        else:
+            g.x, g.y, g.infinity = _int_to_fe(commitment[0]), _int_to_fe(commitment[1]), 0
+            g.z = _int_to_fe(1)
+        return bool(load().porla_secp256k1_inner_product_verify(C.c_void_p(self.handle), self.n - 1, C.byref(g), proof))
 
     def destroy(self) -> None:
         if self.handle:

@@ -399,3 +399,29 @@ def test_inner_product_prove_matches_oracle(n, route):
     if n <= 16:
         assert ipa_py.inner_product_verify(gens, u, O.msm(SE, [x % SE.n for x in a], gens), got)
     tab.destroy()
+
+
+@pytest.mark.parametrize("n", [128, 8])
+def test_inner_product_verify_matches_oracle(n):
+    """porla_secp256k1_inner_product_verify (Client::inner_product_verify, Client.hpp:1465-1630): accepts the prover's
+    proofs, and agrees with the oracle's restatement on tampered ones (every region of the proof, malformed points)."""
+    from oracle import ipa_py
+    rnd = random.Random(1465 + n)
+    G = (SE.gx, SE.gy)
+    gens = [O.mul(SE, rnd.randrange(1, SE.n), G) for _ in range(n)]
+    u = O.mul(SE, rnd.randrange(1, SE.n), G)
+    tab = pb.SecpGenerators(gens + [u])
+    a = [rnd.randrange(1 << 256) for _ in range(n)]
+    b = [rnd.randrange(SE.n) for _ in range(n)]
+    proof = tab.inner_product_prove(a, b)
+    commitment = O.msm(SE, [x % SE.n for x in a], gens)
+    assert tab.inner_product_verify(commitment, proof)
+    assert not tab.inner_product_verify(O.add(SE, commitment, G), proof)          # another commitment
+    assert not tab.inner_product_verify(None, proof)
+    cases = [0, 31, 32, 33, 40, 65, 66, len(proof) - 128, len(proof) - 1]
+    for pos in cases:
+        bad = bytearray(proof)
+        bad[pos] ^= 1 if pos != 32 else 0x06                                      # position 32: the SEC1 tag of the first L
+        want = ipa_py.inner_product_verify(gens, u, commitment, bytes(bad)) if n <= 8 else False
+        assert tab.inner_product_verify(commitment, bytes(bad)) == want, pos
+    tab.destroy()
