@@ -50,4 +50,11 @@ c = O.SECP256K1
 gens = pb.SecpGenerators([(c.gx, c.gy)] * 64)
 print("secp lut", gens.multi(0, [rnd.randrange(c.n) for _ in range(64)])[0], gens.multi(16, [rnd.randrange(c.n) for _ in range(16)])[0])
 gens.destroy()
+# IPA prover and verifier over generators + u (batch of two look-up sums per round, 12-point variable-base MSM)
+pts = [O.mul(c, k_, (c.gx, c.gy)) for k_ in range(2, 19)]
+gu = pb.SecpGenerators(pts)
+a_, b_ = [rnd.randrange(c.n) for _ in range(16)], [rnd.randrange(c.n) for _ in range(16)]
+pr = gu.inner_product_prove(a_, b_)
+print("ipa", len(pr), gu.inner_product_verify(O.msm(c, a_, pts[:16]), pr))
+gu.destroy()
 print("done")
