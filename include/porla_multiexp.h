@@ -175,6 +175,16 @@ void porla_butterfly_stage_device(porla_table* t, int64_t m, const void* twiddle
                                   int twiddles_on_device, void* cuda_stream);
 extern void bn254_butterfly_stage(GoSlice* points, GoInt n, GoInt m, GoSlice* twiddles);
 
+/* The same stage on the DATA blocks (Server.hpp:1582-1588, :1240-1246): for every butterfly (k, k + m/2) and
+ * every chunk p,  t = v_j * X[k + m/2][p];  X[k][p] = (u + t) % LCM;  X[k + m/2][p] = (u - t) % LCM  with u = X[k][p].
+ * blocks: n_blocks x chunks chunks of 64 bytes (little-endian integers below LCM), updated in place; twiddles: m/2 values
+ * of 32 bytes, little-endian (the v_j of the MAC stage, as integers); lcm_le64: LCM (utils.h:42-43, 64 bytes LE, at least
+ * 2^479).  Host-buffer and device-resident forms. */
+void porla_data_butterfly_stage(void* blocks, int64_t n_blocks, int64_t chunks, int64_t m, const void* twiddles_le32,
+                                const void* lcm_le64);
+void porla_data_butterfly_stage_device(void* d_blocks, int64_t n_blocks, int64_t chunks, int64_t m, const void* d_twiddles_le32,
+                                       const void* lcm_le64, void* cuda_stream);
+
 /* Batched Server::align_MAC, KZG branch (Server.hpp:478-562): for each of `batch` data blocks of
  * n_samples chunks A[i] -- 64-byte little-endian integers below LCM = PRIME_MODULUS * r (utils.h:37-44) --
  *       mod = A[i] % PRIME_MODULUS;   c[i] = (mod - A[i]) % r;   A[i] = mod;   align = kzg.Commit(c)

@@ -848,6 +848,31 @@ void bn254_audit_aggregate(GoSlice* coefs, GoSlice* blocks, GoInt n, GoSlice* b_
     go_copy(align_out, res.data(), res.size());
 }
 
+void porla_data_butterfly_stage(void* blocks, int64_t n_blocks, int64_t chunks, int64_t m, const void* twiddles_le32,
+                                const void* lcm_le64) {
+    if (m < 2 || (m & (m - 1)) || n_blocks % m || chunks <= 0) die("porla_data_butterfly_stage: m must be a power of two dividing the block count");
+    device_init();
+    std::lock_guard<std::mutex> lock(g_io_mu);
+    g_stage.init();
+    auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t bytes = (size_t)n_blocks * chunks * 64, tw_bytes = (size_t)(m / 2) * 32;
+    uint8_t* d = g_stage.dev(pad(bytes) + pad(tw_bytes));
+    cudaStream_t st = g_stage.stream;
+    PORLA_CUDA(cudaMemcpyAsync(d, blocks, bytes, cudaMemcpyHostToDevice, st));
+    PORLA_CUDA(cudaMemcpyAsync(d + pad(bytes), twiddles_le32, tw_bytes, cudaMemcpyHostToDevice, st));
+    data_butterfly_stage_device(reinterpret_cast<uint32_t*>(d), (uint32_t)n_blocks, (uint32_t)chunks, (uint32_t)m, d + pad(bytes),
+                                (const uint8_t*)lcm_le64, st);
+    PORLA_CUDA(cudaMemcpyAsync(blocks, d, bytes, cudaMemcpyDeviceToHost, st));
+    PORLA_CUDA(cudaStreamSynchronize(st));
+}
+
+void porla_data_butterfly_stage_device(void* d_blocks, int64_t n_blocks, int64_t chunks, int64_t m, const void* d_twiddles_le32,
+                                       const void* lcm_le64, void* cuda_stream) {
+    if (m < 2 || (m & (m - 1)) || n_blocks % m || chunks <= 0) die("porla_data_butterfly_stage_device: m must be a power of two dividing the block count");
+    data_butterfly_stage_device(reinterpret_cast<uint32_t*>(d_blocks), (uint32_t)n_blocks, (uint32_t)chunks, (uint32_t)m,
+                                (const uint8_t*)d_twiddles_le32, (const uint8_t*)lcm_le64, (cudaStream_t)cuda_stream);
+}
+
 void porla_butterfly_stage_device(porla_table* t, int64_t m, const void* twiddles, int scalar_fmt, int twiddles_on_device,
                                   void* cuda_stream) {
     if (m < 2 || (m & (m - 1)) || (int64_t)t->t.n % m) die("porla_butterfly_stage_device: m must be a power of two dividing the table length");

@@ -402,6 +402,38 @@ void audit_aggregate_device(const uint32_t* d_coefs, const uint32_t* d_blocks, u
     audit_aggregate_impl<Bn254>(d_coefs, d_blocks, n, chunks, d_b_mod_be, d_c_be, stream);   // KZG branch: BN254 order
 }
 
+void data_butterfly_launch(uint32_t*, uint32_t, uint32_t, uint32_t, const uint8_t*, const uint32_t*, const uint32_t*, cudaStream_t);
+
+void data_butterfly_stage_device(uint32_t* d_blocks, uint32_t n_blocks, uint32_t chunks, uint32_t m, const uint8_t* d_twiddles,
+                                 const uint8_t* lcm_le64, cudaStream_t stream) {
+    device_init();
+    uint32_t lcm[16];
+    memcpy(lcm, lcm_le64, 64);
+    // mu = floor(2^1022 / lcm) by restoring division (once per call, 1023 steps on 16 limbs)
+    uint32_t mu[32] = {0}, rem[17] = {0};
+    for (int bit = 1022; bit >= 0; bit--) {
+        for (int i = 16; i > 0; i--) rem[i] = (rem[i] << 1) | (rem[i - 1] >> 31);   // rem = 2 rem + (bit of 2^1022)
+        rem[0] = (rem[0] << 1) | (bit == 1022 ? 1u : 0u);
+        uint32_t d[17];
+        uint64_t borrow = 0;
+        for (int i = 0; i < 17; i++) {
+            uint64_t v = (uint64_t)rem[i] - (i < 16 ? lcm[i] : 0u) - borrow;
+            d[i] = (uint32_t)v;
+            borrow = (v >> 63) & 1;
+        }
+        if (!borrow) {
+            memcpy(rem, d, sizeof(d));
+            mu[bit >> 5] |= 1u << (bit & 31);
+        }
+    }
+    for (int i = 17; i < 32; i++)
+        if (mu[i]) {
+            fprintf(stderr, "[libmultiexp/porla_b200] FATAL: data FFT modulus below 2^479\n");
+            abort();
+        }
+    data_butterfly_launch(d_blocks, n_blocks, chunks, m, d_twiddles, lcm, mu, stream);
+}
+
 void export_points_device(int curve, const void* d_affine, uint32_t n, int fmt, uint8_t* d_out, cudaStream_t stream) {
     device_init();
     if (!n) return;

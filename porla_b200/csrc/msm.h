@@ -132,6 +132,11 @@ void align_scalars_device(uint32_t* d_data, uint32_t total, uint8_t* d_scalars_b
 // c_be[j] = (B_j % PRIME_MODULUS - B_j) % r as 32-byte big-endian scalars, B_j = sum_i coefs[i] * blocks[i][j].
 void audit_aggregate_device(const uint32_t* d_coefs, const uint32_t* d_blocks, uint32_t n, uint32_t chunks, uint8_t* d_b_mod_be,
                             uint8_t* d_c_be, cudaStream_t stream);
+// One radix-2 stage of the FFT on the data blocks themselves (Server.hpp:1582-1588): n_blocks x chunks chunks of 64 bytes
+// (16 LE limbs, values below lcm), in place; twiddles: m/2 scalars of 32 bytes, little-endian; lcm_le64: the modulus
+// (utils.h:42-43), whose Barrett constant is derived on the host per call.
+void data_butterfly_stage_device(uint32_t* d_blocks, uint32_t n_blocks, uint32_t chunks, uint32_t m, const uint8_t* d_twiddles,
+                                 const uint8_t* lcm_le64, cudaStream_t stream);
 void export_points_device(int curve, const void* d_affine, uint32_t n, int point_fmt, uint8_t* d_out,
                           cudaStream_t stream);
 void field_mul_device(int curve, const void* d_a, const void* d_b, uint32_t n, int op, void* d_out,

@@ -516,6 +516,15 @@ void audit_aggregate_impl(const uint32_t* d_coefs, const uint32_t* d_blocks, uin
     PORLA_CUDA(cudaGetLastError());
 }
 
+inline void data_butterfly_impl(uint32_t* d_blocks, uint32_t n_blocks, uint32_t chunks, uint32_t m, const uint8_t* d_twiddles,
+                                const DataFftParams& prm, cudaStream_t stream) {
+    const uint64_t total = (uint64_t)(n_blocks / 2) * chunks;
+    if (!total) return;
+    k_data_butterfly<<<(uint32_t)((total + 127) / 128), 128, 0, stream>>>(d_blocks, n_blocks, chunks, m, d_twiddles, prm);
+    LAUNCHED();
+    PORLA_CUDA(cudaGetLastError());
+}
+
 template <class C>
 void export_impl(const void* d_affine, uint32_t n, int fmt, uint8_t* d_out, cudaStream_t stream) {
     using F = typename C::F;

@@ -1303,6 +1303,112 @@ k_audit_aggregate(const uint32_t* __restrict__ coefs, const uint32_t* __restrict
     store_u256(b_mod_be, j, 1, rem);
 }
 
+// ---- data side of the FFT (CRebuild / mix on the blocks themselves; /root/reference/porla/Server/Server.hpp:1582-1588,
+// :1240-1246): for every butterfly (k, k + m/2) of a stage and every chunk p
+//     t = v_j * X[k + m/2][p];   X[k][p] = (u + t) % LCM;   X[k + m/2][p] = (u - t) % LCM      (u = X[k][p])
+// on 512-bit chunks (16 LE limbs, values below LCM < 2^511, utils.h:42-43) with a 256-bit twiddle.  One thread per
+// (butterfly, chunk); t is reduced with Barrett's method (mu = floor(2^1022 / LCM) computed once on the host), the sum
+// and the difference then need one conditional correction each.  64 B read and written per chunk: HBM-bound.
+struct DataFftParams {
+    uint32_t lcm[16];
+    uint32_t mu[17];      // floor(2^1022 / LCM), < 2^513
+};
+
+// r = a - b on N limbs, returns the borrow
+template <int N>
+PORLA_D uint32_t sub_limbs(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint64_t d = (uint64_t)a[i] - b[i] - borrow;
+        r[i] = (uint32_t)d;
+        borrow = (uint32_t)(d >> 63);
+    }
+    return borrow;
+}
+
+static __global__ void __launch_bounds__(128)
+k_data_butterfly(uint32_t* __restrict__ blocks, uint32_t n_blocks, uint32_t chunks, uint32_t m,
+                 const uint8_t* __restrict__ twiddles_le32, DataFftParams prm) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t m2 = m >> 1;
+    const uint64_t total = (uint64_t)(n_blocks / 2) * chunks;
+    if (gid >= total) return;
+    const uint32_t bfly = (uint32_t)(gid / chunks), p = (uint32_t)(gid - (uint64_t)bfly * chunks);
+    const uint32_t j = bfly % m2, k = (bfly / m2) * m + j;
+    uint4* pu = reinterpret_cast<uint4*>(blocks + ((size_t)k * chunks + p) * 16);
+    uint4* px = reinterpret_cast<uint4*>(blocks + ((size_t)(k + m2) * chunks + p) * 16);
+    uint32_t u[16], x[16], v[8];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint4 a = pu[q], b = px[q];
+        u[4 * q] = a.x; u[4 * q + 1] = a.y; u[4 * q + 2] = a.z; u[4 * q + 3] = a.w;
+        x[4 * q] = b.x; x[4 * q + 1] = b.y; x[4 * q + 2] = b.z; x[4 * q + 3] = b.w;
+    }
+    load_u256(twiddles_le32, j, 0, v);
+    // t = v * x  (24 limbs, < 2^767)
+    uint32_t t[25];
+    mul_limbs<8, 16, 24>(v, x, t);
+    t[24] = 0;
+    // Barrett: q1 = t >> 510, q3 = (q1 * mu) >> 512, r = t - q3 * LCM  (0 <= r < 3 LCM), all mod 2^544
+    uint32_t q1[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) q1[i] = __funnelshift_r(t[15 + i], t[16 + i], 30);
+    uint32_t q2[26];
+    mul_limbs<9, 17, 26>(q1, prm.mu, q2);
+    uint32_t q3[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) q3[i] = q2[16 + i];
+    uint32_t qm[17], r[17];
+    mul_limbs<10, 16, 17>(q3, prm.lcm, qm);
+    sub_limbs<17>(r, t, qm);
+    uint32_t lc[17];
+#pragma unroll
+    for (int i = 0; i < 16; i++) lc[i] = prm.lcm[i];
+    lc[16] = 0;
+#pragma unroll 1
+    for (int it = 0; it < 2; it++) {
+        uint32_t d[17];
+        if (!sub_limbs<17>(d, r, lc)) {
+#pragma unroll
+            for (int i = 0; i < 17; i++) r[i] = d[i];
+        }
+    }
+    // sum and difference mod LCM
+    uint32_t s0[17], s1[17], uu[17];
+#pragma unroll
+    for (int i = 0; i < 16; i++) uu[i] = u[i];
+    uu[16] = 0;
+    uint32_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < 17; i++) {
+        uint64_t a = (uint64_t)uu[i] + r[i] + carry;
+        s0[i] = (uint32_t)a;
+        carry = (uint32_t)(a >> 32);
+    }
+    {
+        uint32_t d[17];
+        if (!sub_limbs<17>(d, s0, lc)) {
+#pragma unroll
+            for (int i = 0; i < 17; i++) s0[i] = d[i];
+        }
+    }
+    if (sub_limbs<17>(s1, uu, r)) {   // u < t': add LCM back
+        carry = 0;
+#pragma unroll
+        for (int i = 0; i < 17; i++) {
+            uint64_t a = (uint64_t)s1[i] + lc[i] + carry;
+            s1[i] = (uint32_t)a;
+            carry = (uint32_t)(a >> 32);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        pu[q] = make_uint4(s0[4 * q], s0[4 * q + 1], s0[4 * q + 2], s0[4 * q + 3]);
+        px[q] = make_uint4(s1[4 * q], s1[4 * q + 1], s1[4 * q + 2], s1[4 * q + 3]);
+    }
+}
+
 // out[i] = a[i] + b[i]
 template <class C>
 __global__ void k_point_add(const Affine<typename C::FC>* __restrict__ a,

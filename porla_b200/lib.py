@@ -31,7 +31,7 @@ NEW_SYMBOLS = [
     "porla_scalar_mul_batch_device", "porla_secp256k1_ecmult_multi_var",
     "porla_secp256k1_gej_serialize", "porla_debug_field_mul", "porla_debug_field_op", "porla_debug_point_add_host", "porla_measure_pint",
     "porla_stage_timing_enable", "porla_stage_timing_read",
-    "porla_butterfly_stage_device", "bn254_butterfly_stage", "bn254_align_mac_batch", "bn254_audit_aggregate",
+    "porla_butterfly_stage_device", "bn254_butterfly_stage", "bn254_align_mac_batch", "bn254_audit_aggregate", "porla_data_butterfly_stage", "porla_data_butterfly_stage_device",
     "porla_msm_table_host_scalars", "porla_msm_table_host_scalars_batch", "porla_secp256k1_table_create", "porla_secp256k1_ecmult_multi_table",
     "porla_debug_pairing_selfcheck", "porla_debug_latency", "porla_secp256k1_inner_product_prove", "porla_secp256k1_inner_product_verify",
 ]
@@ -119,6 +119,8 @@ def load() -> C.CDLL:
         "bn254_butterfly_stage": (None, [GS, LL, LL, GS]),
         "bn254_align_mac_batch": (None, [GS, LL, GS]),
         "bn254_audit_aggregate": (None, [GS, GS, LL, GS, GS]),
+        "porla_data_butterfly_stage": (None, [P, C.c_int64, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p]),
+        "porla_data_butterfly_stage_device": (None, [P, C.c_int64, C.c_int64, C.c_int64, P, C.c_char_p, P]),
         "porla_msm_table_host_scalars": (None, [P, C.c_int64, P, C.c_int64, I, I, P]),
         "porla_msm_table_host_scalars_batch": (None, [P, C.c_int64, P, C.c_int64, C.c_int64, I, I, P]),
         "porla_secp256k1_table_create": (P, [C.POINTER(SecpGe), C.c_size_t]),

@@ -425,3 +425,40 @@ def test_inner_product_verify_matches_oracle(n):
         want = ipa_py.inner_product_verify(gens, u, commitment, bytes(bad)) if n <= 8 else False
         assert tab.inner_product_verify(commitment, bytes(bad)) == want, pos
     tab.destroy()
+
+
+# ------------------------------------------------------------------ SURVEY 8(f)4, second half: the FFT on the data blocks
+LCM_KZG = int("2049369031155707573937272810025244064710333118140408897690954651424664974620215782673575413484558574566298823256897068805013612518402283464943595715297281")   # utils.h:42 (ENABLE_KZG)
+LCM_IPA = int("10841469693352021873483684275893008392101031472050201500515861578010683886271238884283113399568804205471204971859923723932950084770981108620251449466962241")  # utils.h:32
+
+
+@pytest.mark.parametrize("lcm", [LCM_KZG, LCM_IPA])
+@pytest.mark.parametrize("n_blocks,chunks,m", [(2, 3, 2), (16, 128, 4), (64, 128, 64), (8, 5, 8)])
+def test_data_butterfly_stage_matches_reference_arithmetic(lcm, n_blocks, chunks, m):
+    """(u + v x) % LCM and (u - v x) % LCM on 512-bit chunks (Server.hpp:1582-1588) against Python integers, both moduli of
+    utils.h, with the corners of the Barrett reduction (0, LCM - 1, twiddles 0 / 1 / 2^256 - 1)."""
+    import ctypes as C
+    assert lcm == (207 * 2**248 + 1) * (BN.n if lcm == LCM_KZG else SE.n)          # LCM = PRIME_MODULUS * group order
+    rnd = random.Random(n_blocks * 1000 + m)
+    X = [[rnd.randrange(lcm) for _ in range(chunks)] for _ in range(n_blocks)]
+    tw = [rnd.randrange(1 << 256) for _ in range(m // 2)]
+    X[0][0], X[m // 2][0] = lcm - 1, lcm - 1
+    X[1 % n_blocks][1 % chunks] = 0
+    tw[0] = (1 << 256) - 1
+    if m >= 8:
+        tw[1], tw[2] = 0, 1
+    buf = bytearray(b"".join(v.to_bytes(64, "little") for row in X for v in row))
+    pb.load().porla_data_butterfly_stage(C.cast((C.c_ubyte * len(buf)).from_buffer(buf), C.c_void_p), n_blocks, chunks, m,
+                                         b"".join(v.to_bytes(32, "little") for v in tw), lcm.to_bytes(64, "little"))
+    m2 = m // 2
+    want = [row[:] for row in X]
+    for j in range(m2):
+        for k in range(j, n_blocks, m):
+            for p in range(chunks):
+                t = tw[j] * X[k + m2][p]
+                want[k][p] = (X[k][p] + t) % lcm
+                want[k + m2][p] = (X[k][p] - t) % lcm
+    for i in range(n_blocks):
+        for p in range(chunks):
+            off = 64 * (i * chunks + p)
+            assert int.from_bytes(buf[off:off + 64], "little") == want[i][p], (i, p)
