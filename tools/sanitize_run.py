@@ -57,4 +57,11 @@ a_, b_ = [rnd.randrange(c.n) for _ in range(16)], [rnd.randrange(c.n) for _ in r
 pr = gu.inner_product_prove(a_, b_)
 print("ipa", len(pr), gu.inner_product_verify(O.msm(c, a_, pts[:16]), pr))
 gu.destroy()
+# data-side FFT stage
+import ctypes as C
+LCM = (207 * 2**248 + 1) * O.BN254.n
+blk = bytearray(b"".join(rnd.randrange(LCM).to_bytes(64, "little") for _ in range(8 * 5)))
+lib.porla_data_butterfly_stage(C.cast((C.c_ubyte * len(blk)).from_buffer(blk), C.c_void_p), 8, 5, 4,
+                               b"".join(rnd.randrange(1 << 256).to_bytes(32, "little") for _ in range(2)), LCM.to_bytes(64, "little"))
+print("data fft", bytes(blk[:8]).hex())
 print("done")
