@@ -1350,15 +1350,31 @@ k_data_butterfly(uint32_t* __restrict__ blocks, uint32_t n_blocks, uint32_t chun
     uint32_t t[25];
     mul_limbs<8, 16, 24>(v, x, t);
     t[24] = 0;
-    // Barrett: q1 = t >> 510, q3 = (q1 * mu) >> 512, r = t - q3 * LCM  (0 <= r < 3 LCM), all mod 2^544
+    // Barrett: q1 = t >> 510, q3 ~ (q1 * mu) >> 512, r = t - q3 * LCM  (0 <= r < 4 LCM), all mod 2^544
     uint32_t q1[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) q1[i] = __funnelshift_r(t[15 + i], t[16 + i], 30);
-    uint32_t q2[26];
-    mul_limbs<9, 17, 26>(q1, prm.mu, q2);
+    // q3 = (q1 * mu) >> 512 from the partial products at limb 14 and above only: the dropped ones (i + j <= 13, ninety
+    // products below 2^480 each) change q1 * mu by less than 2^487, so q3 is at most one too small and r stays below 4 LCM
+    uint32_t q2h[12];   // limbs 14 .. 25 of the product
+#pragma unroll
+    for (int i = 0; i < 12; i++) q2h[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        uint64_t carry = 0;
+#pragma unroll
+        for (int j = 0; j < 17; j++) {
+            if (i + j >= 14) {
+                uint64_t pv = (uint64_t)q1[i] * prm.mu[j] + q2h[i + j - 14] + carry;
+                q2h[i + j - 14] = (uint32_t)pv;
+                carry = pv >> 32;
+            }
+        }
+        q2h[i + 17 - 14] = (uint32_t)carry;
+    }
     uint32_t q3[10];
 #pragma unroll
-    for (int i = 0; i < 10; i++) q3[i] = q2[16 + i];
+    for (int i = 0; i < 10; i++) q3[i] = q2h[2 + i];
     uint32_t qm[17], r[17];
     mul_limbs<10, 16, 17>(q3, prm.lcm, qm);
     sub_limbs<17>(r, t, qm);
@@ -1367,7 +1383,7 @@ k_data_butterfly(uint32_t* __restrict__ blocks, uint32_t n_blocks, uint32_t chun
     for (int i = 0; i < 16; i++) lc[i] = prm.lcm[i];
     lc[16] = 0;
 #pragma unroll 1
-    for (int it = 0; it < 2; it++) {
+    for (int it = 0; it < 3; it++) {
         uint32_t d[17];
         if (!sub_limbs<17>(d, r, lc)) {
 #pragma unroll
