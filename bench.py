@@ -229,6 +229,7 @@ def porla_calls(lib, pb):
     symbols with host buffers, beside the CPU port of the same MSMs on one host thread."""
     import random
     from oracle import curves_py as O, loader
+    from porla_b200.lib import _slice
     rnd = random.Random(1)
     be = lambda v: v.to_bytes(32, "big")
     k = pb.Kzg(bytes.fromhex("ffeeddccbbaa99887766554433221100"), bytes.fromhex("00112233445566778899aabbccddeeff"))
@@ -258,11 +259,18 @@ def porla_calls(lib, pb):
         got = pb.bn254_multi_exp(bytes(macs), coeff, npts)
         if got != loader.bn254_msm(coeff, bytes(macs), npts, 1):
             raise SystemExit("bench self-check failed: audit-shaped compute_multi_exp differs from the oracle")
-        out["compute_multi_exp_%d" % npts] = {"gpu": timeit(lambda: pb.bn254_multi_exp(bytes(macs), coeff, npts)),
+        # the call as the C++ caller makes it (utils.h:277-292): GoSlices over its own buffers, no per-call copies
+        b_sc, b_pt, b_out = bytearray(coeff), bytearray(macs), bytearray(64)
+        gs = (_slice(b_sc), _slice(b_pt), _slice(b_out))
+        out["compute_multi_exp_%d" % npts] = {"gpu": timeit(lambda: lib.compute_multi_exp(C.byref(gs[0]), C.byref(gs[1]), npts, C.byref(gs[2]))),
                                               "cpu": timeit(lambda: loader.bn254_msm(coeff, bytes(macs), npts, 1), reps=5, warm=1, gpu=False)}
+        if bytes(b_out) != got:
+            raise SystemExit("bench self-check failed: compute_multi_exp result changed between calls")
     if k.compute_digest_from_srs(block) != loader.bn254_msm(block, srs, 128, 1):
         raise SystemExit("bench self-check failed: compute_digest_from_srs differs from the oracle")
-    out["compute_digest_from_srs"] = {"gpu": timeit(lambda: k.compute_digest_from_srs(block)),
+    b_in, b_dg = bytearray(block), bytearray(64)
+    g_in, g_dg = _slice(b_in), _slice(b_dg)
+    out["compute_digest_from_srs"] = {"gpu": timeit(lambda: lib.compute_digest_from_srs(C.byref(g_in), C.byref(g_dg))),
                                       "cpu": timeit(lambda: loader.bn254_msm(block, srs, 128, 1), reps=5, warm=1, gpu=False)}
     out["create_proof"] = {"gpu": timeit(lambda: k.create_proof(123456789, block))}
     c_, h_, z_, y_ = k.create_proof(123456789, block)
