@@ -936,6 +936,17 @@ int porla_debug_pairing_selfcheck(int rounds) {
             bool chain2 = hard_part_chain(c2).is_one(), plain2 = hard_part_plain(c2).is_one();
             bool expect = wrong == 0;
             if (chain1 != expect || plain1 != expect || chain2 != expect || plain2 != expect) bad++;
+            // c1 lies in the cyclotomic subgroup (easy part done): the Granger-Scott squaring must equal the generic one
+            Fq12 g = c1;
+            for (int rep = 0; rep < 3; rep++) {
+                Fq12 s1 = fq12_cyclotomic_sqr(g), s2 = g.sqr();
+                for (int k = 0; k < 6; k++)
+                    if (!(s1.c[k] == s2.c[k])) {
+                        bad++;
+                        break;
+                    }
+                g = s2.mul_dense(c2);
+            }
             // the fixed-argument loop (precomputed lines of qb and g2) must give the very same Fp12 value
             G2Lines la = g2_precompute_lines(qb), lb = g2_precompute_lines(g2);
             const G2Lines* ls[2] = {&la, &lb};

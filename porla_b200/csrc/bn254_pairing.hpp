@@ -521,11 +521,38 @@ inline Fq12 miller_loop_fixed(const G1A* ps, const G2Lines* const* lines, int n)
     return f;
 }
 
-inline Fq12 fq12_pow_u(const Fq12& a) {   // u = 4965661367192848881 (BN254 curve parameter, 63 bits)
+// Squaring in the cyclotomic subgroup (Granger-Scott): for f with f^(p^6 + 1) = 1 -- everything after the easy part of the
+// final exponentiation -- nine Fp2 squarings replace the twelve Fp2 products of the generic square.  In the tower
+// Fp12 = Fp6[w]/(w^2 - v), Fp6 = Fp2[v]/(v^3 - xi) with f = (x0 + x1 v + x2 v^2) + (x3 + x4 v + x5 v^2) w
+// (x0, x1, x2 = c[0], c[2], c[4]; x3, x4, x5 = c[1], c[3], c[5]):
+//   f^2 = (3 (x4^2 xi + x0^2) - 2 x0,  3 (x2^2 xi + x3^2) - 2 x1,  3 (x5^2 xi + x1^2) - 2 x2,
+//          6 x1 x5 xi + 2 x3,          6 x0 x4 + 2 x4,             6 x2 x3 + 2 x5)
+// porla_debug_pairing_selfcheck compares it with Fq12::sqr on cyclotomic elements.
+inline Fq12 fq12_cyclotomic_sqr(const Fq12& f) {
+    const Fq2 &x0 = f.c[0], &x1 = f.c[2], &x2 = f.c[4], &x3 = f.c[1], &x4 = f.c[3], &x5 = f.c[5];
+    Fq2 t0 = x4.sqr(), t1 = x0.sqr(), t6 = (x4 + x0).sqr() - t0 - t1;          // 2 x0 x4
+    Fq2 t2 = x2.sqr(), t3 = x3.sqr(), t7 = (x2 + x3).sqr() - t2 - t3;          // 2 x2 x3
+    Fq2 t4 = x5.sqr(), t5 = x1.sqr(), t8 = ((x5 + x1).sqr() - t4 - t5).mul_xi();   // 2 x1 x5 xi
+    t0 = t0.mul_xi() + t1;
+    t2 = t2.mul_xi() + t3;
+    t4 = t4.mul_xi() + t5;
+    auto three_minus_two = [](const Fq2& t, const Fq2& x) { return (t - x).dbl() + t; };   // 3 t - 2 x
+    auto three_plus_two = [](const Fq2& t, const Fq2& x) { return (t + x).dbl() + t; };    // 3 t + 2 x
+    Fq12 r;
+    r.c[0] = three_minus_two(t0, x0);
+    r.c[2] = three_minus_two(t2, x1);
+    r.c[4] = three_minus_two(t4, x2);
+    r.c[1] = three_plus_two(t8, x3);
+    r.c[3] = three_plus_two(t6, x4);
+    r.c[5] = three_plus_two(t7, x5);
+    return r;
+}
+
+inline Fq12 fq12_pow_u(const Fq12& a) {   // u = 4965661367192848881 (BN254 curve parameter, 63 bits); a cyclotomic
     const uint64_t u = 4965661367192848881ull;
     Fq12 r = a;
     for (int i = 61; i >= 0; i--) {
-        r = r.sqr();
+        r = fq12_cyclotomic_sqr(r);
         if ((u >> i) & 1ull) r = r.mul_dense(a);
     }
     return r;
