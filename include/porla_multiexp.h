@@ -149,6 +149,37 @@ void porla_msm_finalize_host(int curve, const void* h_window_sums, int64_t npart
 /* Multi-GPU combine: parts[k*nbatch + m] (k < count) are XYZZ partials gathered from the ranks. */
 void porla_msm_combine_device(int curve, const void* d_parts, int64_t count, int64_t nbatch,
                               int out_fmt, void* d_out, void* cuda_stream);
+/* ---- One MSM over several GPUs of the box, inside the call (one process, one worker thread per device): the
+ * reference partitions a large multi-exponentiation over 8 host threads by contiguous point range and adds the
+ * partial sums (Client.hpp:747-787, Server.hpp:331-360); here the ranges go to the devices, every device runs the
+ * pipeline up to its per-window sums (about 2 KiB) and the calling thread combines them.
+ *   - compute_multi_exp / porla_msm_host do this by themselves for large calls when the process owns several devices:
+ *     PORLA_DEVICES=k caps the fan-out (1 = off); a process pinned to one device by PORLA_DEVICE / LOCAL_RANK (one
+ *     process per GPU under torchrun) stays on it unless PORLA_DEVICES says otherwise; PORLA_FANOUT_MIN = terms per
+ *     device below which fewer devices are used (default 2^16).
+ *   - porla_mtable: a point table resident in HBM, range-sharded over `ndev` devices (0 = all visible) at creation;
+ *     an MSM over it moves only the scalars (host form) or nothing (resident form: d_scalars_per_part[p] is a device
+ *     pointer ON the device of part p holding that part's scalars). */
+int porla_device_count(void);
+typedef struct porla_mtable porla_mtable;
+porla_mtable* porla_mtable_create(int curve, const void* h_points, int64_t n, int point_fmt, int ndev);
+int porla_mtable_devices(const porla_mtable* mt);
+int64_t porla_mtable_len(const porla_mtable* mt);
+void porla_mtable_range(const porla_mtable* mt, int part, int* device, int64_t* first, int64_t* count);
+void porla_mtable_msm_host_scalars(const porla_mtable* mt, const void* h_scalars, int scalar_fmt, int out_fmt, void* out64);
+void porla_mtable_msm_resident(const porla_mtable* mt, void* const* d_scalars_per_part, int scalar_fmt, int out_fmt, void* out64);
+/* Copies one part's scalars (count(part) x 32 B, host) into a fresh buffer on that part's device / frees it. */
+void* porla_mtable_scalars_upload(const porla_mtable* mt, int part, const void* h_scalars_of_part);
+void porla_mtable_scalars_free(const porla_mtable* mt, int part, void* d_scalars);
+void porla_mtable_destroy(porla_mtable* mt);
+/* The fan-out of compute_multi_exp with an explicit device count (0 = all visible): host scalars and points, the
+ * point range split over `ndev` devices, each copying and multiplying its range concurrently. */
+void porla_msm_host_devices(int curve, const void* scalars, const void* points, int64_t n, int scalar_fmt, int point_fmt,
+                            int ndev, void* out64);
+/* Bytes that reached the device through the pinned-ring copy pool so far (host buffers that are not page-locked,
+ * which is what the reference's callers pass: `new[]` arrays, Client.hpp:124-127). */
+uint64_t porla_debug_copy_ring_bytes(void);
+
 /* Host-buffer MSM (H2D + import + MSM + D2H inside): what compute_multi_exp and the secp256k1
  * adapter are built on.  out: nbatch*64 B. */
 void porla_msm_host(int curve, const void* scalars, const void* points, int64_t n, int64_t nbatch,

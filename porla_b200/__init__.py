@@ -29,7 +29,9 @@ from .lib import (  # noqa: F401
     bn254_butterfly_stage,
     Kzg,
     Table,
+    MultiTable,
     msm_host,
+    msm_host_devices,
     secp256k1_ecmult_multi_var,
     SecpGenerators,
 )

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <shared_mutex>
 #include <random>
 #include <vector>
 
@@ -12,6 +13,8 @@
 #include "bn254_pairing.hpp"
 #include "host_bn254.hpp"
 #include "msm.h"
+#include "multi.h"
+#include "staging.h"
 
 using namespace porla;
 using namespace porla::host;
@@ -34,47 +37,12 @@ struct KzgState {
     G1A h_mac = G1A::inf();
     PointTable srs_table;           // resident in HBM
     bool have_table = false;
+    bool lut_tried = false;         // the wide-window look-up table of a large batch is attempted once per upload
 };
 KzgState g_kzg;
 std::mutex g_io_mu;                 // serialises the staging buffers below
 
-// staging: one device buffer for inputs/outputs of host-buffer calls + a stream
-struct Staging {
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;   // H2D of the second half overlaps the MSM of the first (msm_host_split)
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    uint8_t* d_buf = nullptr;
-    size_t cap = 0;
-    uint8_t* h_pinned = nullptr;
-    size_t h_cap = 0;
-    void init() {
-        if (!stream) {
-            PORLA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-            PORLA_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-            for (auto& e : ev) PORLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        }
-    }
-    uint8_t* dev(size_t bytes) {
-        init();
-        if (bytes > cap) {
-            if (d_buf) {
-                PORLA_CUDA(cudaStreamSynchronize(stream));
-                PORLA_CUDA(cudaFree(d_buf));
-            }
-            cap = bytes + bytes / 4 + 4096;
-            PORLA_CUDA(cudaMalloc(&d_buf, cap));
-        }
-        return d_buf;
-    }
-    uint8_t* pinned(size_t bytes) {
-        if (bytes > h_cap) {
-            if (h_pinned) PORLA_CUDA(cudaFreeHost(h_pinned));
-            h_cap = bytes + 4096;
-            PORLA_CUDA(cudaMallocHost(&h_pinned, h_cap));
-        }
-        return h_pinned;
-    }
-};
+// staging of the default device for the large host-buffer calls (struct Staging: staging.h)
 Staging g_stage;
 
 // Small calls (Porla's 16..766-term MSMs and 128-term commitments) lease one of a few persistent staging slots (device
@@ -138,6 +106,16 @@ void decode_plan(int code, MsmOptions* opt) {
     abort();
 }
 
+// The engine indexes terms with 32 bits: refuse larger shapes at the boundary instead of letting the casts wrap.
+void check_shape(int64_t n, int64_t nbatch, const char* what) {
+    if (n < 0 || nbatch < 0 || n >= ((int64_t)1 << 31) || nbatch >= ((int64_t)1 << 31) ||
+        (nbatch > 0 && n > (((int64_t)1 << 31) - 1) / nbatch)) {
+        fprintf(stderr, "[libmultiexp/porla_b200] FATAL: %s: n = %lld, nbatch = %lld outside the supported range (n * nbatch < 2^31)\n",
+                what, (long long)n, (long long)nbatch);
+        abort();
+    }
+}
+
 // Go's copy(dst, src): min(len(dst), len(src)) bytes
 void go_copy(GoSlice* dst, const uint8_t* src, size_t n) {
     size_t k = (size_t)dst->len < n ? (size_t)dst->len : n;
@@ -168,7 +146,10 @@ void run_and_fetch(int curve, const PointTable& tab, const uint8_t* d_scalars, i
     const char* force_dev = getenv("PORLA_DEVICE_FINALIZE");
     if (nbatch <= kHostFinalizeMaxBatch && !(force_dev && force_dev[0] == '1')) {
         MsmPlan p = msm_plan_table(tab, (uint32_t)n, (uint32_t)nbatch, opt);
-        if (p.mode == kPlanPipeline) opt.window_bits = p.c;
+        if (p.mode == kPlanPipeline) {   // the device must use exactly the layout the host combines (window size AND split)
+            opt.window_bits = p.c;
+            opt.glv = p.glv;
+        }
         opt.d_window_sums = d_scratch_out;
         size_t bytes = (size_t)nbatch * p.nwin * 128;
         msm_device(curve, tab, d_scalars, (uint32_t)n, (uint32_t)nbatch, opt, nullptr, nullptr, st);
@@ -183,61 +164,6 @@ void run_and_fetch(int curve, const PointTable& tab, const uint8_t* d_scalars, i
     PORLA_CUDA(cudaMemcpyAsync(h, d_scratch_out, (size_t)nbatch * 64, cudaMemcpyDeviceToHost, st));
     PORLA_CUDA(cudaStreamSynchronize(st));
     memcpy(out, h, (size_t)nbatch * 64);
-}
-
-// One large MSM from host buffers, as two halves of the point range: the host-to-device copy of the second
-// half (PCIe, ~50 GB/s: 96 B per term) runs while the first half is being multiplied, and the two sets of
-// per-window sums are added by the host finaliser exactly as the multi-GPU path does.  Worth it from 2^19
-// terms (below that the second bucket reduction costs more than the copy it hides).  Caller holds g_io_mu.
-constexpr int kSplitPercentSmall = 25, kSplitPercentLarge = 40;
-void msm_host_split(int curve, const uint8_t* scalars, const uint8_t* points, int64_t n, int scalar_fmt, int point_fmt,
-                    uint8_t* out) {
-    auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    // The first part's copy is exposed, the second part's hides behind the first MSM: a smaller first part shortens
-    // the exposed copy as long as the second copy still fits under the first MSM (PORLA_SPLIT_PERCENT to tune).
-    // Measured at 2^20 (pinned buffers, one B200): 50 % 5.20 ms, 40 % 5.13, 35 % 4.98, 30 % 4.83, 25 % 4.73, 20 % 4.90,
-    // one pass 5.48.  Above 2^21 the copy of the second part (1.75 ns per term) no longer fits under a quarter-size
-    // MSM (~2.7 ns per term), so the first part grows to 40 %.
-    static const int forced_percent = [] {
-        const char* e = getenv("PORLA_SPLIT_PERCENT");
-        int v = e ? atoi(e) : 0;
-        return v < 5 || v > 95 ? 0 : v;
-    }();
-    const int split_percent = forced_percent ? forced_percent : (n <= (1 << 21) ? kSplitPercentSmall : kSplitPercentLarge);
-    const int64_t first_part = n * split_percent / 100;
-    const int64_t half[2] = {first_part, n - first_part};
-    const MsmPlan plan = msm_plan(curve, (uint32_t)half[1], 1, 0);
-    const size_t ws_bytes = (size_t)plan.nwin * 128;
-    // table region: every half's points are followed by their endomorphism image (2 * 64 B per point)
-    size_t sc_off = 0, pt_off = pad((size_t)n * 32), tab_off = pt_off + pad((size_t)n * 64), fl_off = tab_off + pad((size_t)n * 128),
-           ws_off = fl_off + pad((size_t)n);
-    uint8_t* d = g_stage.dev(ws_off + 2 * pad(ws_bytes));
-    cudaStream_t st = g_stage.stream, cs = g_stage.copy_stream;
-    MsmOptions opt;
-    opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
-    opt.out_fmt = point_fmt;
-    opt.shared_points = 1;
-    opt.window_bits = plan.c;
-    opt.glv = plan.glv;           // both parts with the larger part's layout: their window sums are added window by window
-    opt.no_fixed_base = 1;
-    int64_t first = 0;
-    for (int h = 0; h < 2; h++) {
-        const size_t a = (size_t)first, m = (size_t)half[h];
-        PORLA_CUDA(cudaMemcpyAsync(d + sc_off + a * 32, scalars + a * 32, m * 32, cudaMemcpyHostToDevice, cs));
-        PORLA_CUDA(cudaMemcpyAsync(d + pt_off + a * 64, points + a * 64, m * 64, cudaMemcpyHostToDevice, cs));
-        PORLA_CUDA(cudaEventRecord(g_stage.ev[h], cs));
-        PORLA_CUDA(cudaStreamWaitEvent(st, g_stage.ev[h], 0));
-        PointTable tab;
-        table_import_into(curve, d + pt_off + a * 64, point_fmt, (uint32_t)m, d + tab_off + a * 128, d + fl_off + a, &tab, st);
-        opt.d_window_sums = d + ws_off + h * pad(ws_bytes);
-        msm_device(curve, tab, d + sc_off + a * 32, (uint32_t)m, 1, opt, nullptr, nullptr, st);
-        first += half[h];
-    }
-    uint8_t* hbuf = g_stage.pinned(2 * ws_bytes);
-    for (int h = 0; h < 2; h++)
-        PORLA_CUDA(cudaMemcpyAsync(hbuf + h * ws_bytes, d + ws_off + h * pad(ws_bytes), ws_bytes, cudaMemcpyDeviceToHost, st));
-    PORLA_CUDA(cudaStreamSynchronize(st));
-    finalize_host_parts(curve, hbuf, 2, plan.nwin, plan.c, opt.out_fmt, out);
 }
 
 // Bit length of the largest scalar in a host buffer, or 0 when some scalar may need reduction (or, on
@@ -280,11 +206,27 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
         memset(out, 0, (size_t)nbatch * 64);
         return;
     }
+    check_shape(n, nbatch, "host-buffer MSM");
     device_init();
+    if (nbatch == 1) {
+        // a large call is partitioned by point range over the GPUs of the box, inside the call, as the reference
+        // partitions it over 8 host threads (Client.hpp:747-787)
+        const int ndev = fanout_devices(n);
+        if (ndev > 1) {
+            msm_host_fanout(curve, scalars, points, n, scalar_fmt, point_fmt, ndev, out);
+            return;
+        }
+    }
     StageLease lease = lease_stage(n, nbatch);
     Staging& sg = *lease.s;
     if (nbatch == 1 && n >= (1 << 19) && !getenv("PORLA_NO_SPLIT")) {
-        msm_host_split(curve, scalars, points, n, scalar_fmt, point_fmt, out);
+        // two pipelined parts: the copy of the second hides under the kernels of the first (multi.cu)
+        const int64_t first = n * (n <= (1 << 21) ? 25 : 40) / 100;
+        const MsmPlan plan = msm_plan(curve, (uint32_t)(first > n - first ? first : n - first), 1, 0);
+        std::vector<uint8_t> ws((size_t)kMaxPartsPerDevice * plan.nwin * 128);
+        int nparts = 0;
+        msm_host_pipelined(sg, curve, scalars, points, n, scalar_fmt, point_fmt, plan, ws.data(), &nparts);
+        finalize_host_parts(curve, ws.data(), nparts, plan.nwin, plan.c, point_fmt, out);
         return;
     }
     const size_t total = (size_t)n * (size_t)nbatch;
@@ -295,8 +237,8 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
            out_off = fl_off + pad(total), scr_off = out_off + pad(result_scratch_bytes(curve, n, nbatch));
     uint8_t* d = sg.dev(scr_off + (lease.local() ? kSlotScratch : 0));
     cudaStream_t st = sg.stream;
-    PORLA_CUDA(cudaMemcpyAsync(d + sc_off, scalars, sc_bytes, cudaMemcpyHostToDevice, st));
-    PORLA_CUDA(cudaMemcpyAsync(d + pt_off, points, pt_bytes, cudaMemcpyHostToDevice, st));
+    h2d_copy(d + sc_off, scalars, sc_bytes, st);
+    h2d_copy(d + pt_off, points, pt_bytes, st);
     MsmOptions opt;
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.out_fmt = point_fmt;
@@ -314,34 +256,56 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
     run_and_fetch(curve, tab, d + sc_off, n, nbatch, opt, d + out_off, out, st, sg);
 }
 
-void upload_srs();
+void upload_srs_locked();
+
+// g_kzg.srs_table is read by every commitment (also by the small calls that take no other lock) and rebuilt in two
+// places: the first upload and the one-time wide-window look-up table of a large batch.  Readers hold g_srs_mu shared
+// for the whole call, the two writers hold it exclusively (so no kernel of a reader can still be using pointers that
+// table_precompute frees: every reader synchronises its stream before it drops the lock).
+std::shared_mutex g_srs_mu;
+
+// Shared lock on the SRS table with the table present and at least `n` bases long; `batch_terms` = n * nbatch of the
+// call (a large batch over a mid-sized SRS, BASELINE config 3, is worth the one-time wide-window look-up table).
+std::shared_lock<std::shared_mutex> srs_reader(int64_t n, uint64_t batch_terms, int64_t nbatch) {
+    for (;;) {
+        {
+            std::shared_lock<std::shared_mutex> rd(g_srs_mu);
+            const bool want_lut = batch_terms >= (1ull << 22) && g_kzg.srs_table.n > 2048 && g_kzg.srs_table.n <= 8192 &&
+                                  !g_kzg.srs_table.d_lut && !g_kzg.lut_tried && !getenv("PORLA_NO_LUT");
+            if (g_kzg.have_table && !want_lut) {
+                if (n > (int64_t)g_kzg.srs_table.n) die("polynomial longer than the SRS");
+                return rd;
+            }
+        }
+        std::unique_lock<std::shared_mutex> wr(g_srs_mu);
+        if (!g_kzg.have_table) {
+            if (g_kzg.srs_g1.empty()) die("SRS not initialised (call init_SRS or init_SRS_from_data first)");
+            upload_srs_locked();
+        }
+        if (batch_terms >= (1ull << 22) && g_kzg.srs_table.n > 2048 && g_kzg.srs_table.n <= 8192 && !g_kzg.srs_table.d_lut &&
+            !g_kzg.lut_tried && !getenv("PORLA_NO_LUT")) {
+            std::lock_guard<std::mutex> io(g_io_mu);
+            g_stage.init();
+            table_precompute(&g_kzg.srs_table, 0, (uint32_t)n, (uint32_t)nbatch, g_stage.stream);
+            PORLA_CUDA(cudaStreamSynchronize(g_stage.stream));
+            g_kzg.lut_tried = true;
+        }
+    }
+}
 
 // nbatch commitments over the resident SRS
 void srs_commit_core(const uint8_t* coeffs_be, int64_t n, int64_t nbatch, uint8_t* out) {
-    {
-        static std::mutex upload_mu;   // a first commitment may arrive from several pool threads at once
-        std::lock_guard<std::mutex> up(upload_mu);
-        if (!g_kzg.have_table) {
-            if (g_kzg.srs_g1.empty()) die("SRS not initialised (call init_SRS or init_SRS_from_data first)");
-            upload_srs();
-        }
-    }
-    if (n > (int64_t)g_kzg.srs_table.n) die("polynomial longer than the SRS");
+    check_shape(n, nbatch, "commitment over the SRS");
     device_init();
+    std::shared_lock<std::shared_mutex> srs = srs_reader(n, (uint64_t)n * (uint64_t)nbatch, nbatch);
     StageLease lease = lease_stage(n, nbatch);
     Staging& sg = *lease.s;
-    // a large batch over a mid-sized SRS (BASELINE config 3) is worth the one-time wide-window look-up table
-    if ((uint64_t)n * (uint64_t)nbatch >= (1ull << 22) && g_kzg.srs_table.n > 2048 && g_kzg.srs_table.n <= 8192 &&
-        !g_kzg.srs_table.d_lut && !getenv("PORLA_NO_LUT")) {   // (large call: the lease holds g_io_mu)
-        table_precompute(&g_kzg.srs_table, 0, (uint32_t)n, (uint32_t)nbatch, sg.stream);
-        PORLA_CUDA(cudaStreamSynchronize(sg.stream));
-    }
     auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t sc_bytes = (size_t)n * nbatch * 32;
     size_t out_off = pad(sc_bytes), scr_off = out_off + pad(result_scratch_bytes(kCurveBn254, n, nbatch));
     uint8_t* d = sg.dev(scr_off + (lease.local() ? kSlotScratch : 0));
     cudaStream_t st = sg.stream;
-    PORLA_CUDA(cudaMemcpyAsync(d, coeffs_be, sc_bytes, cudaMemcpyHostToDevice, st));
+    h2d_copy(d, coeffs_be, sc_bytes, st);
     MsmOptions opt;
     opt.scalar_be = 1;
     opt.out_fmt = PORLA_POINT_BE64;
@@ -350,12 +314,13 @@ void srs_commit_core(const uint8_t* coeffs_be, int64_t n, int64_t nbatch, uint8_
         opt.d_scratch = d + scr_off;
         opt.scratch_bytes = kSlotScratch;
     }
-    run_and_fetch(kCurveBn254, g_kzg.srs_table, d, n, nbatch, opt, d + out_off, out, st, sg);
+    run_and_fetch(kCurveBn254, g_kzg.srs_table, d, n, nbatch, opt, d + out_off, out, st, sg);   // synchronises `st`
 }
 
 // SRS bases go to HBM once, at init when a device is present (otherwise on the first commit,
 // which aborts loudly if there is still no GPU).
-void upload_srs() {
+// Caller holds g_srs_mu exclusively.
+void upload_srs_locked() {
     device_init();
     std::lock_guard<std::mutex> lock(g_io_mu);
     g_stage.init();
@@ -370,6 +335,12 @@ void upload_srs() {
         PORLA_CUDA(cudaStreamSynchronize(g_stage.stream));
     }
     g_kzg.have_table = true;
+    g_kzg.lut_tried = false;
+}
+
+void upload_srs() {
+    std::unique_lock<std::shared_mutex> wr(g_srs_mu);
+    upload_srs_locked();
 }
 
 }  // namespace
@@ -581,6 +552,7 @@ void compute_digest_from_srs_batch(GoSlice* data_in, GoInt batch, GoSlice* data_
 }
 
 porla_table* porla_table_create(int curve, const void* points, int64_t n, int point_fmt, int on_device, void* cuda_stream) {
+    check_shape(n, 1, "porla_table_create");
     device_init();
     porla_table* t = new porla_table();
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -591,6 +563,7 @@ porla_table* porla_table_create(int curve, const void* points, int64_t n, int po
 
 porla_table* porla_table_create_multiples(int curve, const void* scalars, int64_t n, int scalar_fmt, int on_device,
                                           void* cuda_stream) {
+    check_shape(n, 1, "porla_table_create_multiples");
     device_init();
     cudaStream_t st = (cudaStream_t)cuda_stream;
     // generator as a 1-entry table
@@ -642,6 +615,7 @@ int64_t porla_table_len(const porla_table* t) { return t->t.n; }
 int64_t porla_table_num_infinity(const porla_table* t) { return t->t.n_inf; }
 
 void porla_table_export(const porla_table* t, int point_fmt, void* out, int on_device, void* cuda_stream) {
+    device_init();
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (on_device) {
         export_points_device(t->t.curve, t->t.d_points, t->t.n, point_fmt, (uint8_t*)out, st);
@@ -663,6 +637,7 @@ void porla_table_destroy(porla_table* t) {
 
 void porla_msm_device(const porla_table* t, const void* d_scalars, int64_t n, int64_t nbatch, int scalar_fmt,
                       int shared_points, int window_bits, int out_fmt, void* d_out, void* d_out_xyzz, void* cuda_stream) {
+    check_shape(n, nbatch, "porla_msm_device");
     int64_t need = shared_points ? n : n * nbatch;
     if (need > (int64_t)t->t.n) die("porla_msm_device: table shorter than the MSM");
     MsmOptions opt;
@@ -681,6 +656,8 @@ void porla_msm_resident(const porla_table* t, const void* d_scalars, int64_t n, 
         memset(h_out64, 0, 64);
         return;
     }
+    check_shape(n, 1, "porla_msm_resident");
+    const int dev = device_init();
     std::lock_guard<std::mutex> lock(g_io_mu);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     MsmOptions opt;
@@ -688,13 +665,15 @@ void porla_msm_resident(const porla_table* t, const void* d_scalars, int64_t n, 
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.out_fmt = out_fmt;
     opt.shared_points = 1;
-    static uint8_t* d_ws = nullptr;  // 64 windows x 128 B is the most any plan needs... sized generously
+    static uint8_t* d_ws_dev[kMaxDevices] = {};  // 256 window sums of 128 B: more than any plan produces; one per device
+    uint8_t*& d_ws = d_ws_dev[dev];
     if (!d_ws) PORLA_CUDA(cudaMalloc(&d_ws, 256 * 128));
     run_and_fetch(t->t.curve, t->t, (const uint8_t*)d_scalars, n, 1, opt, d_ws, (uint8_t*)h_out64, st);
 }
 
 void porla_msm_table_host_scalars_batch(const porla_table* t, int64_t first, const void* scalars, int64_t n, int64_t nbatch,
                                         int scalar_fmt, int out_fmt, void* out) {
+    check_shape(n, nbatch, "porla_msm_table_host_scalars");
     if (first < 0 || n < 0 || nbatch < 0 || first + n > (int64_t)t->t.n) die("porla_msm_table_host_scalars: range outside the table");
     if (nbatch == 0) return;
     if (n == 0) {
@@ -708,7 +687,7 @@ void porla_msm_table_host_scalars_batch(const porla_table* t, int64_t first, con
     size_t sc_bytes = (size_t)n * nbatch * 32, out_off = pad(sc_bytes), scr_off = out_off + pad(result_scratch_bytes(t->t.curve, n, nbatch));
     uint8_t* d = sg.dev(scr_off + (lease.local() ? kSlotScratch : 0));
     cudaStream_t st = sg.stream;
-    PORLA_CUDA(cudaMemcpyAsync(d, scalars, sc_bytes, cudaMemcpyHostToDevice, st));
+    h2d_copy(d, scalars, sc_bytes, st);
     PointTable view = t->t;                       // a window [first, first + n) of the resident table
     view.d_points = (uint8_t*)t->t.d_points + (size_t)first * 64;
     view.d_flags = t->t.d_flags ? t->t.d_flags + first : nullptr;
@@ -747,6 +726,7 @@ void porla_msm_plan(int curve, int64_t n, int64_t nbatch, int window_bits, int* 
 
 void porla_msm_window_sums_device(const porla_table* t, const void* d_scalars, int64_t n, int scalar_fmt, int window_bits,
                                   void* d_window_sums, void* cuda_stream) {
+    check_shape(n, 1, "porla_msm_window_sums_device");
     if (n > (int64_t)t->t.n) die("porla_msm_window_sums_device: table shorter than the MSM");
     MsmOptions opt;
     decode_plan(window_bits, &opt);
@@ -776,6 +756,9 @@ void porla_msm_host(int curve, const void* scalars, const void* points, int64_t 
 
 void porla_scalar_mul_batch_device(const porla_table* t, const void* d_scalars, int64_t n, int scalar_fmt, int out_fmt,
                                    void* d_out, void* cuda_stream) {
+    check_shape(n, 1, "porla_scalar_mul_batch_device");
+    if (t->t.n != 1 && n > (int64_t)t->t.n) die("porla_scalar_mul_batch_device: table shorter than the batch");
+    device_init();
     cudaStream_t st = (cudaStream_t)cuda_stream;
     void* d_aff = nullptr;
     PORLA_CUDA(cudaMallocAsync(&d_aff, (size_t)(n ? n : 1) * 64, st));
@@ -788,11 +771,9 @@ void bn254_align_mac_batch(GoSlice* data, GoInt batch, GoSlice* align_out) {
     const int64_t n = g_kzg.n_samples;
     if (batch < 0 || data->len < batch * n * 64) die("bn254_align_mac_batch: data shorter than batch*n_samples*64 bytes");
     if (batch == 0) return;
-    if (!g_kzg.have_table) {
-        if (g_kzg.srs_g1.empty()) die("SRS not initialised (call init_SRS or init_SRS_from_data first)");
-        upload_srs();
-    }
+    check_shape(n, batch, "bn254_align_mac_batch");
     device_init();
+    std::shared_lock<std::shared_mutex> srs = srs_reader(n, 0, batch);   // also refuses n_samples above the SRS length
     std::vector<uint8_t> res((size_t)batch * 64);
     {
         std::lock_guard<std::mutex> lock(g_io_mu);
@@ -801,7 +782,7 @@ void bn254_align_mac_batch(GoSlice* data, GoInt batch, GoSlice* align_out) {
         size_t sc_off = pad(total * 64), out_off = sc_off + pad(total * 32);
         uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(kCurveBn254, n, batch));
         cudaStream_t st = g_stage.stream;
-        PORLA_CUDA(cudaMemcpyAsync(d, data->data, total * 64, cudaMemcpyHostToDevice, st));
+        h2d_copy(d, data->data, total * 64, st);
         align_scalars_device(reinterpret_cast<uint32_t*>(d), (uint32_t)total, d + sc_off, st);
         PORLA_CUDA(cudaMemcpyAsync(data->data, d, total * 64, cudaMemcpyDeviceToHost, st));   // A[i] <- A[i] % PRIME_MODULUS
         MsmOptions opt;
@@ -817,11 +798,9 @@ void bn254_audit_aggregate(GoSlice* coefs, GoSlice* blocks, GoInt n, GoSlice* b_
     const int64_t chunks = g_kzg.n_samples;
     if (n < 0 || n >= (1 << 24)) die("bn254_audit_aggregate: block count out of range");
     if (coefs->len < n * 4 || blocks->len < n * chunks * 64) die("bn254_audit_aggregate: coefs / blocks shorter than n entries");
-    if (!g_kzg.have_table) {
-        if (g_kzg.srs_g1.empty()) die("SRS not initialised (call init_SRS or init_SRS_from_data first)");
-        upload_srs();
-    }
+    check_shape(chunks, 1, "bn254_audit_aggregate");
     device_init();
+    std::shared_lock<std::shared_mutex> srs = srs_reader(chunks, 0, 1);   // also refuses n_samples above the SRS length
     std::vector<uint8_t> b_mod((size_t)chunks * 32), res(64);
     {
         std::lock_guard<std::mutex> lock(g_io_mu);
@@ -832,7 +811,7 @@ void bn254_audit_aggregate(GoSlice* coefs, GoSlice* blocks, GoInt n, GoSlice* b_
         uint8_t* d = g_stage.dev(out_off + result_scratch_bytes(kCurveBn254, chunks, 1));
         cudaStream_t st = g_stage.stream;
         if (n) {
-            PORLA_CUDA(cudaMemcpyAsync(d, blocks->data, blk_bytes, cudaMemcpyHostToDevice, st));
+            h2d_copy(d, blocks->data, blk_bytes, st);
             PORLA_CUDA(cudaMemcpyAsync(d + cf_off, coefs->data, (size_t)n * 4, cudaMemcpyHostToDevice, st));
         }
         audit_aggregate_device(reinterpret_cast<const uint32_t*>(d + cf_off), reinterpret_cast<const uint32_t*>(d), (uint32_t)n,
@@ -858,7 +837,7 @@ void porla_data_butterfly_stage(void* blocks, int64_t n_blocks, int64_t chunks, 
     const size_t bytes = (size_t)n_blocks * chunks * 64, tw_bytes = (size_t)(m / 2) * 32;
     uint8_t* d = g_stage.dev(pad(bytes) + pad(tw_bytes));
     cudaStream_t st = g_stage.stream;
-    PORLA_CUDA(cudaMemcpyAsync(d, blocks, bytes, cudaMemcpyHostToDevice, st));
+    h2d_copy(d, blocks, bytes, st);
     PORLA_CUDA(cudaMemcpyAsync(d + pad(bytes), twiddles_le32, tw_bytes, cudaMemcpyHostToDevice, st));
     data_butterfly_stage_device(reinterpret_cast<uint32_t*>(d), (uint32_t)n_blocks, (uint32_t)chunks, (uint32_t)m, d + pad(bytes),
                                 (const uint8_t*)lcm_le64, st);
@@ -895,7 +874,9 @@ void bn254_butterfly_stage(GoSlice* points, GoInt n, GoInt m, GoSlice* twiddles)
     if (n < 0 || points->len < n * 64 || twiddles->len < (m / 2) * 32)
         die("bn254_butterfly_stage: slices shorter than n points / m/2 twiddles");
     if (n == 0) return;
+    check_shape(n, 1, "bn254_butterfly_stage");
     device_init();
+    std::lock_guard<std::mutex> lock(g_io_mu);
     g_stage.init();
     porla_table t;
     table_import_host(kCurveBn254, (const uint8_t*)points->data, PORLA_POINT_BE64, (uint32_t)n, &t.t, g_stage.stream);

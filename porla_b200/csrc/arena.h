@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "msm.h"
 
@@ -72,6 +73,14 @@ struct StageTimer {
         PORLA_CUDA(cudaEventRecord(ev[i], s));
     }
 };
-extern StageTimer g_stage_timer;
+
+// Per-device engine state.  One process may drive several devices (one worker thread per device inside a call);
+// each device has its own scratch arena, its own engine mutex and its own stage events.
+struct DeviceCtx {
+    std::mutex engine_mu;
+    Arena arena;
+    StageTimer timer;
+};
+DeviceCtx& device_ctx();     // of the calling thread's current engine device (device_init / DeviceScope)
 
 }  // namespace porla

@@ -27,13 +27,21 @@ void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
 
 static std::once_flag g_dev_once;
 static int g_device = -1;
+static int g_device_count = 0;
+static bool g_device_pinned = false;
+static thread_local int t_device = -1;    // >= 0 while the thread holds a DeviceScope
 
 bool device_available() {
     int count = 0;
     return cudaGetDeviceCount(&count) == cudaSuccess && count > 0;
 }
 
-int device_init() {
+int device_count() {
+    int count = 0;
+    return cudaGetDeviceCount(&count) == cudaSuccess ? count : 0;
+}
+
+static void device_init_once() {
     std::call_once(g_dev_once, [] {
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
@@ -44,38 +52,93 @@ int device_init() {
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
             abort();
         }
+        if (count > kMaxDevices) count = kMaxDevices;
         int dev = 0;
         const char* s = getenv("PORLA_DEVICE");
         if (!s) s = getenv("LOCAL_RANK");
-        if (s) dev = atoi(s) % count;
-        PORLA_CUDA(cudaSetDevice(dev));
+        if (s) {
+            dev = atoi(s) % count;
+            g_device_pinned = true;
+        }
+        g_device_count = count;
         g_device = dev;
-        // stream-ordered allocations (twiddle / result staging of the batched entry points) stay in the pool
-        // between calls: with the default threshold of 0 every synchronize hands the memory back to the driver
-        // and the next call pays a real allocation (milliseconds of jitter on a 2 ms butterfly stage)
+    });
+}
+
+// stream-ordered allocations (twiddle / result staging of the batched entry points) stay in the pool
+// between calls: with the default threshold of 0 every synchronize hands the memory back to the driver
+// and the next call pays a real allocation (milliseconds of jitter on a 2 ms butterfly stage)
+static void device_first_use(int dev) {
+    static std::once_flag once[kMaxDevices];
+    std::call_once(once[dev], [dev] {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             uint64_t keep = ~0ull;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     });
-    PORLA_CUDA(cudaSetDevice(g_device));
+}
+
+int device_init() {
+    device_init_once();
+    const int dev = t_device >= 0 ? t_device : g_device;
+    PORLA_CUDA(cudaSetDevice(dev));
+    device_first_use(dev);
+    return dev;
+}
+
+int default_device() {
+    device_init_once();
     return g_device;
 }
 
-// forward declarations of the per-curve drivers (msm_impl.cuh)
-std::mutex g_engine_mu;
-Arena g_arena;
-StageTimer g_stage_timer;
+int current_device() {
+    device_init_once();
+    return t_device >= 0 ? t_device : g_device;
+}
 
-void stage_timing_enable(int on) { g_stage_timer.enabled = on != 0; }
+bool device_pinned_by_env() {
+    device_init_once();
+    return g_device_pinned;
+}
+
+DeviceScope::DeviceScope(int dev) {
+    device_init_once();
+    if (dev < 0 || dev >= g_device_count) {
+        fprintf(stderr, "[libmultiexp/porla_b200] FATAL: device %d outside the %d visible devices\n", dev, g_device_count);
+        abort();
+    }
+    prev = t_device;
+    t_device = dev;
+    PORLA_CUDA(cudaSetDevice(dev));
+    device_first_use(dev);
+}
+DeviceScope::~DeviceScope() {
+    t_device = prev;
+    cudaSetDevice(prev >= 0 ? prev : g_device);
+}
+
+static DeviceCtx g_ctx[kMaxDevices];
+DeviceCtx& device_ctx() {
+    device_init_once();
+    return g_ctx[t_device >= 0 ? t_device : g_device];
+}
+
+// Stage timing is switched on for the whole process; every device records its own events and the read-out is that
+// of the calling thread's device.
+static bool g_stage_timing = false;
+void stage_timing_enable(int on) {
+    g_stage_timing = on != 0;
+    for (auto& c : g_ctx) c.timer.enabled = g_stage_timing;
+}
 int stage_timing_read(float* ms_out) {
-    if (!g_stage_timer.enabled || !g_stage_timer.created) return 0;
-    PORLA_CUDA(cudaEventSynchronize(g_stage_timer.ev[kNumStages]));
+    StageTimer& tm = device_ctx().timer;
+    if (!tm.enabled || !tm.created) return 0;
+    PORLA_CUDA(cudaEventSynchronize(tm.ev[kNumStages]));
     for (int i = 0; i < kNumStages; i++) {
         float ms = 0;
         // a stage that was skipped (empty MSM) keeps a stale event: report what CUDA gives
-        if (cudaEventElapsedTime(&ms, g_stage_timer.ev[i], g_stage_timer.ev[i + 1]) != cudaSuccess) ms = 0;
+        if (cudaEventElapsedTime(&ms, tm.ev[i], tm.ev[i + 1]) != cudaSuccess) ms = 0;
         ms_out[i] = ms;
     }
     return kNumStages;

@@ -15,11 +15,28 @@ enum CurveId : int { kCurveBn254 = 0, kCurveSecp256k1 = 1 };
 void cuda_check(cudaError_t e, const char* what, const char* file, int line);
 #define PORLA_CUDA(x) ::porla::cuda_check((x), #x, __FILE__, __LINE__)
 
-// Selects/initialises the device once (PORLA_DEVICE, else LOCAL_RANK, else 0).  Aborts loudly
-// when no CUDA device is usable.
+// Selects/initialises the process's default device once (PORLA_DEVICE, else LOCAL_RANK, else 0) and makes the calling
+// thread's device current: the default one, or the one a DeviceScope on this thread names.  Aborts loudly when no CUDA
+// device is usable.
 int device_init();
 // Non-aborting probe (lets the host-only entry points of the C-ABI work on a machine without a GPU).
 bool device_available();
+constexpr int kMaxDevices = 16;   // devices one process drives at most
+int device_count();          // visible CUDA devices (0 when there is none)
+int default_device();        // the device a plain call runs on (after device_init)
+int current_device();        // the calling thread's engine device: its DeviceScope's, else the default one
+// true when the process was told which ONE device is its own (PORLA_DEVICE / LOCAL_RANK set: one process per GPU under
+// torchrun); an in-call fan-out over all visible devices is then opt-in (PORLA_DEVICES) instead of automatic.
+bool device_pinned_by_env();
+// Every engine object (scratch arena, engine mutex, stage timer) exists once per device; a thread that works on
+// another device than the default one (the in-call multi-GPU partition, Client.hpp:747-787) holds a DeviceScope.
+struct DeviceScope {
+    int prev;
+    explicit DeviceScope(int dev);
+    ~DeviceScope();
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
 
 // Resident point table in internal form (Montgomery for BN254).
 struct PointTable {

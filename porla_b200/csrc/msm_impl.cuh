@@ -17,8 +17,6 @@ namespace porla {
 extern std::atomic<uint64_t> g_launches;
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
-extern std::mutex g_engine_mu;
-extern Arena g_arena;
 
 
 template <class C> struct CurveIdOf;
@@ -116,7 +114,10 @@ void msm_small_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t 
     if (!nblk) nblk = 1;
     const size_t need = Arena::padded((size_t)slots * nblk, sizeof(XYZZ<F>)) + Arena::padded(slots, 4) +
                         Arena::padded(slots, sizeof(XYZZ<F>)) + 1024;
-    std::unique_lock<std::mutex> lock(g_engine_mu, std::defer_lock);
+    DeviceCtx& cx = device_ctx();
+    Arena& g_arena = cx.arena;
+    StageTimer& g_stage_timer = cx.timer;
+    std::unique_lock<std::mutex> lock(cx.engine_mu, std::defer_lock);
     XYZZ<F>* partials;
     uint32_t* tickets;
     XYZZ<F>* wsum;
@@ -253,7 +254,10 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     const bool radix = nbatch == 1 && n >= (1u << 19) && sh.nwin <= 28 && sh.c >= 9 && sh.c <= 20 && (sh.nbuckets >> (sh.c / 2)) <= (uint32_t)kPartMaxBins && !getenv("PORLA_ATOMIC_SCATTER");
     const int lb = sh.c / 2;                                   // coarse bin = 2^lb consecutive buckets
     const uint32_t ncoarse = radix ? (nbt >> lb) : 0u;
-    std::lock_guard<std::mutex> lock(g_engine_mu);
+    DeviceCtx& cx = device_ctx();
+    Arena& g_arena = cx.arena;
+    StageTimer& g_stage_timer = cx.timer;
+    std::lock_guard<std::mutex> lock(cx.engine_mu);
     size_t need = (radix ? Arena::padded(pairs_cap, 8) + Arena::padded(ncoarse, 4) : 0) + Arena::padded(nbt, 4) * 2 + Arena::padded(ntiles + 1, 4) + 512 +
                   Arena::padded(pairs_cap, 8) + Arena::padded(nbt, sizeof(XYZZ<F>)) +
                   2 * Arena::padded(nslices_cap, sizeof(XYZZ<F>)) + Arena::padded(long_cap, 8) +
@@ -310,7 +314,8 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         LAUNCHED();
         g_stage_timer.mark(kStageScatter, stream);
         if (radix) {
-            static std::once_flag attr_once;
+            static std::once_flag attr_once_dev[kMaxDevices];   // function attributes are per device
+            std::once_flag& attr_once = attr_once_dev[current_device()];
             const size_t smem1 = ((size_t)9 * kPartTile + 2 * kPartMaxBins) * 4 + (size_t)kPartTile * 8;
             const size_t smem2 = (size_t)2 * kFineHist * 4 + (size_t)kFineTile * 8;
             std::call_once(attr_once, [=] {

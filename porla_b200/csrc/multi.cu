@@ -1,0 +1,524 @@
+// In-call multi-GPU partition, pipelined host-buffer MSM and the pageable-memory copy pool.  See multi.h / staging.h.
+#include "multi.h"
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/porla_multiexp.h"
+
+namespace porla {
+
+// ---------------------------------------------------------------------------- pageable-memory copy pool
+bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();   // unregistered host memory reports an error on old drivers: not sticky, clear it
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+namespace {
+
+constexpr size_t kRingChunk = 1u << 20;        // bytes per pinned slot
+constexpr int kRingSlots = 3;                  // slots per copy thread
+constexpr size_t kRingThreshold = 256u << 10;  // smaller pageable copies go through the driver's own staging
+
+std::atomic<uint64_t> g_ring_bytes{0};
+
+struct CopyJob {
+    int dev;
+    uint8_t* dst;
+    const uint8_t* src;
+    size_t bytes;
+    cudaStream_t stream;
+    std::atomic<size_t> next{0};     // next chunk to hand out
+    size_t nchunks;
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t done = 0;
+};
+
+class CopyPool {
+  public:
+    static CopyPool& get() {
+        static CopyPool* p = new CopyPool();   // leaked on purpose: threads may outlive static destruction order
+        return *p;
+    }
+    // Blocks until every chunk of the job has been copied into the ring and its DMA has been issued on job.stream.
+    void run(int dev, void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+        auto job = std::make_shared<CopyJob>();
+        job->dev = dev;
+        job->dst = (uint8_t*)dst;
+        job->src = (const uint8_t*)src;
+        job->bytes = bytes;
+        job->stream = stream;
+        job->nchunks = (bytes + kRingChunk - 1) / kRingChunk;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            start_threads_locked();
+            jobs_.push_back(job);
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> lk(job->mu);
+        job->cv.wait(lk, [&] { return job->done == job->nchunks; });
+        g_ring_bytes.fetch_add(bytes, std::memory_order_relaxed);
+    }
+    int threads() const { return nthreads_; }
+
+  private:
+    struct Slot {
+        uint8_t* buf = nullptr;
+        cudaEvent_t pending = nullptr;          // DMA out of this slot that must finish before it is overwritten
+        cudaEvent_t ev[kMaxDevices] = {};       // one event per device (an event belongs to a device)
+    };
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::shared_ptr<CopyJob>> jobs_;
+    std::vector<std::thread> workers_;
+    int nthreads_ = 0;
+
+    CopyPool() {
+        const char* e = getenv("PORLA_COPY_THREADS");
+        int hw = (int)std::thread::hardware_concurrency();
+        nthreads_ = e && atoi(e) > 0 ? atoi(e) : (hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1));
+        if (nthreads_ > 32) nthreads_ = 32;
+    }
+    void start_threads_locked() {
+        if (!workers_.empty()) return;
+        for (int i = 0; i < nthreads_; i++) workers_.emplace_back([this] { loop(); });
+        for (auto& t : workers_) t.detach();
+    }
+    void loop() {
+        Slot slots[kRingSlots];
+        int turn = 0;
+        for (;;) {
+            std::shared_ptr<CopyJob> job;
+            size_t k = 0;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                for (;;) {
+                    while (!jobs_.empty() && jobs_.front()->next.load() >= jobs_.front()->nchunks) jobs_.pop_front();
+                    if (!jobs_.empty()) {
+                        job = jobs_.front();
+                        k = job->next.fetch_add(1);
+                        if (k < job->nchunks) break;
+                        continue;
+                    }
+                    cv_.wait(lk);
+                }
+            }
+            const size_t off = k * kRingChunk;
+            const size_t len = job->bytes - off < kRingChunk ? job->bytes - off : kRingChunk;
+            Slot& s = slots[turn];
+            turn = (turn + 1) % kRingSlots;
+            PORLA_CUDA(cudaSetDevice(job->dev));
+            if (!s.buf) PORLA_CUDA(cudaHostAlloc(&s.buf, kRingChunk, cudaHostAllocPortable));
+            if (s.pending) PORLA_CUDA(cudaEventSynchronize(s.pending));
+            memcpy(s.buf, job->src + off, len);
+            PORLA_CUDA(cudaMemcpyAsync(job->dst + off, s.buf, len, cudaMemcpyHostToDevice, job->stream));
+            if (!s.ev[job->dev]) PORLA_CUDA(cudaEventCreateWithFlags(&s.ev[job->dev], cudaEventDisableTiming));
+            PORLA_CUDA(cudaEventRecord(s.ev[job->dev], job->stream));
+            s.pending = s.ev[job->dev];
+            {
+                std::lock_guard<std::mutex> g(job->mu);
+                job->done++;
+            }
+            job->cv.notify_all();
+        }
+    }
+};
+
+}  // namespace
+
+uint64_t h2d_ring_bytes() { return g_ring_bytes.load(); }
+
+void h2d_copy(void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream) {
+    if (!bytes) return;
+    static const bool ring_off = getenv("PORLA_NO_COPY_RING") != nullptr;
+    if (bytes < kRingThreshold || ring_off || host_pointer_is_pinned(h_src)) {
+        PORLA_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream));
+        return;
+    }
+    CopyPool::get().run(current_device(), d_dst, h_src, bytes, stream);
+}
+
+// ---------------------------------------------------------------------------- one worker thread per device
+namespace {
+
+struct DevWorker {
+    int dev = 0;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    const std::function<void(int)>* fn = nullptr;
+    int part = 0;
+    bool busy = false;
+    Staging stage;
+};
+
+int visible_devices() {
+    const int c = device_count();
+    return c > kMaxDevices ? kMaxDevices : c;
+}
+int slot_device(int slot) { return slot % visible_devices(); }
+
+std::mutex g_multi_mu;                       // one fan-out at a time
+DevWorker* g_workers[kMaxDevices] = {};      // leaked on purpose: the detached threads outlive static destruction
+thread_local DevWorker* t_worker = nullptr;
+
+void worker_main(DevWorker* w) {
+    DeviceScope scope(w->dev);   // for the life of the thread
+    t_worker = w;
+    w->stage.init();
+    std::unique_lock<std::mutex> lk(w->mu);
+    for (;;) {
+        w->cv.wait(lk, [&] { return w->busy; });
+        const std::function<void(int)>* fn = w->fn;
+        const int part = w->part;
+        lk.unlock();
+        (*fn)(part);
+        lk.lock();
+        w->busy = false;
+        w->cv.notify_all();
+    }
+}
+
+// Worker `slot` drives device slot % visible: with fewer devices than parts (PORLA_OVERSUBSCRIBE_DEVICES=1, a test
+// setting) several workers share a device, each with its own stream and staging; the per-device engine mutex
+// serialises their kernels' scratch.
+DevWorker* get_worker(int slot) {
+    if (!g_workers[slot]) {
+        DevWorker* w = new DevWorker();
+        g_workers[slot] = w;
+        w->dev = slot_device(slot);
+        w->th = std::thread(worker_main, w);
+        w->th.detach();
+    }
+    return g_workers[slot];
+}
+
+}  // namespace
+
+Staging& worker_staging() {
+    if (!t_worker) {
+        fprintf(stderr, "[libmultiexp/porla_b200] FATAL: worker_staging() outside a device worker\n");
+        abort();
+    }
+    return t_worker->stage;
+}
+
+int part_device(int part) { return slot_device(part); }
+
+void run_on_devices(int ndev, const std::function<void(int)>& fn) {
+    if (ndev < 1 || ndev > kMaxDevices) {
+        fprintf(stderr, "[libmultiexp/porla_b200] FATAL: run_on_devices: %d parts\n", ndev);
+        abort();
+    }
+    std::lock_guard<std::mutex> g(g_multi_mu);
+    for (int p = 0; p < ndev; p++) {
+        DevWorker* w = get_worker(p);
+        std::lock_guard<std::mutex> lk(w->mu);
+        w->fn = &fn;
+        w->part = p;
+        w->busy = true;
+        w->cv.notify_all();
+    }
+    for (int p = 0; p < ndev; p++) {
+        DevWorker* w = g_workers[p];
+        std::unique_lock<std::mutex> lk(w->mu);
+        w->cv.wait(lk, [&] { return !w->busy; });
+    }
+}
+
+int fanout_devices(int64_t n) {
+    static const int limit = [] {
+        const char* e = getenv("PORLA_DEVICES");
+        const int count = device_count() > kMaxDevices ? kMaxDevices : device_count();
+        if (e && atoi(e) >= 1) {
+            const int cap = getenv("PORLA_OVERSUBSCRIBE_DEVICES") ? kMaxDevices : count;
+            return atoi(e) < cap ? atoi(e) : cap;
+        }
+        return device_pinned_by_env() ? 1 : count;    // one process per GPU: stay on the process's own device
+    }();
+    static const int64_t min_per_dev = [] {
+        const char* e = getenv("PORLA_FANOUT_MIN");
+        return e && atoll(e) > 0 ? (int64_t)atoll(e) : (int64_t)1 << 16;
+    }();
+    if (limit <= 1) return 1;
+    int d = limit;
+    while (d > 1 && n / d < min_per_dev) d >>= 1;
+    return d;
+}
+
+// ---------------------------------------------------------------------------- pipelined host-buffer MSM (one device)
+// The first part's copy is exposed, the second part's hides behind the first MSM: a smaller first part shortens
+// the exposed copy as long as the second copy still fits under the first MSM (PORLA_SPLIT_PERCENT to tune).
+// Measured at 2^20 (pinned buffers, one B200): 50 % 5.20 ms, 40 % 5.13, 35 % 4.98, 30 % 4.83, 25 % 4.73, 20 % 4.90,
+// one pass 5.48.  Above 2^21 the copy of the second part (1.75 ns per term) no longer fits under a quarter-size
+// MSM (~2.7 ns per term), so the first part grows to 40 %.  Worth it from 2^19 terms (below that the second bucket
+// reduction costs more than the copy it hides).
+static int split_percent_for(int64_t n) {
+    static const int forced = [] {
+        const char* e = getenv("PORLA_SPLIT_PERCENT");
+        int v = e ? atoi(e) : 0;
+        return v < 5 || v > 95 ? 0 : v;
+    }();
+    if (forced) return forced;
+    return n <= (1 << 21) ? 25 : 40;
+}
+static bool split_wanted(int64_t n) { return n >= (1 << 19) && !getenv("PORLA_NO_SPLIT"); }
+
+// term count of the LARGEST part when an n-term MSM runs through msm_host_pipelined: the plan all parts share is
+// chosen for it
+static int64_t largest_part(int64_t n) {
+    if (!split_wanted(n)) return n;
+    const int64_t first = n * split_percent_for(n) / 100;
+    return first > n - first ? first : n - first;
+}
+
+void msm_host_pipelined(Staging& sg, int curve, const uint8_t* scalars, const uint8_t* points, int64_t n, int scalar_fmt,
+                        int point_fmt, const MsmPlan& plan, uint8_t* h_ws, int* nparts_out) {
+    auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const int nparts = split_wanted(n) ? 2 : 1;
+    const int64_t first_part = nparts == 2 ? n * split_percent_for(n) / 100 : n;
+    const int64_t part_len[2] = {first_part, n - first_part};
+    const size_t ws_bytes = (size_t)plan.nwin * 128;
+    // staging layout: scalars | raw points | table + endomorphism image (2 * 64 B per point) | flags | window sums
+    size_t sc_off = 0, pt_off = pad((size_t)n * 32), tab_off = pt_off + pad((size_t)n * 64), fl_off = tab_off + pad((size_t)n * 128),
+           ws_off = fl_off + pad((size_t)n);
+    uint8_t* d = sg.dev(ws_off + 2 * pad(ws_bytes));
+    cudaStream_t st = sg.stream, cs = sg.copy_stream;
+    MsmOptions opt;
+    opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
+    opt.out_fmt = point_fmt;
+    opt.shared_points = 1;
+    opt.window_bits = plan.c;
+    opt.glv = plan.glv;           // every part with the same layout: the window sums are added window by window
+    opt.no_fixed_base = 1;
+    opt.no_small = 1;
+    int64_t first = 0;
+    for (int h = 0; h < nparts; h++) {
+        const size_t a = (size_t)first, m = (size_t)part_len[h];
+        h2d_copy(d + sc_off + a * 32, scalars + a * 32, m * 32, cs);
+        h2d_copy(d + pt_off + a * 64, points + a * 64, m * 64, cs);
+        PORLA_CUDA(cudaEventRecord(sg.ev[h], cs));
+        PORLA_CUDA(cudaStreamWaitEvent(st, sg.ev[h], 0));
+        PointTable tab;
+        table_import_into(curve, d + pt_off + a * 64, point_fmt, (uint32_t)m, d + tab_off + a * 128, d + fl_off + a, &tab, st);
+        opt.d_window_sums = d + ws_off + h * pad(ws_bytes);
+        msm_device(curve, tab, d + sc_off + a * 32, (uint32_t)m, 1, opt, nullptr, nullptr, st);
+        first += part_len[h];
+    }
+    uint8_t* hbuf = sg.pinned((size_t)nparts * ws_bytes);
+    for (int h = 0; h < nparts; h++)
+        PORLA_CUDA(cudaMemcpyAsync(hbuf + h * ws_bytes, d + ws_off + h * pad(ws_bytes), ws_bytes, cudaMemcpyDeviceToHost, st));
+    PORLA_CUDA(cudaStreamSynchronize(st));
+    memcpy(h_ws, hbuf, (size_t)nparts * ws_bytes);
+    *nparts_out = nparts;
+}
+
+// ---------------------------------------------------------------------------- fan-out over the devices of the box
+static void device_ranges(int64_t n, int ndev, int64_t* first, int64_t* count) {
+    // contiguous ranges, the last device takes the remainder (Client.hpp:753-754)
+    const int64_t each = n / ndev;
+    for (int p = 0; p < ndev; p++) {
+        first[p] = each * p;
+        count[p] = p == ndev - 1 ? n - each * p : each;
+    }
+}
+
+void msm_host_fanout(int curve, const uint8_t* scalars, const uint8_t* points, int64_t n, int scalar_fmt, int point_fmt,
+                     int ndev, uint8_t* out64) {
+    int64_t first[kMaxDevices], count[kMaxDevices];
+    int nparts[kMaxDevices];
+    device_ranges(n, ndev, first, count);
+    const MsmPlan plan = msm_plan(curve, (uint32_t)largest_part(count[ndev - 1]), 1, 0);
+    const size_t ws_bytes = (size_t)plan.nwin * 128;
+    std::vector<uint8_t> ws((size_t)ndev * kMaxPartsPerDevice * ws_bytes);
+    run_on_devices(ndev, [&](int p) {
+        msm_host_pipelined(worker_staging(), curve, scalars + (size_t)first[p] * 32, points + (size_t)first[p] * 64, count[p],
+                           scalar_fmt, point_fmt, plan, ws.data() + (size_t)p * kMaxPartsPerDevice * ws_bytes, &nparts[p]);
+    });
+    // compact the parts (a device may have produced one or two) and combine: add window by window, Horner, normalise
+    std::vector<uint8_t> all;
+    all.reserve(ws.size());
+    int total = 0;
+    for (int p = 0; p < ndev; p++) {
+        const uint8_t* src = ws.data() + (size_t)p * kMaxPartsPerDevice * ws_bytes;
+        all.insert(all.end(), src, src + (size_t)nparts[p] * ws_bytes);
+        total += nparts[p];
+    }
+    finalize_host_parts(curve, all.data(), total, plan.nwin, plan.c, point_fmt, out64);
+}
+
+}  // namespace porla
+
+// ============================================================================ C-ABI: tables sharded over devices
+using namespace porla;
+
+struct porla_mtable {
+    int curve = 0;
+    int ndev = 0;
+    int64_t n = 0;
+    int devices[kMaxDevices] = {};
+    int64_t first[kMaxDevices] = {}, count[kMaxDevices] = {};
+    PointTable part[kMaxDevices];
+    uint8_t* d_scalars[kMaxDevices] = {};     // per-device scratch for host-scalar calls (count * 32 B)
+    uint8_t* d_ws[kMaxDevices] = {};          // per-device window sums
+};
+
+extern "C" {
+
+int porla_device_count(void) { return device_count(); }
+
+porla_mtable* porla_mtable_create(int curve, const void* h_points, int64_t n, int point_fmt, int ndev) {
+    device_init();
+    const int visible = device_count() > kMaxDevices ? kMaxDevices : device_count();
+    if (ndev <= 0) ndev = visible;
+    const bool oversubscribe = getenv("PORLA_OVERSUBSCRIBE_DEVICES") != nullptr;   // tests on a box with fewer GPUs
+    if ((ndev > visible && !oversubscribe) || ndev > kMaxDevices || n < 0 || n >= ((int64_t)1 << 31) * ndev) {
+        fprintf(stderr, "[libmultiexp/porla_b200] FATAL: porla_mtable_create: %d devices requested, %d visible (n = %lld)\n", ndev,
+                visible, (long long)n);
+        abort();
+    }
+    porla_mtable* mt = new porla_mtable();
+    mt->curve = curve;
+    mt->ndev = ndev;
+    mt->n = n;
+    device_ranges(n, ndev, mt->first, mt->count);
+    for (int p = 0; p < ndev; p++) mt->devices[p] = part_device(p);
+    const uint8_t* pts = (const uint8_t*)h_points;
+    run_on_devices(ndev, [&](int p) {
+        Staging& sg = worker_staging();
+        const size_t m = (size_t)mt->count[p];
+        uint8_t* d_tmp = nullptr;
+        PORLA_CUDA(cudaMalloc(&d_tmp, (m ? m : 1) * 64));
+        h2d_copy(d_tmp, pts + (size_t)mt->first[p] * 64, m * 64, sg.stream);
+        table_import_device(curve, d_tmp, point_fmt, (uint32_t)m, &mt->part[p], sg.stream);
+        PORLA_CUDA(cudaFree(d_tmp));
+        PORLA_CUDA(cudaMalloc(&mt->d_scalars[p], (m ? m : 1) * 32));
+        PORLA_CUDA(cudaMalloc(&mt->d_ws[p], 256 * 128));
+    });
+    return mt;
+}
+
+int porla_mtable_devices(const porla_mtable* mt) { return mt->ndev; }
+int64_t porla_mtable_len(const porla_mtable* mt) { return mt->n; }
+
+void porla_mtable_range(const porla_mtable* mt, int part, int* device, int64_t* first, int64_t* count) {
+    if (part < 0 || part >= mt->ndev) {
+        fprintf(stderr, "[libmultiexp/porla_b200] FATAL: porla_mtable_range: part %d of %d\n", part, mt->ndev);
+        abort();
+    }
+    *device = mt->devices[part];
+    *first = mt->first[part];
+    *count = mt->count[part];
+}
+
+// Shared body: scalars either in host memory (one array of n, copied range by range) or already resident
+// (d_scalars_per_part[p] on device p).
+static void mtable_msm(const porla_mtable* mt, const uint8_t* h_scalars, void* const* d_scalars_per_part, int scalar_fmt,
+                       int out_fmt, uint8_t* out64) {
+    if (mt->n == 0) {
+        memset(out64, 0, 64);
+        return;
+    }
+    int64_t largest = 0;
+    for (int p = 0; p < mt->ndev; p++) largest = mt->count[p] > largest ? mt->count[p] : largest;
+    const MsmPlan plan = msm_plan(mt->curve, (uint32_t)largest, 1, 0);
+    const size_t ws_bytes = (size_t)plan.nwin * 128;
+    std::vector<uint8_t> ws((size_t)mt->ndev * ws_bytes);
+    run_on_devices(mt->ndev, [&](int p) {
+        Staging& sg = worker_staging();
+        const size_t m = (size_t)mt->count[p];
+        const uint8_t* d_sc;
+        if (d_scalars_per_part) {
+            d_sc = (const uint8_t*)d_scalars_per_part[p];
+        } else {
+            h2d_copy(mt->d_scalars[p], h_scalars + (size_t)mt->first[p] * 32, m * 32, sg.stream);
+            d_sc = mt->d_scalars[p];
+        }
+        MsmOptions opt;
+        opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
+        opt.out_fmt = out_fmt;
+        opt.shared_points = 1;
+        opt.window_bits = plan.c;
+        opt.glv = plan.glv;
+        opt.no_fixed_base = 1;
+        opt.no_small = 1;
+        opt.d_window_sums = mt->d_ws[p];
+        if (m) msm_device(mt->curve, mt->part[p], d_sc, (uint32_t)m, 1, opt, nullptr, nullptr, sg.stream);
+        else PORLA_CUDA(cudaMemsetAsync(mt->d_ws[p], 0, ws_bytes, sg.stream));
+        uint8_t* h = sg.pinned(ws_bytes);
+        PORLA_CUDA(cudaMemcpyAsync(h, mt->d_ws[p], ws_bytes, cudaMemcpyDeviceToHost, sg.stream));
+        PORLA_CUDA(cudaStreamSynchronize(sg.stream));
+        memcpy(ws.data() + (size_t)p * ws_bytes, h, ws_bytes);
+    });
+    finalize_host_parts(mt->curve, ws.data(), mt->ndev, plan.nwin, plan.c, out_fmt, out64);
+}
+
+void porla_mtable_msm_host_scalars(const porla_mtable* mt, const void* h_scalars, int scalar_fmt, int out_fmt, void* out64) {
+    mtable_msm(mt, (const uint8_t*)h_scalars, nullptr, scalar_fmt, out_fmt, (uint8_t*)out64);
+}
+
+void porla_mtable_msm_resident(const porla_mtable* mt, void* const* d_scalars_per_part, int scalar_fmt, int out_fmt, void* out64) {
+    mtable_msm(mt, nullptr, d_scalars_per_part, scalar_fmt, out_fmt, (uint8_t*)out64);
+}
+
+void* porla_mtable_scalars_upload(const porla_mtable* mt, int part, const void* h_scalars_of_part) {
+    if (part < 0 || part >= mt->ndev) return nullptr;
+    void* d = nullptr;
+    DeviceScope scope(mt->devices[part]);
+    const size_t bytes = (size_t)(mt->count[part] ? mt->count[part] : 1) * 32;
+    PORLA_CUDA(cudaMalloc(&d, bytes));
+    PORLA_CUDA(cudaMemcpy(d, h_scalars_of_part, (size_t)mt->count[part] * 32, cudaMemcpyHostToDevice));
+    return d;
+}
+
+void porla_mtable_scalars_free(const porla_mtable* mt, int part, void* d_scalars) {
+    if (part < 0 || part >= mt->ndev || !d_scalars) return;
+    DeviceScope scope(mt->devices[part]);
+    PORLA_CUDA(cudaFree(d_scalars));
+}
+
+void porla_mtable_destroy(porla_mtable* mt) {
+    if (!mt) return;
+    run_on_devices(mt->ndev, [&](int p) {
+        table_free(&mt->part[p]);
+        if (mt->d_scalars[p]) PORLA_CUDA(cudaFree(mt->d_scalars[p]));
+        if (mt->d_ws[p]) PORLA_CUDA(cudaFree(mt->d_ws[p]));
+    });
+    delete mt;
+}
+
+void porla_msm_host_devices(int curve, const void* scalars, const void* points, int64_t n, int scalar_fmt, int point_fmt, int ndev,
+                            void* out64) {
+    device_init();
+    const int visible = device_count() > kMaxDevices ? kMaxDevices : device_count();
+    if (ndev <= 0) ndev = visible;
+    if (n < 0 || n >= ((int64_t)1 << 31) * ndev || ndev > kMaxDevices || (ndev > visible && !getenv("PORLA_OVERSUBSCRIBE_DEVICES"))) {
+        fprintf(stderr, "[libmultiexp/porla_b200] FATAL: porla_msm_host_devices: n = %lld over %d devices (%d visible)\n", (long long)n,
+                ndev, visible);
+        abort();
+    }
+    if (n == 0) {
+        memset(out64, 0, 64);
+        return;
+    }
+    if (n < ndev) ndev = (int)n;
+    msm_host_fanout(curve, (const uint8_t*)scalars, (const uint8_t*)points, n, scalar_fmt, point_fmt, ndev, (uint8_t*)out64);
+}
+
+uint64_t porla_debug_copy_ring_bytes(void) { return h2d_ring_bytes(); }
+
+}  // extern "C"

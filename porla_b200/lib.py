@@ -34,6 +34,9 @@ NEW_SYMBOLS = [
     "porla_butterfly_stage_device", "bn254_butterfly_stage", "bn254_align_mac_batch", "bn254_audit_aggregate", "porla_data_butterfly_stage", "porla_data_butterfly_stage_device",
     "porla_msm_table_host_scalars", "porla_msm_table_host_scalars_batch", "porla_secp256k1_table_create", "porla_secp256k1_ecmult_multi_table",
     "porla_debug_pairing_selfcheck", "porla_debug_latency", "porla_secp256k1_inner_product_prove", "porla_secp256k1_inner_product_verify",
+    "porla_device_count", "porla_mtable_create", "porla_mtable_devices", "porla_mtable_len", "porla_mtable_range",
+    "porla_mtable_msm_host_scalars", "porla_mtable_msm_resident", "porla_mtable_scalars_upload", "porla_mtable_scalars_free",
+    "porla_mtable_destroy", "porla_debug_copy_ring_bytes", "porla_msm_host_devices",
 ]
 
 
@@ -132,6 +135,18 @@ def load() -> C.CDLL:
         "porla_debug_field_mul": (None, [I, P, P, C.c_int64, P]),
         "porla_debug_field_op": (None, [I, I, P, P, C.c_int64, P]),
         "porla_debug_point_add_host": (None, [I, P, P, C.c_int64, I, P]),
+        "porla_device_count": (I, []),
+        "porla_mtable_create": (P, [I, P, C.c_int64, I, I]),
+        "porla_mtable_devices": (I, [P]),
+        "porla_mtable_len": (C.c_int64, [P]),
+        "porla_mtable_range": (None, [P, I, C.POINTER(I), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+        "porla_mtable_msm_host_scalars": (None, [P, P, I, I, P]),
+        "porla_mtable_msm_resident": (None, [P, C.POINTER(P), I, I, P]),
+        "porla_mtable_scalars_upload": (P, [P, I, P]),
+        "porla_mtable_scalars_free": (None, [P, I, P]),
+        "porla_mtable_destroy": (None, [P]),
+        "porla_debug_copy_ring_bytes": (C.c_uint64, []),
+        "porla_msm_host_devices": (None, [I, P, P, C.c_int64, I, I, I, P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -347,6 +362,70 @@ class Table:
         if self.handle:
             load().porla_table_destroy(C.c_void_p(self.handle))
             self.handle = 0
+
+
+def _as_void_p(buf):
+    """void* of a bytes-like object / ctypes buffer / integer address (caller keeps it alive)."""
+    if isinstance(buf, int):
+        return C.c_void_p(buf)
+    if isinstance(buf, bytes):
+        return C.cast(C.c_char_p(buf), C.c_void_p)
+    if isinstance(buf, bytearray):
+        return C.cast((C.c_ubyte * len(buf)).from_buffer(buf), C.c_void_p)
+    return C.cast(buf, C.c_void_p)
+
+
+class MultiTable:
+    """A point table resident in HBM and range-sharded over the GPUs of the box inside ONE process (the in-call
+    partition of Client.hpp:747-787 with devices in place of host threads)."""
+
+    def __init__(self, curve: int, points, n: int, point_fmt: int = POINT_BE64, ndev: int = 0):
+        self.curve, self.n = curve, n
+        self._keep = points
+        self.handle = load().porla_mtable_create(curve, _as_void_p(points), n, point_fmt, ndev)
+        self.ndev = int(load().porla_mtable_devices(C.c_void_p(self.handle)))
+
+    def part_range(self, part: int):
+        d, f, c = C.c_int(0), C.c_int64(0), C.c_int64(0)
+        load().porla_mtable_range(C.c_void_p(self.handle), part, C.byref(d), C.byref(f), C.byref(c))
+        return d.value, f.value, c.value
+
+    def msm_host_scalars(self, scalars, scalar_fmt: int = SCALAR_BE32, out_fmt: int = POINT_BE64) -> bytes:
+        out = (C.c_ubyte * 64)()
+        load().porla_mtable_msm_host_scalars(C.c_void_p(self.handle), _as_void_p(scalars), scalar_fmt, out_fmt, C.cast(out, C.c_void_p))
+        return bytes(out)
+
+    def upload_scalars(self, scalars: bytes):
+        """Per-part resident copies of an n x 32-byte scalar array; returns the handle list msm_resident takes."""
+        ptrs = []
+        for p in range(self.ndev):
+            _, first, count = self.part_range(p)
+            chunk = bytes(scalars[32 * first:32 * (first + count)])
+            ptrs.append(load().porla_mtable_scalars_upload(C.c_void_p(self.handle), p, _as_void_p(chunk)))
+        return ptrs
+
+    def free_scalars(self, ptrs) -> None:
+        for p, d in enumerate(ptrs):
+            load().porla_mtable_scalars_free(C.c_void_p(self.handle), p, C.c_void_p(d))
+
+    def msm_resident(self, ptrs, scalar_fmt: int = SCALAR_BE32, out_fmt: int = POINT_BE64) -> bytes:
+        out = (C.c_ubyte * 64)()
+        arr = (C.c_void_p * self.ndev)(*ptrs)
+        load().porla_mtable_msm_resident(C.c_void_p(self.handle), arr, scalar_fmt, out_fmt, C.cast(out, C.c_void_p))
+        return bytes(out)
+
+    def destroy(self) -> None:
+        if self.handle:
+            load().porla_mtable_destroy(C.c_void_p(self.handle))
+            self.handle = 0
+
+
+def msm_host_devices(curve: int, scalars, points, n: int, ndev: int = 0, scalar_fmt: int = SCALAR_BE32,
+                     point_fmt: int = POINT_BE64) -> bytes:
+    """One MSM from host buffers, its point range split over `ndev` GPUs inside the call (0 = all visible)."""
+    out = (C.c_ubyte * 64)()
+    load().porla_msm_host_devices(curve, _as_void_p(scalars), _as_void_p(points), n, scalar_fmt, point_fmt, ndev, C.cast(out, C.c_void_p))
+    return bytes(out)
 
 
 def msm_host(curve: int, scalars: bytes, points: bytes, n: int, nbatch: int = 1, scalar_fmt: int = SCALAR_BE32,
