@@ -44,8 +44,10 @@ def parse():
     ap.add_argument("--cpu-sample-log2n", type=int, default=22,
                     help="log2 size of the CPU-baseline sample (bounded by --log2n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep", default=os.environ.get("PORLA_BENCH_SWEEP", "16,24"),
+    ap.add_argument("--sweep", default=os.environ.get("PORLA_BENCH_SWEEP", "16,18,22,24,26"),
                     help="extra sizes (log2) timed at N=1 and reported under 'sweep'")
+    ap.add_argument("--strong", default=os.environ.get("PORLA_BENCH_STRONG", "20,24,26"),
+                    help="sizes (log2) of the ONE MSM sharded over all GPUs, reported under 'strong' (N > 1)")
     return ap.parse_args()
 
 
@@ -282,6 +284,162 @@ def porla_calls(lib, pb):
     return out
 
 
+# ------------------------------------------------------------------------------ strong scaling
+def _limbs_of(v, n=8):
+    return [(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
+
+
+def closed_form_inputs(torch, lo, hi, a, b, dev):
+    """Points (i + 1) G (as 32-byte multipliers) and scalars a i + b for i in [lo, hi): the MSM over [0, n) has the closed
+    form [a (n-1) n (n+1) / 3 + b n (n+1) / 2] G whatever the sharding (tests/test_gpu_fullsize.py)."""
+    i = torch.arange(lo, hi, dtype=torch.int64, device=dev)
+    ks = torch.zeros((hi - lo, 8), dtype=torch.int32, device=dev)
+    ks[:, 0] = (i + 1).to(torch.int32)
+    ss = torch.empty((hi - lo, 8), dtype=torch.int32, device=dev)
+    carry = torch.zeros(hi - lo, dtype=torch.int64, device=dev)
+    for j, (al, bl) in enumerate(zip(_limbs_of(a), _limbs_of(b))):
+        v = i * al + bl + carry
+        lo32 = v & 0xFFFFFFFF
+        carry = v >> 32
+        ss[:, j] = (lo32 - ((lo32 >> 31) << 32)).to(torch.int32)
+    return ks, ss
+
+
+def closed_form_bytes(n, a, b):
+    from oracle import curves_py as O
+    total = (a * ((n - 1) * n * (n + 1) // 3) + b * (n * (n + 1) // 2)) % O.BN254.n
+    return O.bn254_marshal(O.mul(O.BN254, total, (1, 2)))
+
+
+def strong_scaling(args, lib, pb, torch, dist, rank, world, dev, stream, barrier):
+    """ONE MSM of 2^k terms (k in --strong) over all `world` GPUs: every rank holds the contiguous range
+    shard_range(2^k, world, rank) resident, runs the pipeline up to its window sums, one all-gather, rank 0 combines.  The
+    result is asserted equal to the closed form.  speedup_vs_n1 = the same MSM on rank 0's GPU alone (same run, same
+    inputs) / the sharded time.  At world == 1 only the single-GPU time is reported."""
+    import random
+    from porla_b200.sharding import ShardedMsm, shard_range
+    out = {}
+    for lg in [int(x) for x in args.strong.split(",") if x]:
+        n = 1 << lg
+        rnd = random.Random(1000 + lg)
+        a = rnd.getrandbits(228) | (1 << 227) | 1
+        b = rnd.getrandbits(255) | (1 << 254)
+        want = closed_form_bytes(n, a, b) if rank == 0 else None
+        steps = max(3, min(args.steps, 6 if lg >= 26 else 10))
+        entry = {"terms": n}
+
+        def run(world_eff, r_eff, active):
+            """time the MSM sharded over world_eff ranks (ranks >= world_eff idle); returns ms per MSM"""
+            if not active:
+                barrier()
+                barrier()
+                return None, None
+            lo, hi = shard_range(n, world_eff, r_eff)
+            ks, ss = closed_form_inputs(torch, lo, hi, a, b, dev)
+            tab = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks.data_ptr(), hi - lo, pb.SCALAR_LE32, on_device=True, stream=stream)
+            del ks
+            torch.cuda.synchronize()
+            if world_eff == 1:
+                res = [None]
+
+                def one():
+                    res[0] = tab.msm_resident(ss.data_ptr(), hi - lo, scalar_fmt=pb.SCALAR_LE32, stream=stream)
+            else:
+                eng = ShardedMsm(pb.CURVE_BN254, n, world_eff, r_eff, dist, dev)
+                res = [None]
+
+                def one():
+                    res[0] = eng.msm(tab, ss.data_ptr(), hi - lo, pb.SCALAR_LE32)
+            for _ in range(3):
+                one()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(steps):
+                one()
+            e1.record()
+            barrier()
+            wall = (time.perf_counter() - t0) * 1e3
+            ms = max(wall, e0.elapsed_time(e1)) / steps
+            tab.destroy()
+            return ms, res[0]
+
+        if world > 1:
+            ms_n, got = run(world, rank, True)
+            t = torch.tensor([ms_n], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_n = float(t.item())
+            if rank == 0 and got != want:
+                raise SystemExit("bench self-check failed: %d-rank sharded 2^%d MSM differs from the closed form" % (world, lg))
+            entry["ms_sharded"] = ms_n
+            entry["points_per_s_sharded"] = n / (ms_n * 1e-3)
+        # the same MSM on one GPU (rank 0 alone; the other ranks wait at the barriers inside run())
+        ms_1, got1 = run(1, 0, rank == 0)
+        if rank == 0:
+            if got1 != want:
+                raise SystemExit("bench self-check failed: single-GPU 2^%d MSM differs from the closed form" % lg)
+            entry["ms_n1"] = ms_1
+            entry["points_per_s_n1"] = n / (ms_1 * 1e-3)
+            entry["checked"] = "closed form, bit-exact"
+            if world > 1:
+                entry["speedup_vs_n1"] = ms_1 / entry["ms_sharded"]
+        out["2^%d" % lg] = entry
+    return out
+
+
+def strong_scaling_in_library(args, lib, pb, torch, ndev):
+    """The same question answered by the library alone: ONE process, `ndev` devices, the in-call partition of multi.cu
+    (porla_mtable: table range-sharded at creation; resident scalars, and host scalars crossing PCIe on every call)."""
+    import random
+    out = {}
+    for lg in [int(x) for x in args.strong.split(",") if x]:
+        if lg > 24:
+            continue
+        n = 1 << lg
+        rnd = random.Random(1000 + lg)
+        a = rnd.getrandbits(228) | (1 << 227) | 1
+        b = rnd.getrandbits(255) | (1 << 254)
+        want = closed_form_bytes(n, a, b)
+        ks, ss = closed_form_inputs(torch, 0, n, a, b, torch.device("cuda", torch.cuda.current_device()))
+        tab = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks.data_ptr(), n, pb.SCALAR_LE32, on_device=True)
+        del ks
+        pts = torch.empty(n * 64, dtype=torch.uint8).pin_memory()
+        lib.porla_table_export(C.c_void_p(tab.handle), pb.POINT_BE64, C.c_void_p(pts.data_ptr()), 0, None)
+        tab.destroy()
+        sc_host = ss.cpu().pin_memory()
+        del ss
+        torch.cuda.synchronize()
+        entry = {"terms": n, "devices": ndev}
+        mt = pb.MultiTable(pb.CURVE_BN254, pts.data_ptr(), n, ndev=ndev)
+        ptrs = mt.upload_scalars(bytes(sc_host.numpy().tobytes()))
+        steps = max(3, min(args.steps, 10))
+        for name, fn in (("resident", lambda: mt.msm_resident(ptrs, scalar_fmt=pb.SCALAR_LE32)),
+                         ("host_scalars", lambda: mt.msm_host_scalars(sc_host.data_ptr(), scalar_fmt=pb.SCALAR_LE32))):
+            for _ in range(3):
+                got = fn()
+            if got != want:
+                raise SystemExit("bench self-check failed: in-library %d-device 2^%d MSM (%s) differs from the closed form" % (ndev, lg, name))
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fn()
+            entry["ms_" + name] = (time.perf_counter() - t0) / steps * 1e3
+        mt.free_scalars(ptrs)
+        mt.destroy()
+        # everything from host buffers: points and scalars cross PCIe on every call, each device copies its own range
+        for _ in range(2):
+            got = pb.msm_host_devices(pb.CURVE_BN254, sc_host.data_ptr(), pts.data_ptr(), n, ndev, scalar_fmt=pb.SCALAR_LE32)
+        if got != want:
+            raise SystemExit("bench self-check failed: in-library host-buffer fan-out differs from the closed form")
+        t0 = time.perf_counter()
+        for _ in range(3):
+            pb.msm_host_devices(pb.CURVE_BN254, sc_host.data_ptr(), pts.data_ptr(), n, ndev, scalar_fmt=pb.SCALAR_LE32)
+        entry["ms_host_buffers"] = (time.perf_counter() - t0) / 3 * 1e3
+        entry["checked"] = "closed form, bit-exact"
+        out["2^%d" % lg] = entry
+    return out
+
+
 # ------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -296,6 +454,7 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")    # host-side waits that must not park a kernel on the idle GPUs
     lib = pb.load()
     lib.porla_device_init()
     dev = torch.device("cuda", local)
@@ -316,19 +475,10 @@ def run_ours(args):
         scalars = [torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device=dev, generator=g) for _ in range(SCALAR_SETS)]
         return n, table, scalars, ks
 
-    from porla_b200.sharding import gather_window_sums
+    from porla_b200.sharding import ShardedMsm
 
     out_host = (C.c_ubyte * 64)()
-    plan = {}
-
-    def get_plan(n):
-        if n not in plan:
-            c_, w_ = C.c_int(0), C.c_int(0)
-            lib.porla_msm_plan(pb.CURVE_BN254, n, 1, 0, C.byref(c_), C.byref(w_))
-            wsum = torch.zeros(w_.value * 128, dtype=torch.uint8, device=dev)
-            host = torch.zeros(world * w_.value * 128, dtype=torch.uint8).pin_memory()
-            plan[n] = (c_.value, w_.value, wsum, host)
-        return plan[n]
+    engines = {}
 
     def step(table, scalars, n, i):
         """One MSM over all world*n points; the 64-byte result lands in host memory on rank 0."""
@@ -338,15 +488,11 @@ def run_ours(args):
             lib.porla_msm_resident(C.c_void_p(table.handle), C.c_void_p(sc.data_ptr()), n, pb.SCALAR_LE32, 0, pb.POINT_BE64,
                                    C.cast(out_host, C.c_void_p), C.c_void_p(stream))
             return
-        c_, nwin, wsum, host = get_plan(n)
-        lib.porla_msm_window_sums_device(C.c_void_p(table.handle), C.c_void_p(sc.data_ptr()), n, pb.SCALAR_LE32, c_,
-                                         C.c_void_p(wsum.data_ptr()), C.c_void_p(stream))
-        allw = gather_window_sums(wsum, world, dist)           # the only exchange: nwin*128 B per rank
-        if rank == 0:
-            host.copy_(allw, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            lib.porla_msm_finalize_host(pb.CURVE_BN254, C.c_void_p(host.data_ptr()), world, nwin, c_, pb.POINT_BE64,
-                                        C.cast(out_host, C.c_void_p))
+        if n not in engines:
+            engines[n] = ShardedMsm(pb.CURVE_BN254, world * n, world, rank, dist, dev)
+        res = engines[n].msm(table, sc.data_ptr(), n, pb.SCALAR_LE32)     # the only exchange: nwin*128 B per rank
+        if res is not None:
+            C.memmove(out_host, res, 64)
 
     def timed(table, scalars, n, steps, warmup):
         for i in range(warmup):
@@ -438,6 +584,18 @@ def run_ours(args):
         # all-device path (device finaliser) -- cheap self-checks of the three routes
         step(table, scalars, n, 0)
         barrier()
+        if world > 1:
+            # the sharded result (window sums of all ranks combined) must equal the sum of the ranks' own complete results:
+            # each rank's compute_multi_exp above ran its range alone (inputs of scalar set 0) and returned a canonical point
+            part = torch.frombuffer(bytearray(bytes(res)), dtype=torch.uint8).to(dev)
+            allp = torch.zeros(64 * world, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allp, part)
+            if rank == 0:
+                acc = bytearray(allp[:64].cpu().numpy().tobytes())
+                for r in range(1, world):
+                    pb.bn254_add(acc, allp[64 * r:64 * r + 64].cpu().numpy().tobytes())
+                if bytes(acc) != bytes(out_host):
+                    raise SystemExit("bench self-check failed: %d-rank sharded MSM differs from the sum of the per-rank results" % world)
         if world == 1:
             if bytes(out_host) != bytes(res):
                 raise SystemExit("bench self-check failed: resident MSM and compute_multi_exp disagree")
@@ -446,6 +604,25 @@ def run_ours(args):
             torch.cuda.synchronize()
             if bytes(d_out.cpu().numpy().tobytes()) != bytes(res):
                 raise SystemExit("bench self-check failed: device-finalised MSM and compute_multi_exp disagree")
+
+    # ---- strong scaling: ONE MSM sharded over all ranks, checked against its closed form (all ranks take part)
+    strong = None
+    if args.strong and world > 1:
+        lib.porla_measure_pint(1, 0.1)
+        strong = strong_scaling(args, lib, pb, torch, dist, rank, world, dev, stream, barrier)
+    strong_lib = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+        # ... and by the library alone: rank 0's process drives all `world` devices (the other ranks idle at the barrier)
+        if rank == 0:
+            try:
+                strong_lib = strong_scaling_in_library(args, lib, pb, torch, min(world, lib.porla_device_count()))
+            except SystemExit:
+                raise
+            except Exception as exc:
+                strong_lib = {"error": repr(exc)}
+        dist.barrier(group=cpu_group)    # (an NCCL barrier would spin a kernel on the very devices rank 0 is driving)
 
     if rank != 0:
         if world > 1:
@@ -554,6 +731,8 @@ def run_ours(args):
             "stage_ms": stages,
         },
         "cpu_baseline": cpu,
+        "strong": strong,
+        "strong_in_library": strong_lib,
         "sweep": sweep,
         "resident_fixed_base": fixed_base,
         "secp256k1_config4": secp,
