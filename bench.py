@@ -284,6 +284,86 @@ def porla_calls(lib, pb):
     return out
 
 
+def config1_replay():
+    """BASELINE configs[0] ("Porla update/audit latency"): tools/replay_config1 (C++, built against the reference's own
+    libmultiexp.h when that tree was present at build time) replays the MAC-side C-ABI call census of ./Client 1024 --
+    1024 updates (the last rebuilds C) and 100 audits -- through the legacy per-call symbols, through the batched symbols,
+    and (a bounded prefix: the cpu_baseline leg) against the CPU restatement.  Runs in its own process."""
+    exe = os.path.join(ROOT, "tools", "replay_config1")
+    if not os.path.exists(exe):
+        return {"unavailable": "tools/replay_config1 not built (make)"}
+    try:
+        cmd = [exe, "--blocks", "1024", "--audits", "100", "--oracle", os.path.join(ROOT, "oracle", "liboracle_bn254.so"),
+               "--cpu-updates", "128", "--cpu-audits", "5"]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        if p.returncode != 0:
+            return {"error": "replay_config1 exit %d: %s" % (p.returncode, (p.stdout + p.stderr)[-400:])}
+        d = json.loads(p.stdout)
+        d["cpu_note"] = "the cpu pass is the first 128 updates and 5 audits against oracle/liboracle_bn254.so (C restatement, 8-thread " \
+                        "pool as the reference); create_proof / verify_proof run in the library in every pass"
+        return d
+    except Exception as exc:
+        return {"error": repr(exc)}
+
+
+def config3_block(lib, pb, torch, stream):
+    """BASELINE configs[2]: 4096 commitments of 2^12 terms over one shared 4096-point table in one launch sequence, at the
+    full shape, through the shipped path (wide-window look-up table when ~85 GB of HBM are free, else the general batched
+    pipeline).  Inputs with a closed form; a sample of the 4096 results is checked bit-exactly."""
+    import random
+    from oracle import curves_py as O
+    n, nb = 1 << 12, 4096
+    rnd = random.Random(33)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ks = torch.zeros((n, 8), dtype=torch.int32, device=dev)
+    ks[:, 0] = torch.arange(1, n + 1, dtype=torch.int64, device=dev).to(torch.int32)
+    tab = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks.data_ptr(), n, pb.SCALAR_LE32, on_device=True, stream=stream)
+    coef = [(rnd.getrandbits(240) | 1, rnd.getrandbits(255)) for _ in range(nb)]
+    ss = torch.empty((nb * n, 8), dtype=torch.int32, device=dev)
+    for m, (a, b) in enumerate(coef):
+        ss[m * n:(m + 1) * n] = closed_form_inputs(torch, 0, n, a, b, dev)[1]
+    out = torch.zeros(64 * nb, dtype=torch.uint8, device=dev)
+    res = {"workload": "4096 MSMs x 2^12 terms over one shared 4096-point table, one launch sequence (BASELINE.json configs[2])"}
+
+    def timed_ms(reps=3):
+        for _ in range(2):
+            tab.msm_device(ss.data_ptr(), n, out.data_ptr(), nbatch=nb, scalar_fmt=pb.SCALAR_LE32, shared_points=True, stream=stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            tab.msm_device(ss.data_ptr(), n, out.data_ptr(), nbatch=nb, scalar_fmt=pb.SCALAR_LE32, shared_points=True, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def check(label):
+        got = out.cpu().numpy().tobytes()
+        s2, s1 = (n - 1) * n * (n + 1) // 3, n * (n + 1) // 2
+        for m in (0, 1, nb // 3, nb - 1):
+            a, b = coef[m]
+            if got[64 * m:64 * m + 64] != O.bn254_marshal(O.mul(O.BN254, (a * s2 + b * s1) % O.BN254.n, (1, 2))):
+                raise SystemExit("bench self-check failed: config-3 result %d (%s) differs from the closed form" % (m, label))
+
+    ms = timed_ms()
+    check("general batched pipeline")
+    res["general_pipeline"] = {"ms": ms, "points_per_s": nb * n / (ms * 1e-3)}
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b > 100e9:
+        t0 = time.perf_counter()
+        c = tab.precompute(0, n, nb)
+        torch.cuda.synchronize()
+        pre_ms = (time.perf_counter() - t0) * 1e3
+        ms = timed_ms()
+        check("look-up table")
+        nwin = (254 + 1 + c - 1) // c
+        res["lookup_table"] = {"window_bits": c, "ms": ms, "points_per_s": nb * n / (ms * 1e-3), "table_bytes": nwin * n * (1 << (c - 1)) * 64,
+                               "table_build_ms_once": pre_ms}
+    res["checked"] = "4 of the 4096 results against their closed form, bit-exact (all 4096: tests/test_gpu_fullsize.py)"
+    tab.destroy()
+    return res
+
+
 # ------------------------------------------------------------------------------ strong scaling
 def _limbs_of(v, n=8):
     return [(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
@@ -690,6 +770,19 @@ def run_ours(args):
         except Exception as exc:
             calls = {"error": repr(exc)}
 
+    # ---- BASELINE config 3 at full shape, and config 1 replayed by the C++ harness
+    config3 = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            config3 = config3_block(lib, pb, torch, stream)
+        except SystemExit:
+            raise
+        except Exception as exc:
+            config3 = {"error": repr(exc)}
+    config1 = None
+    if world == 1 and not args.no_cpu_baseline:
+        config1 = config1_replay()
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -737,6 +830,8 @@ def run_ours(args):
         "resident_fixed_base": fixed_base,
         "secp256k1_config4": secp,
         "porla_calls": calls,
+        "config3_batched": config3,
+        "porla_config1": config1,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

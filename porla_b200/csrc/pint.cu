@@ -4,6 +4,8 @@
 //   0  mad.wide.u32, 8 independent 64-bit accumulators/thread        (IMAD.WIDE.U32)
 //   1  mad.lo.cc / madc.hi.cc carry chains, the mix the field code uses (IMAD.WIDE.U32.X + carry preds)
 //   2  mad.lo.u32 (plain 32-bit IMAD, a 32x32->32 multiply-add), for comparison only
+//   3  fma.rz.f64 (DFMA), 8 independent accumulators: returns DFMA/s
+//   4  8 DFMA + 8 IMAD.WIDE per iteration in every thread: returns the rate of EACH kind (pairs/s)
 // Measured on B200: variants 0/1 ~ 9.2e12 /s (32 lanes/clk/SM: IMAD.WIDE issues at half the rate of
 // the 32-bit IMAD), variant 2 ~ 1.84e13 /s (64 lanes/clk/SM).  The roofline unit "MAC32" is a full
 // 32x32->64 multiply-accumulate, i.e. variant 1.
@@ -84,6 +86,53 @@ __global__ void __launch_bounds__(256) k_pint_lo(uint32_t seed, uint64_t* out) {
     if (s == 0x1234567u) out[0] = s;
 }
 
+// 3: fma.rz.f64, 8 independent accumulators per thread (DFMA; the double-precision route to 52-bit limb products)
+__global__ void __launch_bounds__(256) k_pint_dfma(uint32_t seed, uint64_t* out) {
+    double a = 1.0 + (double)(seed ^ (threadIdx.x * 2654435761u)) * 1e-12, b = 1.0 + (double)(blockIdx.x + 1) * 1e-9;
+    double acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = (double)k;
+    for (int it = 0; it < kIters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(acc[k]) : "d"(a), "d"(b));
+        b += 1e-9;
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += acc[k];
+    if (s == 0.1234567) out[0] = (uint64_t)s;
+}
+
+// 4: both at once -- 8 DFMA and 8 IMAD.WIDE per iteration in every thread: do the two pipes overlap?
+__global__ void __launch_bounds__(256) k_pint_mixed(uint32_t seed, uint64_t* out) {
+    double a = 1.0 + (double)(seed ^ (threadIdx.x * 2654435761u)) * 1e-12, b = 1.0 + (double)(blockIdx.x + 1) * 1e-9;
+    uint32_t ia = seed ^ (threadIdx.x * 2654435761u), ib = seed + blockIdx.x * 40503u + 1u;
+    double acc[8];
+    uint64_t iacc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        acc[k] = (double)k;
+        iacc[k] = (uint64_t)(ia + k) << 7;
+    }
+    for (int it = 0; it < kIters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(acc[k]) : "d"(a), "d"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(iacc[k]) : "r"(ia + (uint32_t)k), "r"(ib));
+        }
+        b += 1e-9;
+        ib += 2;
+    }
+    double s = 0;
+    uint64_t t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        s += acc[k];
+        t ^= iacc[k];
+    }
+    if (s == 0.1234567 || t == 0x1234567ull) out[0] = (uint64_t)s + t;
+}
+
 }  // namespace
 
 extern "C" double porla_measure_pint(int variant, double min_seconds) {
@@ -104,6 +153,8 @@ extern "C" double porla_measure_pint(int variant, double min_seconds) {
         for (int r = 0; r < reps; r++) {
             if (variant == 0) k_pint_wide<<<blocks, threads>>>(12345u + r, d_out);
             else if (variant == 1) k_pint_chain<<<blocks, threads>>>(12345u + r, d_out);
+            else if (variant == 3) k_pint_dfma<<<blocks, threads>>>(12345u + r, d_out);
+            else if (variant == 4) k_pint_mixed<<<blocks, threads>>>(12345u + r, d_out);
             else k_pint_lo<<<blocks, threads>>>(12345u + r, d_out);
         }
     };
