@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 #include <shared_mutex>
+#include <thread>
 #include <random>
 #include <vector>
 
@@ -870,11 +871,48 @@ void porla_butterfly_stage_device(porla_table* t, int64_t m, const void* twiddle
     }
 }
 
+// A stage of at most this many butterflies runs on the calling host (up to 8 threads), like the single-point symbols it
+// replaces: one butterfly is a dependent chain of ~127 doublings and additions, 1.4 ms on one GPU thread against 0.1 ms on a
+// host core, so the device only wins once there are enough butterflies to fill it (measured with tools/replay_config1:
+// Porla's per-update hierarchy rebuilds issue stages of 1 .. 512 butterflies).  PORLA_HOST_BUTTERFLIES overrides (0: always device).
+static int64_t host_butterfly_limit() {
+    const char* e = getenv("PORLA_HOST_BUTTERFLIES");
+    return e ? (int64_t)atoll(e) : (int64_t)96;
+}
+
+static void butterfly_stage_host(uint8_t* pts, int64_t n, int64_t m, const uint8_t* tw) {
+    const int64_t m2 = m / 2, nb = n / 2;
+    auto body = [&](int64_t lo, int64_t hi) {
+        for (int64_t b = lo; b < hi; b++) {
+            const int64_t j = b % m2, k = (b / m2) * m + j;
+            G1A a0 = G1A::inf(), a1 = G1A::inf();
+            g1_unmarshal(pts + 64 * k, 64, &a0);
+            g1_unmarshal(pts + 64 * (k + m2), 64, &a1);
+            const G1A t = g1_mul(a1, elem_from_be<Fr>(tw + 32 * j, 32));
+            g1_marshal(g1_add(a0, t), pts + 64 * k);
+            g1_marshal(g1_add(a0, t.neg()), pts + 64 * (k + m2));
+        }
+    };
+    const int64_t nt = nb >= 16 ? 8 : (nb >= 4 ? 4 : 1);
+    if (nt == 1) {
+        body(0, nb);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int64_t t = 0; t < nt; t++) th.emplace_back(body, nb * t / nt, nb * (t + 1) / nt);
+    for (auto& x : th) x.join();
+}
+
 void bn254_butterfly_stage(GoSlice* points, GoInt n, GoInt m, GoSlice* twiddles) {
     if (n < 0 || points->len < n * 64 || twiddles->len < (m / 2) * 32)
         die("bn254_butterfly_stage: slices shorter than n points / m/2 twiddles");
+    if (m < 2 || (m & (m - 1)) || n % m) die("bn254_butterfly_stage: m must be a power of two dividing n");
     if (n == 0) return;
     check_shape(n, 1, "bn254_butterfly_stage");
+    if (n / 2 <= host_butterfly_limit()) {
+        butterfly_stage_host((uint8_t*)points->data, n, m, (const uint8_t*)twiddles->data);
+        return;
+    }
     device_init();
     std::lock_guard<std::mutex> lock(g_io_mu);
     g_stage.init();

@@ -31,7 +31,8 @@ namespace {
 
 constexpr size_t kRingChunk = 1u << 20;        // bytes per pinned slot
 constexpr int kRingSlots = 3;                  // slots per copy thread
-constexpr size_t kRingThreshold = 256u << 10;  // smaller pageable copies go through the driver's own staging
+constexpr size_t kRingThreshold = 4u << 20;    // smaller pageable copies go through the driver's own staging (a hand-off to the
+                                               // copy threads costs ~0.1 ms: measured on the 1 MiB audit aggregation call)
 
 std::atomic<uint64_t> g_ring_bytes{0};
 

@@ -84,26 +84,24 @@ def test_host_buffer_fanout_matches_single_device(curve):
 
 
 def test_pageable_buffers_go_through_the_copy_ring():
-    """compute_multi_exp with ordinary heap buffers (what utils.h:277-292 passes): the points and scalars reach the device
-    through the pinned ring, the result is that of the oracle; the same call with pinned buffers bypasses the ring."""
+    """The host-buffer MSM with ordinary heap buffers (what utils.h:277-292 passes): large pageable buffers reach the device
+    through the pinned ring of the copy pool, the result is that of the oracle; pinned buffers bypass the ring."""
     import torch
     lib = pb.load()
-    n = 1 << 15
+    n = 1 << 17
     pts, sc = _inputs(n, 77)
-    want = loader.bn254_msm(sc, pts, n, 4)
+    want = loader.bn254_msm(sc, pts, n, 8)
+    b_sc, b_pt = bytearray(sc), bytearray(pts)                          # bytearrays: pageable
     before = lib.porla_debug_copy_ring_bytes()
-    assert pb.bn254_multi_exp(pts, sc, n) == want                      # bytearrays: pageable
-    moved = lib.porla_debug_copy_ring_bytes() - before
-    assert moved == n * 96
+    assert pb.msm_host_devices(pb.CURVE_BN254, b_sc, b_pt, n, 1) == want
+    assert lib.porla_debug_copy_ring_bytes() - before == n * 96
     h_sc = torch.frombuffer(bytearray(sc), dtype=torch.uint8).pin_memory()
     h_pt = torch.frombuffer(bytearray(pts), dtype=torch.uint8).pin_memory()
-    out = bytearray(64)
-    gs = [pb.GoSlice(h_sc.data_ptr(), n * 32, n * 32), pb.GoSlice(h_pt.data_ptr(), n * 64, n * 64),
-          pb.GoSlice(C.cast((C.c_ubyte * 64).from_buffer(out), C.c_void_p).value, 64, 64)]
     before = lib.porla_debug_copy_ring_bytes()
-    lib.compute_multi_exp(C.byref(gs[0]), C.byref(gs[1]), n, C.byref(gs[2]))
-    assert bytes(out) == want
+    assert pb.msm_host_devices(pb.CURVE_BN254, h_sc.data_ptr(), h_pt.data_ptr(), n, 1) == want
     assert lib.porla_debug_copy_ring_bytes() == before
+    # the legacy symbol over the same pageable buffers
+    assert pb.bn254_multi_exp(pts, sc, n) == want
 
 
 def _closed_form_inputs(torch, n, lo, hi, a, b, device):

@@ -275,7 +275,11 @@ def _butterfly_oracle(c, pts, m, tw):
     return out
 
 
-def test_butterfly_stage_host_buffers_match_oracle_with_edge_cases():
+@pytest.mark.parametrize("route", ["host_threads", "device"])
+def test_butterfly_stage_host_buffers_match_oracle_with_edge_cases(route, monkeypatch):
+    """bn254_butterfly_stage runs small stages on the calling host (like the single-point symbols it replaces) and large
+    ones on the device; both routes on the same inputs."""
+    monkeypatch.setenv("PORLA_HOST_BUTTERFLIES", "0" if route == "device" else "1000000")
     rnd = random.Random(77)
     n, m = 16, 4
     pts = bn254_points(n)

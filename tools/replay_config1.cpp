@@ -756,9 +756,22 @@ int main(int argc, char** argv) {
     bool cpu_equal = true;
     if (have_cpu && passes[2].updates == n_blocks) {
         cpu_equal = passes[2].final_state == passes[0].final_state;
-        for (size_t j = 0; cpu_equal && j < passes[2].replies.size(); j++)
-            cpu_equal = passes[2].replies[j].combined_mac == passes[0].replies[j].combined_mac &&
-                        passes[2].replies[j].combined_align == passes[0].replies[j].combined_align;
+        if (!cpu_equal) {
+            size_t bad = 0, first = 0;
+            for (size_t i = 0; i < passes[0].final_state.size(); i++)
+                if (!(passes[0].final_state[i] == passes[2].final_state[i])) {
+                    if (!bad) first = i;
+                    bad++;
+                }
+            fprintf(stderr, "cpu pass: %zu of %zu state entries differ, first at %zu\n", bad, passes[0].final_state.size(), first);
+        }
+        for (size_t j = 0; cpu_equal && j < passes[2].replies.size() && j < passes[0].replies.size(); j++)
+        {
+            const bool m = passes[2].replies[j].combined_mac == passes[0].replies[j].combined_mac;
+            const bool a = passes[2].replies[j].combined_align == passes[0].replies[j].combined_align;
+            if (!m || !a) fprintf(stderr, "cpu pass: audit %zu differs (combined_mac %d, combined_align %d)\n", j, (int)m, (int)a);
+            cpu_equal = m && a;
+        }
     }
     printf("{\n  \"workload\": \"Porla KZG mode, %d data blocks, NUM_CHUNKS = 128, TOP_CACHING_LEVEL = 10: %d updates (the last one "
            "rebuilds C) then %d audits; MAC-side C-ABI call census of SURVEY.md Appendix C\",\n",
