@@ -158,6 +158,7 @@ using SecpFpCompact = Fp<Secp256k1FpParams, true>;
 struct Bn254 {
     using F = Bn254Fp;
     using FC = Bn254FpCompact;  // same layout, non-inlined multiplier (cold kernels)
+    static constexpr int kFieldBits = 254;      // bit length of the base-field modulus
     static constexpr int kScalarBits = 254;     // bits the window recoder covers (r < 2^254)
     static constexpr bool kHalveScalar = false;
     // GLV: phi(x, y) = (beta x, y) = lambda (x, y) with beta^3 = 1 in Fp, lambda^3 = 1 mod r.  A scalar k splits as
@@ -205,6 +206,7 @@ struct Secp256k1 {
     using FC = SecpFpCompact;
     // n is just below 2^256: scalars above n/2 are recoded as -(n - s), so 255 magnitude bits (plus the
     // carry of the signed digits) span exactly 16 windows of 16 bits instead of 17 with a 1-bit top window.
+    static constexpr int kFieldBits = 256;
     static constexpr int kScalarBits = 255;
     static constexpr bool kHalveScalar = true;
     // no GLV here: the split halves of a secp256k1 scalar reach 2^128 (they need 129 bits with the signed digits'

@@ -11,6 +11,8 @@
 //   mode 5  acc.add(q)    XYZZ + XYZZ, outlined multiplier (FC)
 //   mode 6  acc.madd(p)   XYZZ + affine, inlined
 //   mode 7  acc = acc.dbl(), inlined
+//   mode 8  x = 1/x + y    binary-GCD inversion (fp_inv.cuh);   mode 9: the same with the Fermat inversion
+//   mode + 100: the same chain on the whole device (4 blocks per SM): ns_per_op is then the time per operation of a thread under load
 // Measured (B200, BN254): 838 cycles per product with one warp per scheduler whether the thread runs one,
 // two or four independent chains -- also with the two products interleaved round by round at source level
 // (tried and removed) -- against ~600 cycles per product when two warps share a scheduler: the lone warp is
@@ -72,12 +74,18 @@ __global__ void k_latency(int mode, int iters, const Affine<typename C::F>* __re
     } else if (mode == 6) {
 #pragma unroll 1
         for (int i = 0; i < iters; i++) acc.madd_finite(q);
-    } else {
+    } else if (mode == 7) {
 #pragma unroll 1
         for (int i = 0; i < iters; i++) acc = acc.dbl();
+    } else if (mode == 8) {   // binary-GCD inversion (fp_inv.cuh), a dependent chain
+#pragma unroll 1
+        for (int i = 0; i < iters; i++) x0 = x0.inverse() + y;
+    } else {                  // Fermat inversion, for comparison
+#pragma unroll 1
+        for (int i = 0; i < iters; i++) x0 = x0.inverse_fermat() + y;
     }
     const long long t1 = clock64();
-    if (threadIdx.x % 32 == 0) cycles[threadIdx.x / 32] = (unsigned long long)(t1 - t0);
+    if (threadIdx.x % 32 == 0 && blockIdx.x == 0) cycles[threadIdx.x / 32] = (unsigned long long)(t1 - t0);
     acc.x = acc.x + x0 + x1 + x2 + x3;
     if (acc.x.v[0] == 0x12345678u && acc.y.v[1] == 0x9abcdef0u) *sink = acc;   // keep the work alive
 }
@@ -87,6 +95,16 @@ __global__ void k_latency(int mode, int iters, const Affine<typename C::F>* __re
 extern "C" int porla_debug_latency(int curve, int mode, int warps, int iters, double* cycles_per_op, double* ns_per_op) {
     using namespace porla;
     device_init();
+    // mode + 100: the same chain in `warps` warps per block on 4 blocks per SM of the whole device (throughput under load)
+    int blocks = 1;
+    if (mode >= 100) {
+        mode -= 100;
+        cudaDeviceProp prop;
+        int dev = 0;
+        PORLA_CUDA(cudaGetDevice(&dev));
+        PORLA_CUDA(cudaGetDeviceProperties(&prop, dev));
+        blocks = prop.multiProcessorCount * 4;
+    }
     if (warps < 1) warps = 1;
     if (warps > 32) warps = 32;
     // four affine points: small multiples of the generator, built on the host side of the library
@@ -105,10 +123,10 @@ extern "C" int porla_debug_latency(int curve, int mode, int warps, int iters, do
     for (int rep = 0; rep < 3; rep++) {
         PORLA_CUDA(cudaEventRecord(e0));
         if (curve == kCurveBn254)
-            k_latency<Bn254><<<1, warps * 32>>>(mode, iters, reinterpret_cast<const Affine<Bn254::F>*>(pts), d_cycles,
+            k_latency<Bn254><<<blocks, warps * 32>>>(mode, iters, reinterpret_cast<const Affine<Bn254::F>*>(pts), d_cycles,
                                                reinterpret_cast<XYZZ<Bn254::F>*>(d_sink));
         else
-            k_latency<Secp256k1><<<1, warps * 32>>>(mode, iters, reinterpret_cast<const Affine<Secp256k1::F>*>(pts), d_cycles,
+            k_latency<Secp256k1><<<blocks, warps * 32>>>(mode, iters, reinterpret_cast<const Affine<Secp256k1::F>*>(pts), d_cycles,
                                                    reinterpret_cast<XYZZ<Secp256k1::F>*>(d_sink));
         PORLA_CUDA(cudaEventRecord(e1));
         PORLA_CUDA(cudaEventSynchronize(e1));

@@ -11,6 +11,7 @@
 #include "msm.h"
 #include "msm_kernels.cuh"
 #include "small_kernels.cuh"
+#include "affine_kernels.cuh"
 
 namespace porla {
 
@@ -242,6 +243,18 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     if (L < 16) L = 16;
     if (L > 64) L = 64;
     if (const char* e = getenv("PORLA_SLICE_LEN")) { if (atoi(e) >= 2) L = (uint32_t)atoi(e); }
+    // Accumulation in affine coordinates with shared inversions (affine_kernels.cuh): slices of 64 pairs reduced as a tree,
+    // 1 or 2 batched rounds.  PORLA_ACC_AFFINE = number of rounds (0: the XYZZ kernel).
+    int aff_rounds = 0;
+    {
+        const char* e = getenv("PORLA_ACC_AFFINE");
+        const bool big = pairs_cap >= (uint64_t)148 * PORLA_AFF_MIN_BLOCKS * kAffThreads * kAffL * 2;
+        const int want = e ? atoi(e) : (big ? kAffDefaultRounds : 0);
+        if (want > 0) {
+            aff_rounds = want > 2 ? 2 : want;
+            L = kAffL;
+        }
+    }
     const uint32_t nslices_cap = (uint32_t)((pairs_cap + L - 1) / L);
     // One serial XYZZ addition is ~7 us of latency: with few slices in flight (small MSMs) a bucket cut into
     // dozens of slices is better finished by a cooperating block; with the machine full, the serial loop in
@@ -365,8 +378,12 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         }
         }
         g_stage_timer.mark(kStageAccumulate, stream);
-        k_accumulate<C><<<(nslices_cap + kAccThreads - 1) / kAccThreads, kAccThreads, 0, stream>>>(
-            points, reinterpret_cast<const F*>(table.d_phi_x), sh.phi_off, sorted, grand, L, buckets, part_head, part_tail);
+        if (aff_rounds > 0)
+            k_accumulate_affine<C><<<(nslices_cap + kAffThreads - 1) / kAffThreads, kAffThreads, 0, stream>>>(
+                points, reinterpret_cast<const F*>(table.d_phi_x), sh.phi_off, sorted, grand, buckets, part_head, part_tail, aff_rounds);
+        else
+            k_accumulate<C><<<(nslices_cap + kAccThreads - 1) / kAccThreads, kAccThreads, 0, stream>>>(
+                points, reinterpret_cast<const F*>(table.d_phi_x), sh.phi_off, sorted, grand, L, buckets, part_head, part_tail);
         LAUNCHED();
         if (getenv("PORLA_STITCH_COMPACT"))
             k_stitch<C, FC><<<(nslices_cap + 63) / 64, 64, 0, stream>>>(sorted, grand, L, (XC*)buckets, (const XC*)part_head,
