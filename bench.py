@@ -58,7 +58,7 @@ def workload_name(log2n, world):
 
 # ------------------------------------------------------------------------------ CPU reference arm
 def cpu_port_rate(log2n: int, threads: int, steps: int = 1, warmup: int = 0):
-    """points/s of the C restatement (oracle/bn254_oracle.c) on a 2^log2n sample of the workload."""
+    """points/s of the C restatement (oracle/bn254_oracle.c) on a 2^log2n sample of the workload (best step)."""
     from oracle import loader, curves_py as O
     import hashlib
     n = 1 << log2n
@@ -82,11 +82,11 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     log2s = min(args.log2n, args.cpu_sample_log2n)
-    steps = max(1, min(args.steps, 5))
-    rate, sec = cpu_port_rate(log2s, threads, steps=steps, warmup=min(args.warmup, 1))
+    steps, warm = max(1, args.steps), max(0, args.warmup)     # the same K and W as our arm; every step one bounded sample
+    rate, sec = cpu_port_rate(log2s, threads, steps=steps, warmup=warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "points/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 / u64x4 Montgomery (integer)", "data": "synthetic",
         "config": {"workload": workload_name(args.log2n, 1),
                    "note": "CPU arm: C restatement of gnark-crypto v0.6.0 MultiExp (oracle/bn254_oracle.c), NOT gnark-crypto "
@@ -364,6 +364,47 @@ def config3_block(lib, pb, torch, stream):
     return res
 
 
+def distributions_block(lib, pb, torch, stream, table, ks, n, steps):
+    """Secondary scalar distributions of SURVEY.md 8(d), timed on the headline table (resident inputs): 31-bit audit
+    coefficients (Client.hpp:700), and an adversarial mix -- 1 % zero scalars, 1 % points at infinity, 1 % duplicate
+    points.  The slices of k_accumulate have equal length whatever the digit distribution, so these should cost no more
+    than the uniform case."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev)
+    g.manual_seed(99)
+    out = (C.c_ubyte * 64)()
+
+    def time_ms(tab, sc):
+        for _ in range(3):
+            lib.porla_msm_resident(C.c_void_p(tab.handle), C.c_void_p(sc.data_ptr()), n, pb.SCALAR_LE32, 0, pb.POINT_BE64,
+                                   C.cast(out, C.c_void_p), C.c_void_p(stream))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            lib.porla_msm_resident(C.c_void_p(tab.handle), C.c_void_p(sc.data_ptr()), n, pb.SCALAR_LE32, 0, pb.POINT_BE64,
+                                   C.cast(out, C.c_void_p), C.c_void_p(stream))
+        return (time.perf_counter() - t0) / steps * 1e3
+
+    res = {}
+    sc31 = torch.zeros((n, 8), dtype=torch.int32, device=dev)
+    sc31[:, 0] = torch.randint(0, 2**31 - 1, (n,), dtype=torch.int32, device=dev, generator=g)
+    ms = time_ms(table, sc31)
+    res["scalars_31bit"] = {"ms": ms, "points_per_s": n / (ms * 1e-3)}
+    # adversarial mix: the table's multipliers with 1 % zeros (k = 0: infinity) and 1 % duplicates (k_i = k_0)
+    ks2 = ks.clone()
+    r = torch.rand(n, device=dev, generator=g)
+    ks2[r < 0.01] = 0
+    ks2[(r >= 0.01) & (r < 0.02)] = ks2[0]
+    tab2 = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks2.data_ptr(), n, pb.SCALAR_LE32, on_device=True, stream=stream)
+    sc = torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device=dev, generator=g)
+    sc[torch.rand(n, device=dev, generator=g) < 0.01] = 0
+    ms = time_ms(tab2, sc)
+    res["adversarial_mix"] = {"ms": ms, "points_per_s": n / (ms * 1e-3), "points_at_infinity": tab2.num_infinity,
+                              "what": "1 % zero scalars, 1 % points at infinity, 1 % duplicate points"}
+    tab2.destroy()
+    return res
+
+
 # ------------------------------------------------------------------------------ strong scaling
 def _limbs_of(v, n=8):
     return [(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
@@ -609,7 +650,7 @@ def run_ours(args):
     value = world * n / (ms_step * 1e-3)
 
     # ---- roofline of the dominant kernel, measured live with CUDA events on the launch stream
-    p_int = lib.porla_measure_pint(1, 0.25) if rank == 0 else 0.0
+    p_int = lib.porla_measure_pint(1, 1.0) if rank == 0 else 0.0
     lib.porla_stage_timing_enable(1)
     stage = (C.c_float * 8)()
     acc_ms, stage_sum = [], None
@@ -660,6 +701,38 @@ def run_ours(args):
         dt = float(t.item())
         e2e = {"value": world * n / dt, "unit": "points/s", "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": 64,
                "ms_per_step": dt * 1e3, "api": "compute_multi_exp(GoSlice*, GoSlice*, GoInt, GoSlice*) with pinned host buffers"}
+        if world == 1:
+            # (a) the same call with PAGEABLE buffers -- ordinary heap memory, what the reference's callers pass (`new[]`
+            # arrays, Client.hpp:124-127): the library moves them through its pinned-ring copy pool (multi.cu)
+            pg_sc, pg_pt = sc_host.numpy().copy(), pts_host.numpy().copy()
+            gp_sc = pb.GoSlice(pg_sc.ctypes.data, n * 32, n * 32)
+            gp_pt = pb.GoSlice(pg_pt.ctypes.data, n * 64, n * 64)
+            res_pg = (C.c_ubyte * 64)()
+            gp_out = pb.GoSlice(C.cast(res_pg, C.c_void_p), 64, 64)
+            for _ in range(2):
+                lib.compute_multi_exp(C.byref(gp_sc), C.byref(gp_pt), n, C.byref(gp_out))
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                lib.compute_multi_exp(C.byref(gp_sc), C.byref(gp_pt), n, C.byref(gp_out))
+            dtp = (time.perf_counter() - t0) / e2e_steps
+            if bytes(res_pg) != bytes(res):
+                raise SystemExit("bench self-check failed: pageable and pinned compute_multi_exp disagree")
+            e2e["pageable"] = {"value": n / dtp, "ms_per_step": dtp * 1e3, "vs_pinned": dt / dtp,
+                               "api": "the same call over numpy (pageable) buffers"}
+            # (b) resident table, HOST scalars: only the 32-byte scalars cross PCIe (an SRS / generator table uploaded once)
+            res_rt = (C.c_ubyte * 64)()
+            for _ in range(2):
+                lib.porla_msm_table_host_scalars(C.c_void_p(table.handle), 0, C.c_void_p(sc_host.data_ptr()), n, pb.SCALAR_BE32,
+                                                 pb.POINT_BE64, C.cast(res_rt, C.c_void_p))
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                lib.porla_msm_table_host_scalars(C.c_void_p(table.handle), 0, C.c_void_p(sc_host.data_ptr()), n, pb.SCALAR_BE32,
+                                                 pb.POINT_BE64, C.cast(res_rt, C.c_void_p))
+            dtr = (time.perf_counter() - t0) / e2e_steps
+            if bytes(res_rt) != bytes(res):
+                raise SystemExit("bench self-check failed: resident-table / host-scalar MSM and compute_multi_exp disagree")
+            e2e["resident_table_host_scalars"] = {"value": n / dtr, "ms_per_step": dtr * 1e3, "h2d_bytes_per_step": n * 32,
+                                                  "api": "porla_msm_table_host_scalars (pinned scalars)"}
         # the resident-path result of the same scalars must equal the C-ABI result, and so must the
         # all-device path (device finaliser) -- cheap self-checks of the three routes
         step(table, scalars, n, 0)
@@ -721,6 +794,15 @@ def run_ours(args):
                                   "whole_msm_frac_of_imad_peak": n2 * MAC32_PER_POINT / (ms2 * 1e-3) / p_int}
             t2.destroy()
 
+    dists = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            dists = distributions_block(lib, pb, torch, stream, table, ks, n, max(3, min(args.steps, 10)))
+            dists["scalars_uniform_256bit"] = {"ms": ms_step, "points_per_s": value,
+                                               "what": "the headline: uniform 256-bit values, reduced mod r on the device (fr.SetBytes semantics)"}
+        except Exception as exc:
+            dists = {"error": repr(exc)}
+
     # ---- the same MSM when the resident table is treated as a fixed base (an SRS): its window expansion 2^(20 w) P_i is
     # built once (13 x 64 MiB), all windows then share one bucket set and 13 instead of 16 windows are enough.  Reported
     # beside the headline, which keeps the general path (arbitrary points, nothing precomputed from them).
@@ -750,9 +832,12 @@ def run_ours(args):
         threads = os.cpu_count() or 1
         lgs = min(args.log2n, args.cpu_sample_log2n)
         rate, sec = cpu_port_rate(lgs, threads)
+        lg1 = min(lgs, 18)
+        rate1, sec1 = cpu_port_rate(lg1, 1)
         cpu = {"value": rate, "unit": "points/s", "cores": threads, "kind": "port",
                "sample": "one 2^%d-point BN254 MSM (%.2f s) with the C restatement of gnark-crypto MultiExp, "
-                         "window-parallel over %d threads" % (lgs, sec, threads)}
+                         "window-parallel over %d threads" % (lgs, sec, threads),
+               "one_thread": {"value": rate1, "cores": 1, "sample": "one 2^%d-point MSM (%.2f s)" % (lg1, sec1)}}
 
     # ---- BASELINE config 4 beside it: secp256k1, 2^18 terms, against the REAL reference
     # (secp256k1_ecmult_multi_var of the vendored library compiled unmodified into oracle/_ref)
@@ -791,7 +876,7 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     traffic = None
     try:   # DRAM bytes of one k_accumulate launch at this size, from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01g_traffic.json")))["k_accumulate<Bn254>"].get(str(args.log2n))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["k_accumulate<Bn254>"].get(str(args.log2n))
     except Exception:
         pass
     macs = n * MAC32_PER_POINT
@@ -824,6 +909,7 @@ def run_ours(args):
             "stage_ms": stages,
         },
         "cpu_baseline": cpu,
+        "scalar_distributions": dists,
         "strong": strong,
         "strong_in_library": strong_lib,
         "sweep": sweep,

@@ -179,6 +179,8 @@ void porla_msm_host_devices(int curve, const void* scalars, const void* points, 
 /* Bytes that reached the device through the pinned-ring copy pool so far (host buffers that are not page-locked,
  * which is what the reference's callers pass: `new[]` arrays, Client.hpp:124-127). */
 uint64_t porla_debug_copy_ring_bytes(void);
+/* GB/s of the library's host-to-device copy path for a caller-provided host buffer (development aid). */
+double porla_debug_h2d_rate(const void* h_src, uint64_t bytes, int reps);
 
 /* Host-buffer MSM (H2D + import + MSM + D2H inside): what compute_multi_exp and the secp256k1
  * adapter are built on.  out: nbatch*64 B. */

@@ -221,9 +221,8 @@ void msm_host_core(int curve, const uint8_t* scalars, const uint8_t* points, int
     StageLease lease = lease_stage(n, nbatch);
     Staging& sg = *lease.s;
     if (nbatch == 1 && n >= (1 << 19) && !getenv("PORLA_NO_SPLIT")) {
-        // two pipelined parts: the copy of the second hides under the kernels of the first (multi.cu)
-        const int64_t first = n * (n <= (1 << 21) ? 25 : 40) / 100;
-        const MsmPlan plan = msm_plan(curve, (uint32_t)(first > n - first ? first : n - first), 1, 0);
+        // streamed: the terms cross PCIe in parts that are accumulated into one bucket set as they arrive (multi.cu)
+        const MsmPlan plan = msm_plan(curve, (uint32_t)n, 1, 0);
         std::vector<uint8_t> ws((size_t)kMaxPartsPerDevice * plan.nwin * 128);
         int nparts = 0;
         msm_host_pipelined(sg, curve, scalars, points, n, scalar_fmt, point_fmt, plan, ws.data(), &nparts);

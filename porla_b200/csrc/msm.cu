@@ -347,6 +347,8 @@ MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits, int gl
     return p;
 }
 
+size_t msm_bucket_bytes(const MsmPlan& plan) { return ((size_t)plan.nwin << (plan.c - 1)) * 128; }
+
 // ---------------------------------------------------------------------------- host finaliser
 template <class F64>
 static void finalize_host_impl(const void* h_window_sums, int nparts, int nwin, int c, int out_fmt, uint8_t* out64) {

@@ -100,7 +100,14 @@ struct MsmOptions {
     // Server.hpp:1077-1078) run concurrently on their own streams.
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    // Streamed MSM (multi.cu: msm_host_pipelined): the terms arrive in parts, every part is recoded, sorted and accumulated
+    // by its own call INTO ONE shared bucket array, and only the last call reduces the buckets.  part_mode: 0 a whole MSM,
+    // 1 first part (clears the buckets), 2 middle part, 3 last part (accumulates, then reduces).  d_buckets: the shared
+    // array, msm_bucket_bytes() bytes; every part must use the same window layout (window_bits and glv forced).
+    int part_mode = 0;
+    void* d_buckets = nullptr;
 };
+enum : int { kPartWhole = 0, kPartFirst = 1, kPartMiddle = 2, kPartLast = 3 };
 
 enum PlanMode : int { kPlanPipeline = 0, kPlanBits = 1, kPlanLut = 2 };
 struct MsmPlan {
@@ -111,6 +118,8 @@ struct MsmPlan {
 };
 // The sort / accumulate / reduce pipeline's plan for n terms.
 MsmPlan msm_plan(int curve, uint32_t n, uint32_t nbatch, int window_bits, int glv = -1);
+// Bytes of the bucket array of ONE MSM under a pipeline plan (nwin bucket sets of 2^(c-1) XYZZ records).
+size_t msm_bucket_bytes(const MsmPlan& plan);
 // Plan for a specific call.  Fixed-base expansion applicable: nwin = 1 (a single shared bucket set or the
 // look-up table, one "window sum" per MSM, no doublings), c = the expansion's window size.  Few terms in
 // total and no explicit window size: one window per scalar bit (k_small_bits), c = 1.

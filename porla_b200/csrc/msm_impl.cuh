@@ -182,6 +182,11 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     sh.n = n;
     sh.nbatch = nbatch;
     sh.shared = opt.shared_points ? 1u : 0u;
+    const bool streamed = opt.part_mode != kPartWhole;
+    if (streamed && (nbatch != 1 || !opt.d_buckets || opt.window_bits <= 0 || opt.glv < 0 || !opt.no_fixed_base)) {
+        fprintf(stderr, "[libmultiexp/porla_b200] FATAL: a streamed MSM part needs one MSM, a shared bucket array and a forced window layout\n");
+        abort();
+    }
     const bool fixed = table.fb_c > 0 && opt.shared_points && !opt.no_fixed_base &&
                        (opt.window_bits == 0 || opt.window_bits == table.fb_c);
     const MsmPlan wplan = fixed ? MsmPlan{table.fb_c, 1, kPlanPipeline, 0} : msm_plan(curve, n, nbatch, opt.window_bits, opt.glv);
@@ -250,7 +255,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         const char* e = getenv("PORLA_ACC_AFFINE");
         const bool big = pairs_cap >= (uint64_t)148 * PORLA_AFF_MIN_BLOCKS * kAffThreads * kAffL * 2;
         const int want = e ? atoi(e) : (big ? kAffDefaultRounds : 0);
-        if (want > 0) {
+        if (want > 0 && !streamed) {
             aff_rounds = want > 2 ? 2 : want;
             L = kAffL;
         }
@@ -272,7 +277,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     StageTimer& g_stage_timer = cx.timer;
     std::lock_guard<std::mutex> lock(cx.engine_mu);
     size_t need = (radix ? Arena::padded(pairs_cap, 8) + Arena::padded(ncoarse, 4) : 0) + Arena::padded(nbt, 4) * 2 + Arena::padded(ntiles + 1, 4) + 512 +
-                  Arena::padded(pairs_cap, 8) + Arena::padded(nbt, sizeof(XYZZ<F>)) +
+                  Arena::padded(pairs_cap, 8) + (streamed ? 0 : Arena::padded(nbt, sizeof(XYZZ<F>))) +
                   2 * Arena::padded(nslices_cap, sizeof(XYZZ<F>)) + Arena::padded(long_cap, 8) +
                   Arena::padded(slots * blocks_per_slot, sizeof(XYZZ<F>)) + Arena::padded(slots, sizeof(XYZZ<F>));
     g_arena.acquire(stream);
@@ -286,7 +291,8 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     uint2* sorted = g_arena.take<uint2>(pairs_cap);
     uint2* part = radix ? g_arena.take<uint2>(pairs_cap) : nullptr;
     uint32_t* coarse_cursor = radix ? g_arena.take<uint32_t>(ncoarse) : nullptr;
-    XYZZ<F>* buckets = g_arena.take<XYZZ<F>>(nbt);
+    XYZZ<F>* buckets = streamed ? reinterpret_cast<XYZZ<F>*>(opt.d_buckets) : g_arena.take<XYZZ<F>>(nbt);
+    const int into = opt.part_mode == kPartMiddle || opt.part_mode == kPartLast;
     XYZZ<F>* part_head = g_arena.take<XYZZ<F>>(nslices_cap);
     XYZZ<F>* part_tail = g_arena.take<XYZZ<F>>(nslices_cap);
     uint2* long_runs = g_arena.take<uint2>(long_cap);
@@ -304,7 +310,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     PORLA_CUDA(cudaMemsetAsync(counters, 0, (size_t)nbt * 4, stream));
     PORLA_CUDA(cudaMemsetAsync(grand, 0, 4, stream));
     PORLA_CUDA(cudaMemsetAsync(long_count, 0, 4, stream));
-    PORLA_CUDA(cudaMemsetAsync(buckets, 0, (size_t)nbt * sizeof(XYZZ<F>), stream));  // empty bucket = infinity
+    if (!into) PORLA_CUDA(cudaMemsetAsync(buckets, 0, (size_t)nbt * sizeof(XYZZ<F>), stream));  // empty bucket = infinity
     if (total_scalars) {
         uint32_t grid = (uint32_t)((total_scalars + 255) / 256);
         if (grid > 148u * 32u) grid = 148u * 32u;
@@ -383,7 +389,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
                 points, reinterpret_cast<const F*>(table.d_phi_x), sh.phi_off, sorted, grand, buckets, part_head, part_tail, aff_rounds);
         else
             k_accumulate<C><<<(nslices_cap + kAccThreads - 1) / kAccThreads, kAccThreads, 0, stream>>>(
-                points, reinterpret_cast<const F*>(table.d_phi_x), sh.phi_off, sorted, grand, L, buckets, part_head, part_tail);
+                points, reinterpret_cast<const F*>(table.d_phi_x), sh.phi_off, sorted, grand, L, buckets, part_head, part_tail, into);
         LAUNCHED();
         if (getenv("PORLA_STITCH_COMPACT"))
             k_stitch<C, FC><<<(nslices_cap + 63) / 64, 64, 0, stream>>>(sorted, grand, L, (XC*)buckets, (const XC*)part_head,
@@ -401,6 +407,13 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         g_stage_timer.mark(kStageAccumulate, stream);
     }
     g_stage_timer.mark(kStageReduce, stream);
+    if (opt.part_mode == kPartFirst || opt.part_mode == kPartMiddle) {   // the last part reduces the shared buckets
+        g_stage_timer.mark(kStageFinalize, stream);
+        g_stage_timer.mark(kNumStages, stream);
+        g_arena.release(stream);
+        PORLA_CUDA(cudaGetLastError());
+        return;
+    }
     if (slots * blocks_per_slot >= (1ull << 31)) {
         fprintf(stderr, "[libmultiexp/porla_b200] FATAL: too many window slots for one launch\n");
         abort();

@@ -756,12 +756,29 @@ PORLA_D Affine<typename C::F> load_signed_point(const Affine<typename C::F>* __r
     return p;
 }
 
+// `into` != 0 (a later part of a streamed MSM, msm_host_pipelined): the buckets already hold the sums of the earlier parts;
+// the thread that owns the START of a bucket's run continues from that value (one more mixed addition per bucket and part)
+// instead of starting from the first point, so that all parts of the MSM share one bucket set and one reduction.  The
+// stored value only seeds the accumulator: the loop keeps ONE call site of the mixed addition (three inlined copies of it
+// overflow the instruction cache -- measured: 2.4x slower per pair).
+template <class F>
+PORLA_D XYZZ<F> bucket_seed(const XYZZ<F>* __restrict__ buckets, uint32_t key, int into) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (into) {   // plain loads: written by the previous part's kernels on this stream
+        const uint4* s = reinterpret_cast<const uint4*>(buckets + key);
+        uint4* d = reinterpret_cast<uint4*>(&acc);
+#pragma unroll
+        for (int i = 0; i < 8; i++) d[i] = s[i];
+    }
+    return acc;
+}
+
 template <class C>
 __global__ void __launch_bounds__(kAccThreads, PORLA_ACC_MIN_BLOCKS)
 k_accumulate(const Affine<typename C::F>* __restrict__ points, const typename C::F* __restrict__ phi_x, uint32_t phi_off,
              const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_pairs, uint32_t L,
              XYZZ<typename C::F>* __restrict__ buckets, XYZZ<typename C::F>* __restrict__ part_head,
-             XYZZ<typename C::F>* __restrict__ part_tail) {
+             XYZZ<typename C::F>* __restrict__ part_tail, int into) {
     using F = typename C::F;
     const uint32_t M = *total_pairs;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -772,25 +789,22 @@ k_accumulate(const Affine<typename C::F>* __restrict__ points, const typename C:
     const uint32_t prev_key = start > 0 ? __ldg(&sorted[start - 1].x) : 0xffffffffu;
     const uint32_t next_key = end < M ? __ldg(&sorted[end].x) : 0xffffffffu;
 
-    uint2 e = __ldg(&sorted[start]);
-    uint32_t key = e.x;
+    uint32_t key = __ldg(&sorted[start].x);
     bool first = true;  // still inside the first bucket of this slice
-    Affine<F> p = load_signed_point<C>(points, phi_x, phi_off, e.y);
-    XYZZ<F> acc{p.x, p.y, F::one(), F::one()};
-    for (uint32_t pos = start + 1; pos < end; ++pos) {
-        e = __ldg(&sorted[pos]);
-        Affine<F> q = load_signed_point<C>(points, phi_x, phi_off, e.y);
+    // the run's first pair lies in this slice unless the bucket continues from the left (then the owner slice seeded it)
+    XYZZ<F> acc = prev_key == key ? XYZZ<F>::inf() : bucket_seed<F>(buckets, key, into);
+    for (uint32_t pos = start; pos < end; ++pos) {
+        const uint2 e = __ldg(&sorted[pos]);
+        const Affine<F> q = load_signed_point<C>(points, phi_x, phi_off, e.y);
         if (e.x != key) {
             if (first && prev_key == key) st16(part_head + t, acc);
             else st16(buckets + key, acc);
             first = false;
             key = e.x;
-            acc = XYZZ<F>{q.x, q.y, F::one(), F::one()};
-        } else if (acc.is_inf()) {
-            acc = XYZZ<F>{q.x, q.y, F::one(), F::one()};
-        } else {
-            acc.madd_finite(q);
+            acc = bucket_seed<F>(buckets, key, into);
         }
+        if (acc.is_inf()) acc = XYZZ<F>{q.x, q.y, F::one(), F::one()};
+        else acc.madd_finite(q);
     }
     if (first && prev_key == key) st16(part_head + t, acc);        // continues from the left (maybe also to the right)
     else if (next_key == key) st16(part_tail + t, acc);            // starts here, continues to the right

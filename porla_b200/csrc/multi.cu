@@ -2,6 +2,7 @@
 #include "multi.h"
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -29,7 +30,12 @@ bool host_pointer_is_pinned(const void* p) {
 
 namespace {
 
-constexpr size_t kRingChunk = 1u << 20;        // bytes per pinned slot
+// bytes per pinned slot (PORLA_COPY_CHUNK_KB to tune)
+static const size_t kRingChunk = [] {
+    const char* e = getenv("PORLA_COPY_CHUNK_KB");
+    const size_t kb = e && atoi(e) >= 64 ? (size_t)atoi(e) : 1024;
+    return kb << 10;
+}();
 constexpr int kRingSlots = 3;                  // slots per copy thread
 constexpr size_t kRingThreshold = 4u << 20;    // smaller pageable copies go through the driver's own staging (a hand-off to the
                                                // copy threads costs ~0.1 ms: measured on the 1 MiB audit aggregation call)
@@ -91,7 +97,9 @@ class CopyPool {
     CopyPool() {
         const char* e = getenv("PORLA_COPY_THREADS");
         int hw = (int)std::thread::hardware_concurrency();
-        nthreads_ = e && atoi(e) > 0 ? atoi(e) : (hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1));
+        // measured on the GPU box (16 vCPUs, tools/h2d_probe.py): 4 threads 29 GB/s, 8 threads 22 GB/s, 16 threads 18 GB/s -- the copy
+        // into the ring, the DMA out of it and the source reads share the host's memory bandwidth
+        nthreads_ = e && atoi(e) > 0 ? atoi(e) : (hw >= 8 ? 4 : (hw >= 4 ? 2 : 1));
         if (nthreads_ > 32) nthreads_ = 32;
     }
     void start_threads_locked() {
@@ -262,70 +270,68 @@ int fanout_devices(int64_t n) {
 }
 
 // ---------------------------------------------------------------------------- pipelined host-buffer MSM (one device)
-// The first part's copy is exposed, the second part's hides behind the first MSM: a smaller first part shortens
-// the exposed copy as long as the second copy still fits under the first MSM (PORLA_SPLIT_PERCENT to tune).
-// Measured at 2^20 (pinned buffers, one B200): 50 % 5.20 ms, 40 % 5.13, 35 % 4.98, 30 % 4.83, 25 % 4.73, 20 % 4.90,
-// one pass 5.48.  Above 2^21 the copy of the second part (1.75 ns per term) no longer fits under a quarter-size
-// MSM (~2.7 ns per term), so the first part grows to 40 %.  Worth it from 2^19 terms (below that the second bucket
-// reduction costs more than the copy it hides).
-static int split_percent_for(int64_t n) {
-    static const int forced = [] {
-        const char* e = getenv("PORLA_SPLIT_PERCENT");
-        int v = e ? atoi(e) : 0;
-        return v < 5 || v > 95 ? 0 : v;
-    }();
-    if (forced) return forced;
-    return n <= (1 << 21) ? 25 : 40;
-}
-static bool split_wanted(int64_t n) { return n >= (1 << 19) && !getenv("PORLA_NO_SPLIT"); }
-
-// term count of the LARGEST part when an n-term MSM runs through msm_host_pipelined: the plan all parts share is
-// chosen for it
-static int64_t largest_part(int64_t n) {
-    if (!split_wanted(n)) return n;
-    const int64_t first = n * split_percent_for(n) / 100;
-    return first > n - first ? first : n - first;
+// The terms of a large call cross PCIe in several parts; every part is imported, recoded, sorted and accumulated INTO ONE
+// shared bucket array as soon as it has arrived (MsmOptions::part_mode), while the next part is being copied; the buckets
+// are reduced once, after the last part.  Only the first part's copy is exposed, and a slow source (pageable memory through
+// the pinned ring: ~29 GB/s on the GPU box against ~54 GB/s for pinned buffers, tools/h2d_probe.py) hides behind the
+// kernels of the previous part as long as a part's copy is not longer than its kernels.  Round 1 ran two independent
+// MSMs (25 % + 75 % of the terms) and added their window sums: 4.79 ms at 2^20 with pinned buffers, 6.98 ms with pageable ones.
+// Every part pays one extra mixed addition per non-empty bucket (it continues from the stored sum) and ~15 launches, so a
+// part should hold at least 2^18 terms and bring at least ~8 pairs to each bucket.  Measured (one B200, pinned buffers,
+// tools/e2e_stages.py), whole call: 2^20 -- 1 part 5.54 ms, 2 parts 4.90, 4 parts 4.85, 8 parts 5.36; 2^22 -- 19.4 / 16.1 /
+// 15.0 (4 parts); 2^24 -- 73.1 / 59.1 / 52.5 (4 parts).
+static int stream_parts_for(int64_t n, const MsmPlan& plan) {
+    const char* e = getenv("PORLA_STREAM_PARTS");     // (read per call: the tests force small MSMs through the streamed path)
+    const int forced = e ? atoi(e) : 0;
+    if (forced >= 1 && forced <= 8) return n >= forced ? forced : 1;
+    if (n < (1 << 19) || getenv("PORLA_NO_SPLIT")) return 1;
+    const int64_t per_bucket = (n * (plan.glv ? 2 : 1)) >> (plan.c - 1);
+    int64_t p = per_bucket / 8;
+    if (p > (n >> 18)) p = n >> 18;
+    return p < 1 ? 1 : (p > 8 ? 8 : (int)p);
 }
 
 void msm_host_pipelined(Staging& sg, int curve, const uint8_t* scalars, const uint8_t* points, int64_t n, int scalar_fmt,
                         int point_fmt, const MsmPlan& plan, uint8_t* h_ws, int* nparts_out) {
     auto pad = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const int nparts = split_wanted(n) ? 2 : 1;
-    const int64_t first_part = nparts == 2 ? n * split_percent_for(n) / 100 : n;
-    const int64_t part_len[2] = {first_part, n - first_part};
+    const int nparts = stream_parts_for(n, plan);
     const size_t ws_bytes = (size_t)plan.nwin * 128;
-    // staging layout: scalars | raw points | table + endomorphism image (2 * 64 B per point) | flags | window sums
+    const size_t bk_bytes = nparts > 1 ? msm_bucket_bytes(plan) : 0;
+    // staging layout: scalars | raw points | table + endomorphism image (2 * 64 B per point) | flags | window sums | buckets
     size_t sc_off = 0, pt_off = pad((size_t)n * 32), tab_off = pt_off + pad((size_t)n * 64), fl_off = tab_off + pad((size_t)n * 128),
-           ws_off = fl_off + pad((size_t)n);
-    uint8_t* d = sg.dev(ws_off + 2 * pad(ws_bytes));
+           ws_off = fl_off + pad((size_t)n), bk_off = ws_off + pad(ws_bytes);
+    uint8_t* d = sg.dev(bk_off + pad(bk_bytes));
     cudaStream_t st = sg.stream, cs = sg.copy_stream;
     MsmOptions opt;
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.out_fmt = point_fmt;
     opt.shared_points = 1;
     opt.window_bits = plan.c;
-    opt.glv = plan.glv;           // every part with the same layout: the window sums are added window by window
+    opt.glv = plan.glv;           // every part with the same layout: they fill the same buckets
     opt.no_fixed_base = 1;
     opt.no_small = 1;
+    opt.d_window_sums = d + ws_off;
+    if (nparts > 1) opt.d_buckets = d + bk_off;
     int64_t first = 0;
     for (int h = 0; h < nparts; h++) {
-        const size_t a = (size_t)first, m = (size_t)part_len[h];
+        // the first part is half a regular part (its copy is the exposed one), the last part takes what that leaves
+        const int64_t last = h == nparts - 1 ? n : (n * (2 * h + 1)) / (2 * nparts);
+        const size_t a = (size_t)first, m = (size_t)(last - first);
         h2d_copy(d + sc_off + a * 32, scalars + a * 32, m * 32, cs);
         h2d_copy(d + pt_off + a * 64, points + a * 64, m * 64, cs);
         PORLA_CUDA(cudaEventRecord(sg.ev[h], cs));
         PORLA_CUDA(cudaStreamWaitEvent(st, sg.ev[h], 0));
         PointTable tab;
         table_import_into(curve, d + pt_off + a * 64, point_fmt, (uint32_t)m, d + tab_off + a * 128, d + fl_off + a, &tab, st);
-        opt.d_window_sums = d + ws_off + h * pad(ws_bytes);
+        opt.part_mode = nparts == 1 ? kPartWhole : (h == 0 ? kPartFirst : (h == nparts - 1 ? kPartLast : kPartMiddle));
         msm_device(curve, tab, d + sc_off + a * 32, (uint32_t)m, 1, opt, nullptr, nullptr, st);
-        first += part_len[h];
+        first = last;
     }
-    uint8_t* hbuf = sg.pinned((size_t)nparts * ws_bytes);
-    for (int h = 0; h < nparts; h++)
-        PORLA_CUDA(cudaMemcpyAsync(hbuf + h * ws_bytes, d + ws_off + h * pad(ws_bytes), ws_bytes, cudaMemcpyDeviceToHost, st));
+    uint8_t* hbuf = sg.pinned(ws_bytes);
+    PORLA_CUDA(cudaMemcpyAsync(hbuf, d + ws_off, ws_bytes, cudaMemcpyDeviceToHost, st));
     PORLA_CUDA(cudaStreamSynchronize(st));
-    memcpy(h_ws, hbuf, (size_t)nparts * ws_bytes);
-    *nparts_out = nparts;
+    memcpy(h_ws, hbuf, ws_bytes);
+    *nparts_out = 1;
 }
 
 // ---------------------------------------------------------------------------- fan-out over the devices of the box
@@ -343,7 +349,7 @@ void msm_host_fanout(int curve, const uint8_t* scalars, const uint8_t* points, i
     int64_t first[kMaxDevices], count[kMaxDevices];
     int nparts[kMaxDevices];
     device_ranges(n, ndev, first, count);
-    const MsmPlan plan = msm_plan(curve, (uint32_t)largest_part(count[ndev - 1]), 1, 0);
+    const MsmPlan plan = msm_plan(curve, (uint32_t)count[ndev - 1], 1, 0);
     const size_t ws_bytes = (size_t)plan.nwin * 128;
     std::vector<uint8_t> ws((size_t)ndev * kMaxPartsPerDevice * ws_bytes);
     run_on_devices(ndev, [&](int p) {
@@ -521,5 +527,29 @@ void porla_msm_host_devices(int curve, const void* scalars, const void* points, 
 }
 
 uint64_t porla_debug_copy_ring_bytes(void) { return h2d_ring_bytes(); }
+
+// Host-to-device copy rate of the library's own copy path (GB/s): `bytes` from a host buffer the caller provides (pinned or
+// pageable) into a scratch device buffer, `reps` times, stream-synchronised.  Development aid for the copy pool.
+double porla_debug_h2d_rate(const void* h_src, uint64_t bytes, int reps) {
+    device_init();
+    static void* d = nullptr;
+    static uint64_t cap = 0;
+    static cudaStream_t st = nullptr;
+    if (!st) PORLA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (bytes > cap) {
+        if (d) PORLA_CUDA(cudaFree(d));
+        PORLA_CUDA(cudaMalloc(&d, bytes));
+        cap = bytes;
+    }
+    h2d_copy(d, h_src, bytes, st);
+    PORLA_CUDA(cudaStreamSynchronize(st));
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; r++) {
+        h2d_copy(d, h_src, bytes, st);
+        PORLA_CUDA(cudaStreamSynchronize(st));
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return (double)bytes * reps / sec / 1e9;
+}
 
 }  // extern "C"

@@ -19,7 +19,7 @@ namespace porla {
 struct Staging {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // H2D of the next part overlaps the MSM of the current one
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {};
     uint8_t* d_buf = nullptr;
     size_t cap = 0;
     uint8_t* h_pinned = nullptr;

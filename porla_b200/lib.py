@@ -36,7 +36,7 @@ NEW_SYMBOLS = [
     "porla_debug_pairing_selfcheck", "porla_debug_latency", "porla_secp256k1_inner_product_prove", "porla_secp256k1_inner_product_verify",
     "porla_device_count", "porla_mtable_create", "porla_mtable_devices", "porla_mtable_len", "porla_mtable_range",
     "porla_mtable_msm_host_scalars", "porla_mtable_msm_resident", "porla_mtable_scalars_upload", "porla_mtable_scalars_free",
-    "porla_mtable_destroy", "porla_debug_copy_ring_bytes", "porla_msm_host_devices",
+    "porla_mtable_destroy", "porla_debug_copy_ring_bytes", "porla_msm_host_devices", "porla_debug_h2d_rate",
 ]
 
 
@@ -146,6 +146,7 @@ def load() -> C.CDLL:
         "porla_mtable_scalars_free": (None, [P, I, P]),
         "porla_mtable_destroy": (None, [P]),
         "porla_debug_copy_ring_bytes": (C.c_uint64, []),
+        "porla_debug_h2d_rate": (C.c_double, [P, C.c_uint64, I]),
         "porla_msm_host_devices": (None, [I, P, P, C.c_int64, I, I, I, P]),
     }
     for name, (res, args) in sig.items():

@@ -83,6 +83,38 @@ def test_host_buffer_fanout_matches_single_device(curve):
         assert pb.msm_host_devices(curve, sc, pts, n, ndev, scalar_fmt=fmt) == want, ndev
 
 
+@pytest.mark.parametrize("parts", [2, 3, 8])
+@pytest.mark.parametrize("kind", ["uniform", "constant", "small31", "pairs_cancel"])
+def test_streamed_parts_share_one_bucket_set(parts, kind, monkeypatch):
+    """msm_host_pipelined: the terms arrive in parts, every part is accumulated INTO the buckets the earlier parts filled and
+    the buckets are reduced once.  Forced on small inputs (PORLA_STREAM_PARTS) with the cases that stress the carry-over:
+    a constant scalar (one bucket per window, cut by every slice and continued by every part), 31-bit scalars (empty top
+    windows), and points that cancel ACROSS parts (P in one part, -P in another: the bucket returns to infinity)."""
+    n = 6000
+    pts, sc = _inputs(n, 11 + parts)
+    if kind == "constant":
+        sc = sc[:32] * n
+    elif kind == "small31":
+        sc = b"".join(bytes(28) + sc[32 * i + 28:32 * i + 32] for i in range(n))
+    elif kind == "pairs_cancel":
+        half = n // 2
+        P = bytearray(pts)
+        neg = bytearray()
+        for i in range(half):
+            x, y = pts[64 * i:64 * i + 32], int.from_bytes(pts[64 * i + 32:64 * i + 64], "big")
+            neg += x + ((BN.p - y) % BN.p if y else 0).to_bytes(32, "big")
+        P[64 * half:64 * n] = neg[:64 * (n - half)]
+        pts = bytes(P)
+        sc = sc[:32 * half] + sc[:32 * (n - half)]          # term i + half = -(term i), except the first few made different
+        sc = sc[:32 * half] + bytes(31) + b"\x05" + sc[32 * (half + 1):]
+    want = loader.bn254_msm(sc, pts, n, 4)
+    monkeypatch.setenv("PORLA_STREAM_PARTS", str(parts))
+    assert pb.msm_host_devices(pb.CURVE_BN254, sc, pts, n, 1) == want
+    assert pb.msm_host_devices(pb.CURVE_BN254, sc, pts, n, 2) == want      # two devices (or two workers), each streaming its range
+    monkeypatch.setenv("PORLA_NO_GLV", "1")
+    assert pb.msm_host_devices(pb.CURVE_BN254, sc, pts, n, 1) == want
+
+
 def test_pageable_buffers_go_through_the_copy_ring():
     """The host-buffer MSM with ordinary heap buffers (what utils.h:277-292 passes): large pageable buffers reach the device
     through the pinned ring of the copy pool, the result is that of the oracle; pinned buffers bypass the ring."""
