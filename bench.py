@@ -394,7 +394,7 @@ def distributions_block(lib, pb, torch, stream, table, ks, n, steps):
     ks2 = ks.clone()
     r = torch.rand(n, device=dev, generator=g)
     ks2[r < 0.01] = 0
-    ks2[(r >= 0.01) & (r < 0.02)] = ks2[0]
+    ks2[(r >= 0.01) & (r < 0.02)] = ks2[0].clone()
     tab2 = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks2.data_ptr(), n, pb.SCALAR_LE32, on_device=True, stream=stream)
     sc = torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device=dev, generator=g)
     sc[torch.rand(n, device=dev, generator=g) < 0.01] = 0
