@@ -64,4 +64,33 @@ blk = bytearray(b"".join(rnd.randrange(LCM).to_bytes(64, "little") for _ in rang
 lib.porla_data_butterfly_stage(C.cast((C.c_ubyte * len(blk)).from_buffer(blk), C.c_void_p), 8, 5, 4,
                                b"".join(rnd.randrange(1 << 256).to_bytes(32, "little") for _ in range(2)), LCM.to_bytes(64, "little"))
 print("data fft", bytes(blk[:8]).hex())
+# round 2: streamed host-buffer MSM (parts accumulated into one bucket set), in-call partition over several workers, sharded
+# resident table, affine accumulation kernel, batched scalar multiplication, device butterfly stage forced
+from oracle import loader
+os.environ["PORLA_OVERSUBSCRIBE_DEVICES"] = "1"
+n = 6000
+G = O.bn254_marshal((1, 2)); step = O.bn254_marshal(O.mul(O.BN254, 0xC0FFEE, (1, 2)))
+hp = bytearray(loader.bn254_point_chain(G, step, n)); hp[64 * 9:64 * 10] = bytes(64)
+hs = b"".join(be(rnd.randrange(1 << 256)) for _ in range(n))
+os.environ["PORLA_STREAM_PARTS"] = "3"
+r1 = pb.msm_host_devices(pb.CURVE_BN254, hs, bytes(hp), n, 1)
+r2 = pb.msm_host_devices(pb.CURVE_BN254, hs, bytes(hp), n, 3)
+del os.environ["PORLA_STREAM_PARTS"]
+mt = pb.MultiTable(pb.CURVE_BN254, bytes(hp), n, ndev=3)
+r3 = mt.msm_host_scalars(hs)
+ptrs = mt.upload_scalars(hs); r4 = mt.msm_resident(ptrs); mt.free_scalars(ptrs); mt.destroy()
+os.environ["PORLA_ACC_AFFINE"] = "2"; os.environ["PORLA_NO_SMALL"] = "1"
+r5 = pb.bn254_multi_exp(bytes(hp), hs, n)
+del os.environ["PORLA_ACC_AFFINE"]; del os.environ["PORLA_NO_SMALL"]
+print("streamed / fan-out / sharded table / affine:", r1 == r2 == r3 == r4 == r5, r1.hex()[:16])
+tabs = pb.Table.from_host(pb.CURVE_BN254, bytes(hp[:64 * 40]))
+d_sc = torch.frombuffer(bytearray(hs[:32 * 40]), dtype=torch.uint8).cuda()
+d_out = torch.zeros(64 * 40, dtype=torch.uint8, device="cuda")
+lib.porla_scalar_mul_batch_device(C.c_void_p(tabs.handle), C.c_void_p(d_sc.data_ptr()), 40, pb.SCALAR_BE32, pb.POINT_BE64,
+                                  C.c_void_p(d_out.data_ptr()), None)
+torch.cuda.synchronize(); tabs.destroy()
+os.environ["PORLA_HOST_BUTTERFLIES"] = "0"
+buf = bytearray(hp[:64 * 16]); pb.bn254_butterfly_stage(buf, 16, 4, be(7) + be(9))
+del os.environ["PORLA_HOST_BUTTERFLIES"]
+print("scalar mul batch / device butterfly", bytes(buf[:8]).hex())
 print("done")
