@@ -432,45 +432,52 @@ def closed_form_bytes(n, a, b):
     return O.bn254_marshal(O.mul(O.BN254, total, (1, 2)))
 
 
+def strong_shard_inputs(torch, lg, world, r, dev):
+    """Shard r of `world` of the strong-scaling inputs at 2^lg terms: points (i + 1) G (as 32-byte multipliers) and uniform
+    random 256-bit scalars, reproducible from (lg, world, r) on any rank."""
+    from porla_b200.sharding import shard_range
+    lo, hi = shard_range(1 << lg, world, r)
+    i = torch.arange(lo, hi, dtype=torch.int64, device=dev)
+    ks = torch.zeros((hi - lo, 8), dtype=torch.int32, device=dev)
+    ks[:, 0] = (i + 1).to(torch.int32)
+    g = torch.Generator(device=dev)
+    g.manual_seed(77 + 1000 * lg + 16 * world + r)
+    ss = torch.randint(-2**31, 2**31 - 1, (hi - lo, 8), dtype=torch.int32, device=dev, generator=g)
+    return lo, hi, ks, ss
+
+
+def weighted_scalar_sum(torch, ss, lo):
+    """sum_i s_i (i + 1) over a shard as an exact Python integer (s_i: the 256-bit value of row i of `ss`, i counted from
+    `lo`): 16-bit half limbs times the 27-bit weights summed in chunks of 2^16 terms stay below 2^59 in int64."""
+    n = ss.shape[0]
+    w = torch.arange(lo + 1, lo + n + 1, dtype=torch.int64, device=ss.device)
+    pad = (-n) % 65536
+    total = 0
+    for j in range(8):
+        limb = ss[:, j].to(torch.int64) & 0xFFFFFFFF
+        for half, shift in ((limb & 0xFFFF, 32 * j), (limb >> 16, 32 * j + 16)):
+            prod = half * w
+            if pad:
+                prod = torch.cat([prod, torch.zeros(pad, dtype=torch.int64, device=ss.device)])
+            total += sum(int(v) for v in prod.view(-1, 65536).sum(1).cpu().tolist()) << shift
+    return total
+
+
 def strong_scaling(args, lib, pb, torch, dist, rank, world, dev, stream, barrier):
     """ONE MSM of 2^k terms (k in --strong) over all `world` GPUs: every rank holds the contiguous range
-    shard_range(2^k, world, rank) resident, runs the pipeline up to its window sums, one all-gather, rank 0 combines.  The
-    result is asserted equal to the closed form.  speedup_vs_n1 = the same MSM on rank 0's GPU alone (same run, same
-    inputs) / the sharded time.  At world == 1 only the single-GPU time is reported."""
-    import random
-    from porla_b200.sharding import ShardedMsm, shard_range
+    shard_range(2^k, world, rank) resident, runs the pipeline up to its window sums, one all-gather, rank 0 combines.
+    Inputs: points (i + 1) G and uniform random scalars, so the result has the closed form [sum s_i (i + 1) mod r] G, which
+    is evaluated exactly (integer arithmetic on the GPU + Python integers) and asserted.  speedup_vs_n1 = the SAME MSM (same
+    points, same scalars) on rank 0's GPU alone, in the same run, / the sharded time."""
+    from oracle import curves_py as O
+    from porla_b200.sharding import ShardedMsm
     out = {}
     for lg in [int(x) for x in args.strong.split(",") if x]:
         n = 1 << lg
-        rnd = random.Random(1000 + lg)
-        a = rnd.getrandbits(228) | (1 << 227) | 1
-        b = rnd.getrandbits(255) | (1 << 254)
-        want = closed_form_bytes(n, a, b) if rank == 0 else None
         steps = max(3, min(args.steps, 6 if lg >= 26 else 10))
         entry = {"terms": n}
 
-        def run(world_eff, r_eff, active):
-            """time the MSM sharded over world_eff ranks (ranks >= world_eff idle); returns ms per MSM"""
-            if not active:
-                barrier()
-                barrier()
-                return None, None
-            lo, hi = shard_range(n, world_eff, r_eff)
-            ks, ss = closed_form_inputs(torch, lo, hi, a, b, dev)
-            tab = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks.data_ptr(), hi - lo, pb.SCALAR_LE32, on_device=True, stream=stream)
-            del ks
-            torch.cuda.synchronize()
-            if world_eff == 1:
-                res = [None]
-
-                def one():
-                    res[0] = tab.msm_resident(ss.data_ptr(), hi - lo, scalar_fmt=pb.SCALAR_LE32, stream=stream)
-            else:
-                eng = ShardedMsm(pb.CURVE_BN254, n, world_eff, r_eff, dist, dev)
-                res = [None]
-
-                def one():
-                    res[0] = eng.msm(tab, ss.data_ptr(), hi - lo, pb.SCALAR_LE32)
+        def timed_ms(one):
             for _ in range(3):
                 one()
             barrier()
@@ -482,29 +489,56 @@ def strong_scaling(args, lib, pb, torch, dist, rank, world, dev, stream, barrier
             e1.record()
             barrier()
             wall = (time.perf_counter() - t0) * 1e3
-            ms = max(wall, e0.elapsed_time(e1)) / steps
-            tab.destroy()
-            return ms, res[0]
+            return max(wall, e0.elapsed_time(e1)) / steps
 
-        if world > 1:
-            ms_n, got = run(world, rank, True)
-            t = torch.tensor([ms_n], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_n = float(t.item())
-            if rank == 0 and got != want:
-                raise SystemExit("bench self-check failed: %d-rank sharded 2^%d MSM differs from the closed form" % (world, lg))
-            entry["ms_sharded"] = ms_n
-            entry["points_per_s_sharded"] = n / (ms_n * 1e-3)
-        # the same MSM on one GPU (rank 0 alone; the other ranks wait at the barriers inside run())
-        ms_1, got1 = run(1, 0, rank == 0)
+        # ---- sharded over all ranks
+        lo, hi, ks, ss = strong_shard_inputs(torch, lg, world, rank, dev)
+        tab = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks.data_ptr(), hi - lo, pb.SCALAR_LE32, on_device=True, stream=stream)
+        del ks
+        torch.cuda.synchronize()
+        eng = ShardedMsm(pb.CURVE_BN254, n, world, rank, dist, dev)
+        res = [None]
+
+        def one_sharded():
+            res[0] = eng.msm(tab, ss.data_ptr(), hi - lo, pb.SCALAR_LE32)
+        ms_n = timed_ms(one_sharded)
+        t = torch.tensor([ms_n], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_n = float(t.item())
+        got_sharded = res[0]
+        tab.destroy()
+        del ss
+        entry["ms_sharded"] = ms_n
+        entry["points_per_s_sharded"] = n / (ms_n * 1e-3)
+        # ---- the same MSM on rank 0's GPU alone (the other ranks wait at the two barriers of timed_ms)
         if rank == 0:
-            if got1 != want:
+            parts = [strong_shard_inputs(torch, lg, world, r, dev) for r in range(world)]
+            ks_all = torch.cat([p[2] for p in parts])
+            ss_all = torch.cat([p[3] for p in parts])
+            total = sum(weighted_scalar_sum(torch, p[3], p[0]) for p in parts) % O.BN254.n
+            del parts
+            want = O.bn254_marshal(O.mul(O.BN254, total, (1, 2)))
+            tab1 = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks_all.data_ptr(), n, pb.SCALAR_LE32, on_device=True, stream=stream)
+            del ks_all
+            torch.cuda.synchronize()
+            res1 = [None]
+
+            def one_single():
+                res1[0] = tab1.msm_resident(ss_all.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32, stream=stream)
+            ms_1 = timed_ms(one_single)
+            tab1.destroy()
+            del ss_all
+            if res1[0] != want:
                 raise SystemExit("bench self-check failed: single-GPU 2^%d MSM differs from the closed form" % lg)
+            if got_sharded != want:
+                raise SystemExit("bench self-check failed: %d-rank sharded 2^%d MSM differs from the closed form" % (world, lg))
             entry["ms_n1"] = ms_1
             entry["points_per_s_n1"] = n / (ms_1 * 1e-3)
-            entry["checked"] = "closed form, bit-exact"
-            if world > 1:
-                entry["speedup_vs_n1"] = ms_1 / entry["ms_sharded"]
+            entry["speedup_vs_n1"] = ms_1 / ms_n
+            entry["checked"] = "sharded and single-GPU results equal the closed form [sum s_i (i+1) mod r] G, bit-exact"
+        else:
+            barrier()
+            barrier()
         out["2^%d" % lg] = entry
     return out
 
@@ -518,11 +552,9 @@ def strong_scaling_in_library(args, lib, pb, torch, ndev):
         if lg > 24:
             continue
         n = 1 << lg
-        rnd = random.Random(1000 + lg)
-        a = rnd.getrandbits(228) | (1 << 227) | 1
-        b = rnd.getrandbits(255) | (1 << 254)
-        want = closed_form_bytes(n, a, b)
-        ks, ss = closed_form_inputs(torch, 0, n, a, b, torch.device("cuda", torch.cuda.current_device()))
+        from oracle import curves_py as O
+        _, _, ks, ss = strong_shard_inputs(torch, lg, 1, 0, torch.device("cuda", torch.cuda.current_device()))
+        want = O.bn254_marshal(O.mul(O.BN254, weighted_scalar_sum(torch, ss, 0) % O.BN254.n, (1, 2)))
         tab = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks.data_ptr(), n, pb.SCALAR_LE32, on_device=True)
         del ks
         pts = torch.empty(n * 64, dtype=torch.uint8).pin_memory()
@@ -556,6 +588,15 @@ def strong_scaling_in_library(args, lib, pb, torch, ndev):
         for _ in range(3):
             pb.msm_host_devices(pb.CURVE_BN254, sc_host.data_ptr(), pts.data_ptr(), n, ndev, scalar_fmt=pb.SCALAR_LE32)
         entry["ms_host_buffers"] = (time.perf_counter() - t0) / 3 * 1e3
+        # ... and the same host-buffer call kept on ONE device (what an unchanged caller gets on a one-GPU box)
+        got = pb.msm_host_devices(pb.CURVE_BN254, sc_host.data_ptr(), pts.data_ptr(), n, 1, scalar_fmt=pb.SCALAR_LE32)
+        if got != want:
+            raise SystemExit("bench self-check failed: single-device host-buffer MSM differs from the closed form")
+        t0 = time.perf_counter()
+        for _ in range(2):
+            pb.msm_host_devices(pb.CURVE_BN254, sc_host.data_ptr(), pts.data_ptr(), n, 1, scalar_fmt=pb.SCALAR_LE32)
+        entry["ms_host_buffers_one_device"] = (time.perf_counter() - t0) / 2 * 1e3
+        entry["host_buffers_speedup"] = entry["ms_host_buffers_one_device"] / entry["ms_host_buffers"]
         entry["checked"] = "closed form, bit-exact"
         out["2^%d" % lg] = entry
     return out
@@ -877,6 +918,7 @@ def run_ours(args):
     traffic = None
     try:   # DRAM bytes of one k_accumulate launch at this size, from the committed ncu --set full capture
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["k_accumulate<Bn254>"].get(str(args.log2n))
+        traffic = traffic.get("dram_bytes") if isinstance(traffic, dict) else traffic
     except Exception:
         pass
     macs = n * MAC32_PER_POINT
@@ -901,7 +943,7 @@ def run_ours(args):
             "peak_source": "measured live: porla_measure_pint (mad.lo.cc/madc.hi.cc chains, all SMs); integer pipe is not in MEASURED_PEAKS.json",
             "whole_msm_frac": macs / (ms_step * 1e-3) / p_int if world == 1 else None,
             "traffic": traffic,
-            "traffic_note": "dram__bytes_read+write of one k_accumulate launch (ncu capture in profiles/); the kernel gathers each "
+            "traffic_note": "dram__bytes_read+write of one k_accumulate launch, bytes (ncu --set full capture of this round's tree, profiles/r02_traffic.json); the kernel gathers each "
                             "64-byte point once per window, so DRAM traffic exceeds the 96 B/point algorithmic figure yet stays "
                             "under 5 % of HBM bandwidth: the bound is the integer pipe",
             "hbm": {"algorithmic_gbs": n * BYTES_PER_POINT / (ms_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
