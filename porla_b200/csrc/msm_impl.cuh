@@ -307,11 +307,71 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     const uint64_t total_scalars = (uint64_t)n * nbatch;
 
     g_stage_timer.mark(kStageCount, stream);
+    // radix path without the exact histogram (k_coarse_count ... k_fine_local, msm_kernels.cuh): opt-in (PORLA_SORT_V2=1).
+    // Measured on one B200 (profiles/r02b_sort_without_exact_histogram.txt): the coarse count is 2.2x faster than the exact
+    // one (2^24: 1.57 -> 0.71 ms) but one block per coarse bin scattering 8-byte pairs loses more than that to uncoalesced
+    // writes (scatter 3.67 -> 6.05 ms), so the default stays the exact histogram + tile-staged fine pass.
+    const bool sort_v2 = radix && lb <= 10 && (size_t)ncoarse * 4 <= (160u << 10) && getenv("PORLA_SORT_V2") != nullptr;
     PORLA_CUDA(cudaMemsetAsync(counters, 0, (size_t)nbt * 4, stream));
     PORLA_CUDA(cudaMemsetAsync(grand, 0, 4, stream));
     PORLA_CUDA(cudaMemsetAsync(long_count, 0, 4, stream));
     if (!into) PORLA_CUDA(cudaMemsetAsync(buckets, 0, (size_t)nbt * sizeof(XYZZ<F>), stream));  // empty bucket = infinity
-    if (total_scalars) {
+    if (total_scalars && sort_v2) {
+        static std::once_flag attr_once_dev2[kMaxDevices];   // function attributes are per device
+        const size_t smem0 = (size_t)ncoarse * 4;
+        const size_t smem1 = ((size_t)9 * kPartTile + 2 * kPartMaxBins) * 4 + (size_t)kPartTile * 8;
+        const size_t smem2 = (size_t)2 * kFineHist * 4 + (size_t)kFineTile * 8;
+        std::call_once(attr_once_dev2[current_device()], [=] {
+            PORLA_CUDA(cudaFuncSetAttribute(k_coarse_count<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 << 10));
+            PORLA_CUDA(cudaFuncSetAttribute(k_partition_coarse<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            if constexpr (C::kGlv) {
+                PORLA_CUDA(cudaFuncSetAttribute(k_coarse_count<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 << 10));
+                PORLA_CUDA(cudaFuncSetAttribute(k_partition_coarse<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            }
+            PORLA_CUDA(cudaFuncSetAttribute(k_partition_fine_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        });
+        uint32_t* coarse_count = offsets;                 // the exact-offset array is not needed on this path: reuse it
+        uint32_t* coarse_off = offsets + ncoarse + 1;     // (nbt >= 2 * (ncoarse + 1): 2^lb >= 16 buckets per bin)
+        PORLA_CUDA(cudaMemsetAsync(coarse_count, 0, (size_t)(ncoarse + 1) * 4, stream));
+        uint32_t cgrid = (uint32_t)((total_scalars + kCoarseCountThreads - 1) / kCoarseCountThreads);
+        if (cgrid > 148u * 2u) cgrid = 148u * 2u;
+        bool glv_done = false;
+        if constexpr (C::kGlv) {
+            if (glv) {
+                k_coarse_count<C, true><<<cgrid, kCoarseCountThreads, smem0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, lb, ncoarse, coarse_count);
+                glv_done = true;
+            }
+        }
+        if (!glv_done)
+            k_coarse_count<C, false><<<cgrid, kCoarseCountThreads, smem0, stream>>>(d_scalars, opt.scalar_be, table.d_flags, sh, lb, ncoarse, coarse_count);
+        LAUNCHED();
+        g_stage_timer.mark(kStageScan, stream);
+        k_coarse_scan<<<1, 1024, 0, stream>>>(coarse_count, ncoarse, coarse_off, coarse_cursor, grand);
+        LAUNCHED();
+        g_stage_timer.mark(kStageScatter, stream);
+        glv_done = false;
+        if constexpr (C::kGlv) {
+            if (glv) {
+                k_partition_coarse<C, true><<<(n + kPartTile - 1) / kPartTile, kPartThreads, smem1, stream>>>(
+                    d_scalars, opt.scalar_be, table.d_flags, sh, lb, coarse_cursor, part);
+                glv_done = true;
+            }
+        }
+        if (!glv_done)
+            k_partition_coarse<C, false><<<(n + kPartTile - 1) / kPartTile, kPartThreads, smem1, stream>>>(
+                d_scalars, opt.scalar_be, table.d_flags, sh, lb, coarse_cursor, part);
+        LAUNCHED();
+        k_fine_local<<<ncoarse, kFineLocalThreads, 0, stream>>>(part, coarse_off, lb, sorted);
+        LAUNCHED();
+        // bins too long for one block (skewed inputs): counted, scanned and scattered by tiles; no-ops otherwise
+        const uint32_t tiles = (uint32_t)((pairs_cap + kFineTile - 1) / kFineTile);
+        k_big_count<<<tiles, kFineThreads, 0, stream>>>(part, grand, coarse_off, lb, counters);
+        LAUNCHED();
+        k_big_scan<<<ncoarse, kFineLocalThreads, 0, stream>>>(coarse_off, lb, counters);
+        LAUNCHED();
+        k_partition_fine_big<<<tiles, kFineThreads, smem2, stream>>>(part, grand, coarse_off, lb, counters, sorted);
+        LAUNCHED();
+    } else if (total_scalars) {
         uint32_t grid = (uint32_t)((total_scalars + 255) / 256);
         if (grid > 148u * 32u) grid = 148u * 32u;
         bool launched_glv = false;
@@ -383,6 +443,8 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
             LAUNCHED();
         }
         }
+    }
+    if (total_scalars) {
         g_stage_timer.mark(kStageAccumulate, stream);
         if (aff_rounds > 0)
             k_accumulate_affine<C><<<(nslices_cap + kAffThreads - 1) / kAffThreads, kAffThreads, 0, stream>>>(

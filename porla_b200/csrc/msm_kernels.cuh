@@ -722,6 +722,270 @@ k_partition_fine(const uint2* __restrict__ part, const uint32_t* __restrict__ to
     }
 }
 
+// ---------------------------------------------------------------------------- sort without the exact histogram (round 2, opt-in:
+// PORLA_SORT_V2=1 -- measured slower overall than the default, see msm_impl.cuh and profiles/r02b_sort_without_exact_histogram.txt)
+// The exact bucket histogram (k_digits<COUNT>: one global atomic per pair, 218 M of them at 2^24) exists only to give every
+// bucket its output range.  The radix path does not need it: a COARSE histogram (one counter per 2^lb consecutive buckets,
+// kept in shared memory while a block walks its share of the scalars) is enough to place the coarse bins, and each coarse
+// bin is then sorted by ONE block that counts, scans and scatters its own 2^lb buckets in shared memory.
+//   k_coarse_count   recode every scalar, shared-memory histogram over (window, coarse bin), a few global atomics per block
+//   k_coarse_scan    exclusive scan of the <= 28 k coarse counters -> bin offsets, partition cursors, total pair count
+//   k_partition_coarse (above) writes the pairs grouped by coarse bin into `part`
+//   k_fine_local     block b owns coarse bin b: histogram of its buckets, scan, scatter into `sorted`
+// Skewed inputs (a constant scalar, 31-bit scalars' empty top windows ...) put up to all pairs of a window into one coarse
+// bin; bins above kBigBin pairs are left to the tile-based route, which is the round-1 fine pass preceded by its own
+// counting pass over the same tiles (k_big_count, k_big_scan, k_partition_fine_big) and costs nothing when no bin is big.
+constexpr uint32_t kBigBin = 1u << 16;
+constexpr int kCoarseCountThreads = 512;
+constexpr int kFineLocalThreads = 256;
+constexpr uint32_t kFineLocalBuckets = 1024;   // 2^lb <= 2^10 buckets per coarse bin (c <= 20)
+
+template <class C, bool GLV>
+__global__ void __launch_bounds__(kCoarseCountThreads)
+k_coarse_count(const uint8_t* __restrict__ scalars, int big_endian, const uint8_t* __restrict__ inf_flags, MsmShape sh, int lb,
+               uint32_t ncoarse, uint32_t* __restrict__ coarse_count) {
+    extern __shared__ uint32_t smem[];   // [ncoarse]
+    for (uint32_t b = threadIdx.x; b < ncoarse; b += blockDim.x) smem[b] = 0;
+    __syncthreads();
+    const uint32_t half = 1u << (sh.c - 1);
+    const uint32_t mask = (1u << sh.c) - 1u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sh.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (inf_flags && inf_flags[i]) continue;
+        uint32_t s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // GLV: |k1| in s[0..3], |k2| in s[4..7]
+        if constexpr (GLV) {
+            uint32_t k[8], n1, n2;
+            load_u256(scalars, i, big_endian, k);
+            reduce_scalar<C>(k);
+            glv_split<C>(k, s, s + 4, n1, n2);
+        } else {
+            load_u256(scalars, i, big_endian, s);
+            reduce_scalar<C>(s);
+            if (C::kHalveScalar) {
+                uint32_t ord[8], t[8], u[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) ord[k] = C::order(k);
+                sub256(t, ord, s);
+                if (sub256(u, t, s)) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) s[k] = t[k];
+                }
+            }
+        }
+        uint32_t carry = 0;
+        for (int w = 0; w < sh.nwin; w++) {
+            uint32_t lo, hi, sft;
+            int wl = w;
+            if (GLV) {
+                const int h = w >= sh.glv_wh ? 1 : 0;
+                wl = w - h * sh.glv_wh;
+                if (wl == 0) carry = 0;
+                const uint32_t pos = (uint32_t)wl * sh.c, word = pos >> 5;
+                sft = pos & 31;
+                lo = s[4 * h + word];
+                hi = word < 3 ? s[4 * h + word + 1] : 0u;
+            } else {
+                const uint32_t pos = (uint32_t)w * sh.c, word = pos >> 5;
+                sft = pos & 31;
+                lo = s[word < 8 ? word : 8];
+                hi = s[word < 7 ? word + 1 : 8];
+            }
+            const uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry;
+            const uint32_t dneg = d > half;
+            carry = dneg;
+            const uint32_t mag = dneg ? ((1u << sh.c) - d) : d;
+            if (mag != 0) {
+                const uint32_t key0 = sh.fixed_n ? 0u : (uint32_t)wl * sh.nbuckets;
+                atomicAdd(&smem[(key0 + (mag - 1)) >> lb], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < ncoarse; b += blockDim.x)
+        if (smem[b]) atomicAdd(&coarse_count[b], smem[b]);
+}
+
+// single block: coarse_off[0..ncoarse] = exclusive scan of coarse_count, cursor copy, total
+static __global__ void __launch_bounds__(1024)
+k_coarse_scan(const uint32_t* __restrict__ coarse_count, uint32_t ncoarse, uint32_t* __restrict__ coarse_off,
+              uint32_t* __restrict__ coarse_cursor, uint32_t* __restrict__ grand) {
+    __shared__ uint32_t total;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < ncoarse; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < ncoarse ? coarse_count[i] : 0u;
+        const uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < ncoarse) {
+            coarse_off[i] = carry + ex;
+            coarse_cursor[i] = carry + ex;
+        }
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        coarse_off[ncoarse] = carry;
+        *grand = carry;
+    }
+}
+
+// block b sorts coarse bin b (pairs part[off[b] .. off[b+1])) by bucket into the same range of `sorted`
+static __global__ void __launch_bounds__(kFineLocalThreads)
+k_fine_local(const uint2* __restrict__ part, const uint32_t* __restrict__ coarse_off, int lb, uint2* __restrict__ sorted) {
+    __shared__ uint32_t hist[kFineLocalBuckets];
+    __shared__ uint32_t total;
+    const uint32_t start = coarse_off[blockIdx.x], cnt = coarse_off[blockIdx.x + 1] - start;
+    if (cnt == 0 || cnt > kBigBin) return;
+    const uint32_t nb = 1u << lb, bmask = nb - 1u;
+    for (uint32_t b = threadIdx.x; b < kFineLocalBuckets; b += kFineLocalThreads) hist[b] = 0;
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < cnt; j += kFineLocalThreads) atomicAdd(&hist[__ldg(&part[start + j].x) & bmask], 1u);
+    __syncthreads();
+    {
+        constexpr uint32_t ept = kFineLocalBuckets / kFineLocalThreads;   // 4
+        uint32_t v[ept], sum = 0;
+        const uint32_t b0 = threadIdx.x * ept;
+#pragma unroll
+        for (uint32_t k = 0; k < ept; k++) {
+            v[k] = hist[b0 + k];
+            sum += v[k];
+        }
+        uint32_t ex = block_exclusive_scan(sum, &total);
+#pragma unroll
+        for (uint32_t k = 0; k < ept; k++) {
+            hist[b0 + k] = ex;
+            ex += v[k];
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < cnt; j += kFineLocalThreads) {
+        const uint2 e = __ldg(&part[start + j]);
+        sorted[start + atomicAdd(&hist[e.x & bmask], 1u)] = e;
+    }
+}
+
+// ---- bins above kBigBin pairs: the tile-based fine pass with its own counting pass
+PORLA_D bool bin_is_big(const uint32_t* __restrict__ coarse_off, uint32_t bin) {
+    return coarse_off[bin + 1] - coarse_off[bin] > kBigBin;
+}
+
+static __global__ void __launch_bounds__(kFineThreads)
+k_big_count(const uint2* __restrict__ part, const uint32_t* __restrict__ total_pairs, const uint32_t* __restrict__ coarse_off,
+            int lb, uint32_t* __restrict__ counters) {
+    const uint32_t M = *total_pairs;
+    const uint64_t lo64 = (uint64_t)blockIdx.x * kFineTile;
+    if (lo64 >= M) return;
+    const uint32_t lo = (uint32_t)lo64;
+    const uint32_t hi = M - lo > (uint32_t)kFineTile ? lo + kFineTile : M;
+    // the tile covers the bins of its first .. last pair (pass 1 keeps the coarse bins in order)
+    const uint32_t bin_lo = __ldg(&part[lo].x) >> lb, bin_hi = __ldg(&part[hi - 1].x) >> lb;
+    bool any = false;
+    for (uint32_t b = bin_lo; b <= bin_hi && !any; b++) any = bin_is_big(coarse_off, b);
+    if (!any) return;
+    // shared-memory histogram of the tile (a constant scalar sends every pair of the tile to ONE bucket), one global atomic
+    // per (tile, bucket)
+    __shared__ uint32_t hist[kFineHist];
+    for (uint32_t b = threadIdx.x; b < kFineHist; b += kFineThreads) hist[b] = 0;
+    const uint32_t kbase = bin_lo << lb;
+    __syncthreads();
+    for (uint32_t idx = lo + threadIdx.x; idx < hi; idx += kFineThreads) {
+        const uint32_t key = __ldg(&part[idx].x);
+        if (!bin_is_big(coarse_off, key >> lb)) continue;
+        const uint32_t rel = key - kbase;
+        if (rel < kFineHist) atomicAdd(&hist[rel], 1u);
+        else atomicAdd(&counters[key], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < kFineHist; b += kFineThreads)
+        if (hist[b]) atomicAdd(&counters[kbase + b], hist[b]);
+}
+
+// block b: if bin b is big, counters[b << lb ..] <- its output offsets (bin start + exclusive prefix of the counts)
+static __global__ void __launch_bounds__(kFineLocalThreads)
+k_big_scan(const uint32_t* __restrict__ coarse_off, int lb, uint32_t* __restrict__ counters) {
+    __shared__ uint32_t total;
+    if (!bin_is_big(coarse_off, blockIdx.x)) return;
+    const uint32_t nb = 1u << lb;
+    uint32_t* c = counters + ((size_t)blockIdx.x << lb);
+    uint32_t carry = coarse_off[blockIdx.x];
+    for (uint32_t base = 0; base < nb; base += kFineLocalThreads) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nb ? c[i] : 0u;
+        const uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < nb) c[i] = carry + ex;
+        carry += total;
+        __syncthreads();
+    }
+}
+
+// k_partition_fine restricted to the pairs of big bins (cursor = the offsets k_big_scan wrote)
+static __global__ void __launch_bounds__(kFineThreads, 3)
+k_partition_fine_big(const uint2* __restrict__ part, const uint32_t* __restrict__ total_pairs, const uint32_t* __restrict__ coarse_off,
+                     int lb, uint32_t* __restrict__ cursor, uint2* __restrict__ sorted) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* cnt = smem;                                   // [kFineHist] counts, then local offsets
+    uint32_t* delta = cnt + kFineHist;                      // [kFineHist] reserved global base - local offset
+    uint2* stage = reinterpret_cast<uint2*>(delta + kFineHist);   // [kFineTile] pairs grouped by bucket
+    __shared__ uint32_t s_total;
+    const uint32_t M = *total_pairs;
+    const uint64_t lo64 = (uint64_t)blockIdx.x * kFineTile;
+    if (lo64 >= M) return;
+    const uint32_t lo = (uint32_t)lo64;
+    const uint32_t hi = M - lo > (uint32_t)kFineTile ? lo + kFineTile : M;
+    const uint32_t bin_lo = __ldg(&part[lo].x) >> lb, bin_hi = __ldg(&part[hi - 1].x) >> lb;
+    bool any = false;
+    for (uint32_t b = bin_lo; b <= bin_hi && !any; b++) any = bin_is_big(coarse_off, b);
+    if (!any) return;
+    for (uint32_t b = threadIdx.x; b < kFineHist; b += kFineThreads) cnt[b] = 0;
+    const uint32_t kbase = bin_lo << lb;
+    __syncthreads();
+    uint2 e[kFinePerThread];
+    uint32_t rank[kFinePerThread];
+#pragma unroll
+    for (int q = 0; q < kFinePerThread; q++) {
+        const uint32_t idx = lo + q * kFineThreads + threadIdx.x;
+        e[q] = make_uint2(0xffffffffu, 0u);
+        if (idx < hi) {
+            const uint2 v = __ldg(&part[idx]);
+            if (bin_is_big(coarse_off, v.x >> lb)) {
+                e[q] = v;
+                const uint32_t rel = v.x - kbase;
+                if (rel < kFineHist) rank[q] = atomicAdd(&cnt[rel], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    {
+        constexpr uint32_t ept = kFineHist / kFineThreads;   // 8
+        uint32_t v[ept], sum = 0;
+        const uint32_t b0 = threadIdx.x * ept;
+#pragma unroll
+        for (uint32_t k = 0; k < ept; k++) {
+            v[k] = cnt[b0 + k];
+            sum += v[k];
+        }
+        uint32_t ex = block_exclusive_scan(sum, &s_total);
+#pragma unroll
+        for (uint32_t k = 0; k < ept; k++) {
+            cnt[b0 + k] = ex;
+            delta[b0 + k] = v[k] ? atomicAdd(&cursor[kbase + b0 + k], v[k]) - ex : 0u;
+            ex += v[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kFinePerThread; q++) {
+        if (e[q].x == 0xffffffffu) continue;
+        const uint32_t rel = e[q].x - kbase;
+        if (rel < kFineHist) stage[cnt[rel] + rank[q]] = e[q];
+        else sorted[atomicAdd(&cursor[e[q].x], 1u)] = e[q];
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    for (uint32_t j = threadIdx.x; j < total; j += kFineThreads) {
+        const uint2 x = stage[j];
+        sorted[delta[x.x - kbase] + j] = x;
+    }
+}
+
 // ---------------------------------------------------------------------------- accumulation
 // Load-balanced segmented accumulation.  `sorted` holds the M (bucket id, point index | sign << 31)
 // pairs grouped by bucket.  Thread t owns the fixed-length slice [t*L, (t+1)*L) regardless of where
