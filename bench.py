@@ -941,7 +941,7 @@ def run_ours(args):
             "achieved": macs / (acc_avg * 1e-3) / 1e12, "peak": p_int / 1e12, "unit": "TMAC32/s",
             "frac": macs / (acc_avg * 1e-3) / p_int,
             "peak_source": "measured live: porla_measure_pint (mad.lo.cc/madc.hi.cc chains, all SMs); integer pipe is not in MEASURED_PEAKS.json",
-            "whole_msm_frac": macs / (ms_step * 1e-3) / p_int if world == 1 else None,
+            "whole_msm_frac": macs / (ms_step * 1e-3) / p_int,     # per GPU: its n points in the step time (max over ranks)
             "traffic": traffic,
             "traffic_note": "dram__bytes_read+write of one k_accumulate launch, bytes (ncu --set full capture of this round's tree, profiles/r02_traffic.json); the kernel gathers each "
                             "64-byte point once per window, so DRAM traffic exceeds the 96 B/point algorithmic figure yet stays "

@@ -449,8 +449,48 @@ static void mtable_msm(const porla_mtable* mt, const uint8_t* h_scalars, void* c
         Staging& sg = worker_staging();
         const size_t m = (size_t)mt->count[p];
         const uint8_t* d_sc;
+        const int nparts = d_scalars_per_part ? 1 : stream_parts_for((int64_t)m, plan);
         if (d_scalars_per_part) {
             d_sc = (const uint8_t*)d_scalars_per_part[p];
+        } else if (nparts > 1) {
+            // host scalars of a large range: streamed like msm_host_pipelined -- the scalars of part h+1 cross PCIe while
+            // part h (a view of the resident table) is accumulated into the shared bucket set
+            const size_t bk_bytes = msm_bucket_bytes(plan);
+            uint8_t* d_bk = sg.dev(bk_bytes);
+            MsmOptions so;
+            so.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
+            so.out_fmt = out_fmt;
+            so.shared_points = 1;
+            so.window_bits = plan.c;
+            so.glv = plan.glv;
+            so.no_fixed_base = 1;
+            so.no_small = 1;
+            so.d_window_sums = mt->d_ws[p];
+            so.d_buckets = d_bk;
+            const PointTable& full = mt->part[p];
+            size_t a = 0;
+            for (int h = 0; h < nparts; h++) {
+                const size_t last = h == nparts - 1 ? m : (m * (2 * (size_t)h + 1)) / (2 * (size_t)nparts);
+                const size_t len = last - a;
+                h2d_copy(mt->d_scalars[p] + a * 32, h_scalars + ((size_t)mt->first[p] + a) * 32, len * 32, sg.copy_stream);
+                PORLA_CUDA(cudaEventRecord(sg.ev[h], sg.copy_stream));
+                PORLA_CUDA(cudaStreamWaitEvent(sg.stream, sg.ev[h], 0));
+                PointTable view = full;          // entries [a, a + len) of this device's range
+                view.d_points = (uint8_t*)full.d_points + a * 64;
+                view.d_flags = full.d_flags ? full.d_flags + a : nullptr;
+                view.n = (uint32_t)len;
+                view.d_fb_points = nullptr;
+                view.d_lut = nullptr;
+                view.fb_c = view.fb_nwin = 0;
+                if (full.d_phi_x) {
+                    view.d_phi_x = (uint8_t*)full.d_phi_x + a * 32;
+                    view.phi_off = (uint32_t)len;
+                }
+                so.part_mode = h == 0 ? kPartFirst : (h == nparts - 1 ? kPartLast : kPartMiddle);
+                msm_device(mt->curve, view, mt->d_scalars[p] + a * 32, (uint32_t)len, 1, so, nullptr, nullptr, sg.stream);
+                a = last;
+            }
+            d_sc = nullptr;
         } else {
             h2d_copy(mt->d_scalars[p], h_scalars + (size_t)mt->first[p] * 32, m * 32, sg.stream);
             d_sc = mt->d_scalars[p];
@@ -464,8 +504,8 @@ static void mtable_msm(const porla_mtable* mt, const uint8_t* h_scalars, void* c
         opt.no_fixed_base = 1;
         opt.no_small = 1;
         opt.d_window_sums = mt->d_ws[p];
-        if (m) msm_device(mt->curve, mt->part[p], d_sc, (uint32_t)m, 1, opt, nullptr, nullptr, sg.stream);
-        else PORLA_CUDA(cudaMemsetAsync(mt->d_ws[p], 0, ws_bytes, sg.stream));
+        if (m && d_sc) msm_device(mt->curve, mt->part[p], d_sc, (uint32_t)m, 1, opt, nullptr, nullptr, sg.stream);
+        else if (!m) PORLA_CUDA(cudaMemsetAsync(mt->d_ws[p], 0, ws_bytes, sg.stream));
         uint8_t* h = sg.pinned(ws_bytes);
         PORLA_CUDA(cudaMemcpyAsync(h, mt->d_ws[p], ws_bytes, cudaMemcpyDeviceToHost, sg.stream));
         PORLA_CUDA(cudaStreamSynchronize(sg.stream));

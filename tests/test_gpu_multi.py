@@ -111,6 +111,9 @@ def test_streamed_parts_share_one_bucket_set(parts, kind, monkeypatch):
     monkeypatch.setenv("PORLA_STREAM_PARTS", str(parts))
     assert pb.msm_host_devices(pb.CURVE_BN254, sc, pts, n, 1) == want
     assert pb.msm_host_devices(pb.CURVE_BN254, sc, pts, n, 2) == want      # two devices (or two workers), each streaming its range
+    mt = pb.MultiTable(pb.CURVE_BN254, pts, n, ndev=2)                     # resident sharded table, host scalars streamed in parts
+    assert mt.msm_host_scalars(sc) == want
+    mt.destroy()
     monkeypatch.setenv("PORLA_NO_GLV", "1")
     assert pb.msm_host_devices(pb.CURVE_BN254, sc, pts, n, 1) == want
 
