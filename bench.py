@@ -296,9 +296,22 @@ def config1_replay():
         cmd = [exe, "--blocks", "1024", "--audits", "100", "--oracle", os.path.join(ROOT, "oracle", "liboracle_bn254.so"),
                "--cpu-updates", "128", "--cpu-audits", "5"]
         p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        if p.returncode == 1:
+            raise SystemExit("bench self-check failed: replay_config1: the legacy and batched passes disagree: " + p.stdout[-400:])
         if p.returncode != 0:
             return {"error": "replay_config1 exit %d: %s" % (p.returncode, (p.stdout + p.stderr)[-400:])}
         d = json.loads(p.stdout)
+        # a complete small run (64 blocks) in which the CPU pass covers every update, so that its final MAC arrays and audit
+        # sums can be compared with the library's byte for byte
+        q = subprocess.run([exe, "--blocks", "64", "--audits", "3", "--cpu-audits", "3", "--oracle",
+                            os.path.join(ROOT, "oracle", "liboracle_bn254.so")], capture_output=True, text=True, timeout=300)
+        try:
+            small = json.loads(q.stdout)
+            d["small_run_64_blocks"] = {k: small[k] for k in ("legacy_equals_batched_state", "legacy_equals_batched_audits", "cpu_equals_legacy")}
+            if q.returncode != 0:
+                raise SystemExit("bench self-check failed: replay_config1 (64 blocks): the passes disagree: %s" % d["small_run_64_blocks"])
+        except ValueError:
+            d["small_run_64_blocks"] = {"error": (q.stdout + q.stderr)[-300:]}
         d["cpu_note"] = "the cpu pass is the first 128 updates and 5 audits against oracle/liboracle_bn254.so (C restatement, 8-thread " \
                         "pool as the reference); create_proof / verify_proof run in the library in every pass"
         return d
