@@ -34,7 +34,20 @@ struct MsmShape {
     uint32_t fixed_n;    // 0: general.  > 0: fixed-base table of stride fixed_n (windows share buckets)
     int glv_wh;          // 0: off.  > 0: GLV, windows per half; nwin = 2 * glv_wh, window w and w + glv_wh share buckets
     uint32_t phi_off;    // GLV: phi(P_i) is the table entry phi_off + i
+    // Bucket slice (one MSM over several devices, every device sees ALL terms): this launch keeps only the digits whose
+    // bucket (|d| - 1) is congruent to slice_r modulo 2^slice_shift and files them under the local bucket (|d| - 1) >>
+    // slice_shift; nbuckets is then the LOCAL count 2^(c-1) >> slice_shift.  The interleaving spreads every window --
+    // also the short top one and short (31-bit) scalars -- evenly over the slices.  slice_shift = 0: everything.
+    uint32_t slice_shift;
+    uint32_t slice_r;
 };
+
+// local bucket of digit magnitude `mag` (0xffffffff: not in this launch's slice, or mag == 0)
+PORLA_D uint32_t slice_bucket(const MsmShape& sh, uint32_t mag) {
+    const uint32_t b = mag - 1u;
+    if (mag == 0u || (b & ((1u << sh.slice_shift) - 1u)) != sh.slice_r) return 0xffffffffu;
+    return b >> sh.slice_shift;
+}
 
 // ---------------------------------------------------------------------------- small helpers
 template <class T>
@@ -377,12 +390,13 @@ k_digits(const uint8_t* __restrict__ scalars, int big_endian,
                     carry = dneg;
                     uint32_t mag = dneg ? ((1u << sh.c) - d) : d;
                     uint32_t neg = dneg ^ flip[h];
-                    if (mag != 0 && w >= w_begin && w < w_end) {
+                    const uint32_t lbk = slice_bucket(sh, mag);
+                    if (lbk != 0xffffffffu && w >= w_begin && w < w_end) {
                         if (sh.fixed_n) {
-                            bucket[k] = slot_base + (mag - 1);
+                            bucket[k] = slot_base + lbk;
                             val[k] = ((uint32_t)w * sh.fixed_n + pidx) | (neg << 31);
                         } else {
-                            bucket[k] = slot_base + (uint32_t)wl * sh.nbuckets + (mag - 1);
+                            bucket[k] = slot_base + (uint32_t)wl * sh.nbuckets + lbk;
                             val[k] = (pidx + (h ? sh.phi_off : 0u)) | (neg << 31);
                         }
                     }
@@ -618,9 +632,10 @@ k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const ui
                 uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + ((m >> w) & 1u);
                 uint32_t dneg = d > half;
                 uint32_t mag = dneg ? ((1u << sh.c) - d) : d;
-                if (mag != 0) {
-                    uint32_t r = atomicAdd(&cnt[(mag - 1) >> lb], 1u);     // r < kPartTile = 2^11
-                    item[q] = (mag - 1) | (r << 20) | ((dneg ^ ((m >> flip_bit) & 1u)) << 31);
+                const uint32_t lbk = slice_bucket(sh, mag);
+                if (lbk != 0xffffffffu) {
+                    uint32_t r = atomicAdd(&cnt[lbk >> lb], 1u);     // r < kPartTile = 2^11
+                    item[q] = lbk | (r << 20) | ((dneg ^ ((m >> flip_bit) & 1u)) << 31);
                 }
             }
         }
@@ -1179,7 +1194,8 @@ constexpr int kRedThreads = 64;
 template <class C>
 __global__ void __launch_bounds__(kRedThreads)
 k_reduce(const XYZZ<typename C::FC>* __restrict__ buckets, uint32_t nb, uint32_t chunk,
-         uint32_t threads_per_slot, uint32_t total_slots, XYZZ<typename C::FC>* __restrict__ partials) {
+         uint32_t threads_per_slot, uint32_t total_slots, XYZZ<typename C::FC>* __restrict__ partials,
+         uint32_t slice_shift, uint32_t slice_r) {
     using F = typename C::FC;
     __shared__ XYZZ<F> sh[kRedThreads];
     // Geometry (1-D grid; gridDim.y would cap the number of window slots at 65535):
@@ -1213,8 +1229,18 @@ k_reduce(const XYZZ<typename C::FC>* __restrict__ buckets, uint32_t nb, uint32_t
             run.add(bk);
             acc.add(run);
         }
-        if (lo != 0) {
-            XYZZ<F> w = mul_small(run, lo);
+        if (slice_shift == 0) {
+            if (lo != 0) {
+                XYZZ<F> w = mul_small(run, lo);
+                acc.add(w);
+            }
+        } else {
+            // bucket slice: local bucket k stands for the digit magnitude (k << slice_shift) + slice_r + 1, so the chunk is
+            // 2^shift * sum (k - lo + 1) B_k + ((lo - 1) * 2^shift + slice_r + 1) * S; written with non-negative weights as
+            // 2^shift * (acc - S) + ((lo << shift) + slice_r + 1) * S
+            acc.add(run.neg());
+            for (uint32_t d = 0; d < slice_shift; d++) acc = acc.dbl();
+            XYZZ<F> w = mul_small(run, (lo << slice_shift) + slice_r + 1u);
             acc.add(w);
         }
     }
@@ -1230,6 +1256,145 @@ k_reduce(const XYZZ<typename C::FC>* __restrict__ buckets, uint32_t nb, uint32_t
         __syncthreads();
     }
     if (local == 0 && slot < total_slots) st16(partials + out_index, sh[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------- bucket reduction, scan form (round 2)
+// The same weighted sum  sum_k (k + 1) B_k  per window slot as k_reduce, restated so that a thread holds ONE accumulator (128
+// registers: 16 warps per SM instead of 8 -- the multiplier pipe saturates at four warps per scheduler) and pays no per-thread
+// double-and-add weighting:  sum_k (k + 1) B_k = sum_k R_k  with R_k = sum_{j >= k} B_j the suffix sums.  A block of
+// kRsThreads threads owns m * kRsThreads consecutive buckets of one slot (m = 2^log_m per thread):
+//   1. thread t turns its chunk into LOCAL suffix sums in place (m - 1 additions, stored back over the buckets);
+//   2. a Hillis-Steele suffix scan over the chunk totals in shared memory gives RS_t = sum_{u >= t} S_u (log2 T steps);
+//   3. the block's sum of suffix sums is  sum_k R_k(local) + m * sum_{t >= 1} RS_t : thread t starts from 2^log_m * RS_t (t >= 1),
+//      adds m of the stored local suffix sums (strided, coalesced) and a shared-memory tree adds the threads up.
+// Output per block: its weighted sum with weights 1 .. m T (out_w) and its plain sum RS_0 (out_s); k_reduce_top combines the
+// blocks of a slot the same way (suffix scan over the block sums, weight 2^log_u = m T).  Slots with fewer than m T buckets
+// share a block (group = threads per slot, the scan and the tree stop at the group boundary).
+constexpr int kRsThreads = 128;
+constexpr int kTopMaxBlocks = 256;     // blocks per slot k_reduce_top combines with one thread each
+
+template <class C>
+__global__ void __launch_bounds__(kRsThreads, 4)
+k_reduce_scan(XYZZ<typename C::FC>* __restrict__ buckets, uint32_t nb, uint32_t log_m, uint32_t group, uint32_t total_slots,
+              XYZZ<typename C::FC>* __restrict__ out_w, XYZZ<typename C::FC>* __restrict__ out_s) {
+    using F = typename C::FC;
+    __shared__ XYZZ<F> sh[kRsThreads];
+    const uint32_t m = 1u << log_m;
+    uint32_t slot, blk, blocks_per_slot;
+    if (group == (uint32_t)kRsThreads) {
+        blocks_per_slot = (nb >> log_m) / kRsThreads;
+        slot = blockIdx.x / blocks_per_slot;
+        blk = blockIdx.x - slot * blocks_per_slot;
+    } else {
+        blocks_per_slot = 1;
+        slot = blockIdx.x * (kRsThreads / group) + threadIdx.x / group;
+        blk = 0;
+    }
+    const uint32_t l = threadIdx.x & (group - 1);          // thread within its slot's group
+    const bool live = slot < total_slots;
+    XYZZ<F>* base = buckets + (size_t)slot * nb + (size_t)blk * ((size_t)group << log_m);
+    // 1. local suffix sums of the chunk [l m, (l + 1) m), in place
+    XYZZ<F> a = XYZZ<F>::inf();
+    if (live) {
+        XYZZ<F>* p = base + ((size_t)l << log_m);
+        a = ld16(p + (m - 1));
+        for (uint32_t k = m - 1; k-- > 0;) {
+            a.add(ld16(p + k));
+            st16(p + k, a);
+        }
+    }
+    sh[threadIdx.x] = a;
+    __syncthreads();                                        // also orders the stores of step 1 before the loads of step 3
+    // 2. inclusive suffix scan of the chunk totals over the group
+    for (uint32_t d = 1; d < group; d <<= 1) {
+        const bool has = l + d < group;
+        XYZZ<F> b;
+        if (has) b = sh[threadIdx.x + d];
+        __syncthreads();
+        if (has) {
+            a.add(b);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (l == 0 && live) st16(out_s + (size_t)slot * blocks_per_slot + blk, a);
+    // 3. m * RS_l (l >= 1) + the local suffix sums l, l + group, ...
+    XYZZ<F> v = XYZZ<F>::inf();
+    if (l != 0) {
+        v = a;
+        for (uint32_t d = 0; d < log_m; d++) v = v.dbl();
+    }
+    if (live) {
+        for (uint32_t i = 0; i < m; i++) v.add(ld16(base + l + (size_t)i * group));
+    }
+    __syncthreads();
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (uint32_t o = group / 2; o > 0; o >>= 1) {
+        if (l < o) {
+            XYZZ<F> x = sh[threadIdx.x];
+            x.add(sh[threadIdx.x + o]);
+            sh[threadIdx.x] = x;
+        }
+        __syncthreads();
+    }
+    if (l == 0 && live) st16(out_w + (size_t)slot * blocks_per_slot + blk, sh[threadIdx.x]);
+}
+
+// One block per window slot, one thread per block of k_reduce_scan (nblk a power of two <= kTopMaxBlocks = blockDim.x):
+// window sum = sum_b W_b + 2^log_u * sum_b b S_b, the second term again as the sum of the suffix sums RS_b, b >= 1.
+// Bucket slice (MsmShape::slice_shift / slice_r): local bucket k stands for the digit magnitude (k << shift) + r + 1, so the
+// slot's sum is 2^shift * (Z1 - G) + (r + 1) G = 2^shift * Z1 - (2^shift - 1 - r) G with Z1 the 1-based sum and G = RS_0.
+template <class C>
+__global__ void __launch_bounds__(kTopMaxBlocks)
+k_reduce_top(const XYZZ<typename C::FC>* __restrict__ in_w, const XYZZ<typename C::FC>* __restrict__ in_s, uint32_t nblk,
+             uint32_t log_u, uint32_t slice_shift, uint32_t slice_r, XYZZ<typename C::FC>* __restrict__ wsum) {
+    using F = typename C::FC;
+    __shared__ XYZZ<F> sh[kTopMaxBlocks];
+    const uint32_t b = threadIdx.x;
+    const size_t at = (size_t)blockIdx.x * nblk + b;
+    XYZZ<F> a = XYZZ<F>::inf();
+    if (b < nblk) a = ld16(in_s + at);
+    sh[b] = a;
+    __syncthreads();
+    for (uint32_t d = 1; d < nblk; d <<= 1) {
+        const bool has = b + d < nblk;
+        XYZZ<F> x;
+        if (has) x = sh[b + d];
+        __syncthreads();
+        if (has) {
+            a.add(x);
+            sh[b] = a;
+        }
+        __syncthreads();
+    }
+    XYZZ<F> g = sh[0];                                       // RS_0: the plain sum of the slot's buckets
+    XYZZ<F> v = XYZZ<F>::inf();
+    if (b != 0 && b < nblk) {
+        v = a;
+        for (uint32_t d = 0; d < log_u; d++) v = v.dbl();
+    }
+    if (b < nblk) v.add(ld16(in_w + at));
+    __syncthreads();
+    sh[b] = v;
+    __syncthreads();
+    for (uint32_t o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (b < o) {
+            XYZZ<F> x = sh[b];
+            x.add(sh[b + o]);
+            sh[b] = x;
+        }
+        __syncthreads();
+    }
+    if (b == 0) {
+        XYZZ<F> z = sh[0];
+        if (slice_shift != 0) {
+            for (uint32_t d = 0; d < slice_shift; d++) z = z.dbl();
+            XYZZ<F> w = mul_small(g, (1u << slice_shift) - 1u - slice_r);
+            z.add(w.neg());
+        }
+        st16(wsum + blockIdx.x, z);
+    }
 }
 
 // ---------------------------------------------------------------------------- window sums

@@ -158,6 +158,41 @@ def test_window_sizes_agree(window, monkeypatch):
     assert got == O.bn254_marshal(O.msm(BN, sc, pts))
 
 
+@pytest.mark.parametrize("switch", ["PORLA_REDUCE_SCAN", "PORLA_SORT_V2", "PORLA_ACC_AFFINE"])
+@pytest.mark.parametrize("n,window", [(600, 9), (5000, 0), (70001, 0), ((1 << 19) + 5, 0)])
+def test_opt_in_kernel_variants_agree(switch, n, window, monkeypatch):
+    """The variants kept behind environment switches (measured slower, see profiles/r02*): the scan-form bucket reduction,
+    the sort without the exact histogram, the affine bucket accumulation.  Same bytes as the default pipeline; the large
+    sizes go through the resident path with points k_i G and the closed form (sum s_i k_i) G."""
+    import torch
+    rnd = random.Random(n)
+    if window:
+        monkeypatch.setenv("PORLA_WINDOW_BITS", str(window))
+    if n <= 5000:
+        pts = rand_points(BN, n, 5)
+        sc = [rnd.randrange(1 << 256) for _ in range(n)]
+        args = (enc_points(pts), b"".join(map(be, sc)), n)
+        want = pb.bn254_multi_exp(*args)
+        assert want == O.bn254_marshal(O.msm(BN, sc, pts))
+        monkeypatch.setenv(switch, "1")
+        assert pb.bn254_multi_exp(*args) == want
+        return
+    g = torch.Generator(device="cuda")
+    g.manual_seed(n)
+    ks = torch.randint(0, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda", generator=g)
+    ks[:, 1:] = 0
+    ss = torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda", generator=g)
+    tab = pb.Table.multiples_of_generator(pb.CURVE_BN254, ks.data_ptr(), n, pb.SCALAR_LE32, on_device=True)
+    kv = ks[:, 0].cpu().numpy().astype("uint32").tolist()
+    sv = ss.cpu().numpy().view("uint32")
+    total = sum(k * sum(int(v) << (32 * j) for j, v in enumerate(row)) for k, row in zip(kv, sv.tolist())) % BN.n
+    want = O.bn254_marshal(O.mul(BN, total, (1, 2)))
+    assert tab.msm_resident(ss.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32) == want
+    monkeypatch.setenv(switch, "1")
+    assert tab.msm_resident(ss.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32) == want
+    tab.destroy()
+
+
 def test_multiples_table_and_closed_form():
     # table[i] = k_i G; MSM(s, table) = (sum s_i k_i) G  -- size-independent checksum
     import torch
