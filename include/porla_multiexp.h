@@ -308,6 +308,9 @@ double porla_measure_pint(int variant, double min_seconds);
  * products (mode 0; 1 / 2: two / four independent chains per thread; 3: squarings) or point operations
  * (4: XYZZ add, 5: the same with the outlined multiplier, 6: mixed add, 7: doubling), `warps` warps. */
 int porla_debug_latency(int curve, int mode, int warps, int iters, double* cycles_per_op, double* ns_per_op);
+/* Parity harness of the four-lane point operations (csrc/quad.cuh): out64[i] = op(A_i, B_i) over two resident tables,
+ * op 0: A + B, 1: 2A, 2: 3A + B, 3: 32A (through the P + P branch), 4: (A + B) - B, 5: 2 (A + B) via scatter / gather. */
+void porla_debug_quad_op(int curve, int op, const porla_table* a, const porla_table* b, int64_t n, int point_fmt, void* out64);
 
 /* ---- test hooks (host buffers; GPU kernels underneath) */
 /* out[i] = a[i] (*) b[i], the device field product on raw 8x32 LE limbs: a*b mod p for secp256k1,

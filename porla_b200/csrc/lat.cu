@@ -12,6 +12,7 @@
 //   mode 6  acc.madd(p)   XYZZ + affine, inlined
 //   mode 7  acc = acc.dbl(), inlined
 //   mode 8  x = 1/x + y    binary-GCD inversion (fp_inv.cuh);   mode 9: the same with the Fermat inversion
+//   mode 10 / 11  quad_add / quad_dbl chains (quad.cuh: four lanes per point operation)
 //   mode + 100: the same chain on the whole device (4 blocks per SM): ns_per_op is then the time per operation of a thread under load
 // Measured (B200, BN254): 838 cycles per product with one warp per scheduler whether the thread runs one,
 // two or four independent chains -- also with the two products interleaved round by round at source level
@@ -22,6 +23,7 @@
 #include "../../include/porla_multiexp.h"
 #include "msm.h"
 #include "msm_kernels.cuh"
+#include "quad.cuh"
 
 struct porla_table {   // as in abi.cu
     porla::PointTable t;
@@ -77,6 +79,16 @@ __global__ void k_latency(int mode, int iters, const Affine<typename C::F>* __re
     } else if (mode == 7) {
 #pragma unroll 1
         for (int i = 0; i < iters; i++) acc = acc.dbl();
+    } else if (mode == 10 || mode == 11) {   // four lanes per point (quad.cuh): addition / doubling chains
+        QuadPoint<F> qa = QuadPoint<F>::scatter(acc, 0), qo = QuadPoint<F>::scatter(other, 0);
+        if (mode == 10) {
+#pragma unroll 1
+            for (int i = 0; i < iters; i++) qa = quad_add(qa, qo);
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < iters; i++) qa = quad_dbl(qa);
+        }
+        acc = qa.gather();
     } else if (mode == 8) {   // binary-GCD inversion (fp_inv.cuh), a dependent chain
 #pragma unroll 1
         for (int i = 0; i < iters; i++) x0 = x0.inverse() + y;
@@ -90,7 +102,67 @@ __global__ void k_latency(int mode, int iters, const Affine<typename C::F>* __re
     if (acc.x.v[0] == 0x12345678u && acc.y.v[1] == 0x9abcdef0u) *sink = acc;   // keep the work alive
 }
 
+// Parity harness of quad.cuh: out[i] = op(A_i, B_i), one quad per i (see porla_debug_quad_op).
+template <class C>
+__global__ void k_quad_op(int op, const Affine<typename C::F>* __restrict__ a, const Affine<typename C::F>* __restrict__ b, uint32_t n,
+                          XYZZ<typename C::F>* __restrict__ out) {
+    using F = typename C::F;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const uint32_t j = i < n ? i : 0;
+    QuadPoint<F> A = QuadPoint<F>::load_affine(a + j, false), B = QuadPoint<F>::load_affine(b + j, false);
+    if (i >= n) A = B = QuadPoint<F>::inf();
+    QuadPoint<F> r = QuadPoint<F>::inf();
+    if (op == 0) r = quad_add(A, B);
+    else if (op == 1) r = quad_dbl(A);
+    else if (op == 2) r = quad_add(quad_dbl(A), quad_add(A, B));                  // 3A + B on general XYZZ operands
+    else if (op == 3) {                                                            // 32 A through the P + P branch of quad_add
+        r = A;
+        for (int k = 0; k < 5; k++) r = quad_add(r, r);
+    } else if (op == 4) r = quad_add(quad_add(A, B), QuadPoint<F>::load_affine(b + j, true));   // (A + B) - B = A, or inf cases
+    else if (op == 5) {                                                            // scatter / gather round trip of the thread form
+        XYZZ<F> t = XYZZ<F>::from_affine(ld16(a + j));
+        t.madd(ld16(b + j));
+        r = QuadPoint<F>::scatter(t, (int)(i & 3));
+        XYZZ<F> g = r.gather();
+        g = g.dbl();
+        r = QuadPoint<F>::scatter(g, (int)((i + 1) & 3));                          // 2 (A + B)
+    }
+    else if (op == 100) r = A;
+    else if (op == 101) r.c = A.c * quad_xor(B.c, 2);
+    else if (op == 102) r = quad_add(A, B);
+    else if (op == 103) r = quad_dbl(A);
+    if (i < n) r.store(out + i);
+}
+
 }  // namespace porla
+
+// out64[i] (affine, external bytes) = op(A_i, B_i) computed with the four-lane point operations of quad.cuh:
+// op 0: A + B, 1: 2A, 2: 3A + B, 3: 32A, 4: (A + B) - B, 5: 2 (A + B) through scatter / gather.
+extern "C" void porla_debug_quad_op(int curve, int op, const porla_table* a, const porla_table* b, int64_t n, int point_fmt, void* out64) {
+    using namespace porla;
+    device_init();
+    void* d_x = nullptr;
+    uint8_t* d_out = nullptr;
+    PORLA_CUDA(cudaMalloc(&d_x, (size_t)n * 128 + 128));
+    PORLA_CUDA(cudaMalloc(&d_out, (size_t)n * 64 + 64));
+    const uint32_t threads = (uint32_t)n * 4, blocks = (threads + 127) / 128;
+    if (curve == kCurveBn254) {
+        k_quad_op<Bn254><<<blocks, 128>>>(op, reinterpret_cast<const Affine<Bn254::F>*>(a->t.d_points),
+                                          reinterpret_cast<const Affine<Bn254::F>*>(b->t.d_points), (uint32_t)n, reinterpret_cast<XYZZ<Bn254::F>*>(d_x));
+        k_finalize<Bn254><<<((uint32_t)n + 31) / 32, 32>>>(reinterpret_cast<const XYZZ<Bn254::FC>*>(d_x), (uint32_t)n, 1, 1, point_fmt, d_out, nullptr);
+    } else {
+        k_quad_op<Secp256k1><<<blocks, 128>>>(op, reinterpret_cast<const Affine<Secp256k1::F>*>(a->t.d_points),
+                                              reinterpret_cast<const Affine<Secp256k1::F>*>(b->t.d_points), (uint32_t)n,
+                                              reinterpret_cast<XYZZ<Secp256k1::F>*>(d_x));
+        k_finalize<Secp256k1><<<((uint32_t)n + 31) / 32, 32>>>(reinterpret_cast<const XYZZ<Secp256k1::FC>*>(d_x), (uint32_t)n, 1, 1, point_fmt, d_out,
+                                                               nullptr);
+    }
+    PORLA_CUDA(cudaGetLastError());
+    if (op >= 100) PORLA_CUDA(cudaMemcpy(out64, d_x, (size_t)n * 128, cudaMemcpyDeviceToHost));     // raw records (debugging)
+    else PORLA_CUDA(cudaMemcpy(out64, d_out, (size_t)n * 64, cudaMemcpyDeviceToHost));
+    PORLA_CUDA(cudaFree(d_x));
+    PORLA_CUDA(cudaFree(d_out));
+}
 
 extern "C" int porla_debug_latency(int curve, int mode, int warps, int iters, double* cycles_per_op, double* ns_per_op) {
     using namespace porla;

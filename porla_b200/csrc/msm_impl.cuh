@@ -242,24 +242,22 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     if (chunk > sh.nbuckets) chunk = sh.nbuckets;
     uint32_t threads_per_slot = (sh.nbuckets + chunk - 1) / chunk;  // nbuckets and chunk are powers of two
     uint32_t blocks_per_slot = (threads_per_slot + kRedThreads - 1) / kRedThreads;
-    // Scan form (k_reduce_scan, opt-in: PORLA_REDUCE_SCAN=1): m = 2^log_m buckets per thread, the smallest chunk that leaves at
-    // most one resident wave of threads (148 SMs x 4 blocks x 128), at most 64, at least what keeps a slot within kTopMaxBlocks
-    // blocks; PORLA_REDUCE_CHUNK overrides.  Measured slower than k_reduce at every size (2^16 0.35 against 0.25 ms, 2^20 0.60
-    // against 0.45, 2^21 1.12 against 0.92, 2^24 equal: profiles/r02c_bucket_slices_and_scan_reduce.md): two warps per
-    // scheduler already saturate the multiplier pipe, so the 16 resident warps per SM of the one-accumulator form buy nothing
-    // and its scan and tree steps run with partly empty warps.
-    const bool reduce_v1 = getenv("PORLA_REDUCE_SCAN") == nullptr;
+    // Scan form on quads (k_reduce_scan + k_reduce_top: four lanes per point, 2.35 us per dependent addition instead of 6.9):
+    // used while the reduction is bound by the depth of its additions, i.e. up to PORLA_REDUCE_QUAD_MAX buckets in total
+    // (default 600 k; above that k_reduce is near the multiplier pipe's limit and the quads' extra pipe work loses).  m = 2^log_m
+    // buckets per quad: the smallest chunk that leaves at most PORLA_REDUCE_QUADS quads in flight (default 148 x 64: one block
+    // of 64 quads, 8 warps, per SM), at most 64 and at least what keeps a slot within kTopMaxBlocks blocks.
+    // PORLA_REDUCE_V1=1 keeps the round-1 kernel at every size.
+    static const uint64_t quad_max = [] { const char* e = getenv("PORLA_REDUCE_QUAD_MAX"); return e ? (uint64_t)atoll(e) : 600000ull; }();
+    static const uint64_t quad_target = [] { const char* e = getenv("PORLA_REDUCE_QUADS"); return e && atoll(e) > 0 ? (uint64_t)atoll(e) : 148ull * kQuadsPerBlock; }();
+    const bool reduce_v1 = getenv("PORLA_REDUCE_V1") != nullptr || (uint64_t)nbt > quad_max;
     uint32_t log_m = 0;
-    while (log_m < 6 && ((uint64_t)nbt >> log_m) > 148ull * 4ull * kRsThreads) log_m++;
-    if (const char* e = getenv("PORLA_REDUCE_CHUNK")) {
-        log_m = 0;
-        while ((2u << log_m) <= (uint32_t)atoi(e)) log_m++;
-    }
-    while ((sh.nbuckets >> log_m) > (uint32_t)(kTopMaxBlocks * kRsThreads)) log_m++;
+    while (log_m < 6 && ((uint64_t)nbt >> log_m) > quad_target) log_m++;
+    while ((sh.nbuckets >> log_m) > (uint32_t)(kTopMaxBlocks * kQuadsPerBlock)) log_m++;
     while (log_m > 0 && (1u << log_m) > sh.nbuckets) log_m--;
-    const uint32_t scan_tps = sh.nbuckets >> log_m;                                        // threads per slot
-    const uint32_t scan_group = scan_tps >= (uint32_t)kRsThreads ? (uint32_t)kRsThreads : scan_tps;
-    const uint32_t scan_bps = scan_tps >= (uint32_t)kRsThreads ? scan_tps / kRsThreads : 1u;   // blocks per slot
+    const uint32_t scan_tps = sh.nbuckets >> log_m;                                        // quads per slot
+    const uint32_t scan_group = scan_tps >= (uint32_t)kQuadsPerBlock ? (uint32_t)kQuadsPerBlock : scan_tps;
+    const uint32_t scan_bps = scan_tps >= (uint32_t)kQuadsPerBlock ? scan_tps / kQuadsPerBlock : 1u;   // blocks per slot
     if (!reduce_v1) blocks_per_slot = 2 * scan_bps;                                        // partials: out_w then out_s
 
     // accumulation geometry: slice length L (pairs per thread)
@@ -530,18 +528,17 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
             window_sums = wsum;
         }
     } else {
-        XC* out_w = (XC*)partials;
-        XC* out_s = out_w + slots * scan_bps;
-        const uint32_t sgrid = scan_group == (uint32_t)kRsThreads
+        XYZZ<F>* out_w = partials;
+        XYZZ<F>* out_s = out_w + slots * scan_bps;
+        const uint32_t sgrid = scan_group == (uint32_t)kQuadsPerBlock
                                    ? (uint32_t)(slots * scan_bps)
-                                   : (uint32_t)((slots + kRsThreads / scan_group - 1) / (kRsThreads / scan_group));
-        k_reduce_scan<C><<<sgrid, kRsThreads, 0, stream>>>((XC*)buckets, sh.nbuckets, log_m, scan_group, (uint32_t)slots, out_w, out_s);
+                                   : (uint32_t)((slots + kQuadsPerBlock / scan_group - 1) / (kQuadsPerBlock / scan_group));
+        k_reduce_scan<C><<<sgrid, kQuadThreads, 0, stream>>>(buckets, sh.nbuckets, log_m, scan_group, (uint32_t)slots, out_w, out_s);
         LAUNCHED();
         if (scan_bps > 1 || sh.slice_shift != 0) {
-            uint32_t log_u = log_m;                      // weight of one block: m * kRsThreads buckets
-            while ((1u << log_u) < ((uint32_t)kRsThreads << log_m)) log_u++;
-            k_reduce_top<C><<<(uint32_t)slots, scan_bps < 32 ? 32 : scan_bps, 0, stream>>>(out_w, out_s, scan_bps, log_u, sh.slice_shift,
-                                                                                       sh.slice_r, (XC*)wsum);
+            uint32_t log_u = log_m;                      // weight of one block: m * kQuadsPerBlock buckets
+            while ((1u << log_u) < ((uint32_t)kQuadsPerBlock << log_m)) log_u++;
+            k_reduce_top<C><<<(uint32_t)slots, kQuadThreads, 0, stream>>>(out_w, out_s, scan_bps, log_u, sh.slice_shift, sh.slice_r, wsum);
             LAUNCHED();
             window_sums = wsum;
         }

@@ -18,6 +18,7 @@
 // XYZZ records; the sorted index array is 4 B per (point, window) pair.
 #pragma once
 #include "ec.cuh"
+#include "quad.cuh"
 
 namespace porla {
 
@@ -1258,142 +1259,162 @@ k_reduce(const XYZZ<typename C::FC>* __restrict__ buckets, uint32_t nb, uint32_t
     if (local == 0 && slot < total_slots) st16(partials + out_index, sh[threadIdx.x]);
 }
 
-// ---------------------------------------------------------------------------- bucket reduction, scan form (round 2)
-// The same weighted sum  sum_k (k + 1) B_k  per window slot as k_reduce, restated so that a thread holds ONE accumulator (128
-// registers: 16 warps per SM instead of 8 -- the multiplier pipe saturates at four warps per scheduler) and pays no per-thread
-// double-and-add weighting:  sum_k (k + 1) B_k = sum_k R_k  with R_k = sum_{j >= k} B_j the suffix sums.  A block of
-// kRsThreads threads owns m * kRsThreads consecutive buckets of one slot (m = 2^log_m per thread):
-//   1. thread t turns its chunk into LOCAL suffix sums in place (m - 1 additions, stored back over the buckets);
+// ---------------------------------------------------------------------------- bucket reduction, scan form on quads (round 2)
+// Below ~half a million buckets k_reduce is bound by the DEPTH of its dependent additions (6.9 us each on a lone warp), not
+// by the multiplier pipe.  This form shortens every addition instead: four lanes per point (quad.cuh, 2.35 us per addition),
+// and replaces the per-thread double-and-add weighting by scans:  sum_k (k + 1) B_k = sum_k R_k  with R_k = sum_{j >= k} B_j.
+// A block of kQuadsPerBlock quads owns m * kQuadsPerBlock consecutive buckets of one slot (m = 2^log_m per quad):
+//   1. quad t turns its chunk into LOCAL suffix sums in place (m - 1 additions, stored back over the buckets);
 //   2. a Hillis-Steele suffix scan over the chunk totals in shared memory gives RS_t = sum_{u >= t} S_u (log2 T steps);
-//   3. the block's sum of suffix sums is  sum_k R_k(local) + m * sum_{t >= 1} RS_t : thread t starts from 2^log_m * RS_t (t >= 1),
-//      adds m of the stored local suffix sums (strided, coalesced) and a shared-memory tree adds the threads up.
+//   3. the block's sum of suffix sums is  sum_k R_k(local) + m * sum_{t >= 1} RS_t : quad t starts from 2^log_m * RS_t (t >= 1),
+//      adds m of the stored local suffix sums (strided, coalesced) and a shared-memory tree adds the quads up.
 // Output per block: its weighted sum with weights 1 .. m T (out_w) and its plain sum RS_0 (out_s); k_reduce_top combines the
 // blocks of a slot the same way (suffix scan over the block sums, weight 2^log_u = m T).  Slots with fewer than m T buckets
-// share a block (group = threads per slot, the scan and the tree stop at the group boundary).
-constexpr int kRsThreads = 128;
-constexpr int kTopMaxBlocks = 256;     // blocks per slot k_reduce_top combines with one thread each
+// share a block (group = quads per slot; the scan and the tree stop at the group boundary).
+// (The same scan form with one THREAD per chunk was measured slower than k_reduce at every size:
+// profiles/r02c_bucket_slices_and_scan_reduce.md.)
+constexpr int kQuadsPerBlock = 64;
+constexpr int kQuadThreads = 4 * kQuadsPerBlock;
+constexpr int kTopMaxBlocks = kQuadsPerBlock;     // blocks per slot k_reduce_top combines with one quad each
+
+// ONE copy of the four-lane addition / doubling per kernel (seven inlined field products each time otherwise)
+template <class F>
+__device__ __noinline__ QuadPoint<F> quad_add_nl(QuadPoint<F> a, QuadPoint<F> b) { return quad_add(a, b); }
+template <class F>
+__device__ __noinline__ QuadPoint<F> quad_dbl_nl(QuadPoint<F> a) { return quad_dbl(a); }
+
+template <class F>
+PORLA_D QuadPoint<F> quad_from_shared(const XYZZ<F>* p) { return QuadPoint<F>{reinterpret_cast<const F*>(p)[threadIdx.x & 3]}; }
+template <class F>
+PORLA_D void quad_to_shared(XYZZ<F>* p, const QuadPoint<F>& v) { reinterpret_cast<F*>(p)[threadIdx.x & 3] = v.c; }
+
+// sum of sh[first .. first + count) (count a power of two) into sh[first]; l = this quad's index within the group.
+// Every warp of the block must call (barriers); warps whose quads all lie outside a level skip its arithmetic.
+template <class F>
+PORLA_D void quad_tree_sum(XYZZ<F>* sh, uint32_t q, uint32_t l, uint32_t count) {
+    for (uint32_t o = count / 2; o > 0; o >>= 1) {
+        const bool act = l < o;
+        if (__any_sync(kFullMask, act)) {
+            QuadPoint<F> x = QuadPoint<F>::inf(), y = QuadPoint<F>::inf();
+            if (act) {
+                x = quad_from_shared(&sh[q]);
+                y = quad_from_shared(&sh[q + o]);
+            }
+            x = quad_add_nl(x, y);
+            if (act) quad_to_shared(&sh[q], x);
+        }
+        __syncthreads();
+    }
+}
+
+// inclusive suffix scan over the group's values (a = this quad's value, also left in sh[q])
+template <class F>
+PORLA_D QuadPoint<F> quad_suffix_scan(XYZZ<F>* sh, uint32_t q, uint32_t l, uint32_t count, QuadPoint<F> a) {
+    quad_to_shared(&sh[q], a);
+    __syncthreads();
+    for (uint32_t d = 1; d < count; d <<= 1) {
+        const bool has = l + d < count;
+        QuadPoint<F> b = QuadPoint<F>::inf();
+        if (has) b = quad_from_shared(&sh[q + d]);
+        __syncthreads();
+        a = quad_add_nl(a, b);
+        if (has) quad_to_shared(&sh[q], a);
+        __syncthreads();
+    }
+    return a;
+}
 
 template <class C>
-__global__ void __launch_bounds__(kRsThreads, 4)
-k_reduce_scan(XYZZ<typename C::FC>* __restrict__ buckets, uint32_t nb, uint32_t log_m, uint32_t group, uint32_t total_slots,
-              XYZZ<typename C::FC>* __restrict__ out_w, XYZZ<typename C::FC>* __restrict__ out_s) {
-    using F = typename C::FC;
-    __shared__ XYZZ<F> sh[kRsThreads];
+__global__ void __launch_bounds__(kQuadThreads)
+k_reduce_scan(XYZZ<typename C::F>* __restrict__ buckets, uint32_t nb, uint32_t log_m, uint32_t group, uint32_t total_slots,
+              XYZZ<typename C::F>* __restrict__ out_w, XYZZ<typename C::F>* __restrict__ out_s) {
+    using F = typename C::F;
+    using Q = QuadPoint<F>;
+    __shared__ XYZZ<F> sh[kQuadsPerBlock];
     const uint32_t m = 1u << log_m;
+    const uint32_t q = threadIdx.x >> 2;
     uint32_t slot, blk, blocks_per_slot;
-    if (group == (uint32_t)kRsThreads) {
-        blocks_per_slot = (nb >> log_m) / kRsThreads;
+    if (group == (uint32_t)kQuadsPerBlock) {
+        blocks_per_slot = (nb >> log_m) / kQuadsPerBlock;
         slot = blockIdx.x / blocks_per_slot;
         blk = blockIdx.x - slot * blocks_per_slot;
     } else {
         blocks_per_slot = 1;
-        slot = blockIdx.x * (kRsThreads / group) + threadIdx.x / group;
+        slot = blockIdx.x * (kQuadsPerBlock / group) + q / group;
         blk = 0;
     }
-    const uint32_t l = threadIdx.x & (group - 1);          // thread within its slot's group
+    const uint32_t l = q & (group - 1);                    // quad within its slot's group
     const bool live = slot < total_slots;
     XYZZ<F>* base = buckets + (size_t)slot * nb + (size_t)blk * ((size_t)group << log_m);
     // 1. local suffix sums of the chunk [l m, (l + 1) m), in place
-    XYZZ<F> a = XYZZ<F>::inf();
-    if (live) {
-        XYZZ<F>* p = base + ((size_t)l << log_m);
-        a = ld16(p + (m - 1));
-        for (uint32_t k = m - 1; k-- > 0;) {
-            a.add(ld16(p + k));
-            st16(p + k, a);
-        }
+    XYZZ<F>* p = base + ((size_t)l << log_m);
+    Q a = Q::inf();
+    if (live) a = Q::load(p + (m - 1));
+    for (uint32_t k = m - 1; k-- > 0;) {
+        Q b = Q::inf();
+        if (live) b = Q::load(p + k);
+        a = quad_add_nl(a, b);
+        if (live) a.store(p + k);
     }
-    sh[threadIdx.x] = a;
-    __syncthreads();                                        // also orders the stores of step 1 before the loads of step 3
-    // 2. inclusive suffix scan of the chunk totals over the group
-    for (uint32_t d = 1; d < group; d <<= 1) {
-        const bool has = l + d < group;
-        XYZZ<F> b;
-        if (has) b = sh[threadIdx.x + d];
-        __syncthreads();
-        if (has) {
-            a.add(b);
-            sh[threadIdx.x] = a;
-        }
-        __syncthreads();
-    }
-    if (l == 0 && live) st16(out_s + (size_t)slot * blocks_per_slot + blk, a);
+    // 2. inclusive suffix scan of the chunk totals over the group (its first barrier also orders step 1's stores before step 3)
+    a = quad_suffix_scan(sh, q, l, group, a);
+    if (l == 0 && live) a.store(out_s + (size_t)slot * blocks_per_slot + blk);
     // 3. m * RS_l (l >= 1) + the local suffix sums l, l + group, ...
-    XYZZ<F> v = XYZZ<F>::inf();
-    if (l != 0) {
-        v = a;
-        for (uint32_t d = 0; d < log_m; d++) v = v.dbl();
-    }
-    if (live) {
-        for (uint32_t i = 0; i < m; i++) v.add(ld16(base + l + (size_t)i * group));
+    Q v = l != 0 ? a : Q::inf();
+    for (uint32_t d = 0; d < log_m; d++) v = quad_dbl_nl(v);
+    for (uint32_t i = 0; i < m; i++) {
+        Q b = Q::inf();
+        if (live) b = Q::load(base + l + (size_t)i * group);
+        v = quad_add_nl(v, b);
     }
     __syncthreads();
-    sh[threadIdx.x] = v;
+    quad_to_shared(&sh[q], v);
     __syncthreads();
-    for (uint32_t o = group / 2; o > 0; o >>= 1) {
-        if (l < o) {
-            XYZZ<F> x = sh[threadIdx.x];
-            x.add(sh[threadIdx.x + o]);
-            sh[threadIdx.x] = x;
-        }
-        __syncthreads();
-    }
-    if (l == 0 && live) st16(out_w + (size_t)slot * blocks_per_slot + blk, sh[threadIdx.x]);
+    quad_tree_sum(sh, q, l, group);
+    if (l == 0 && live) quad_from_shared(&sh[q]).store(out_w + (size_t)slot * blocks_per_slot + blk);
 }
 
-// One block per window slot, one thread per block of k_reduce_scan (nblk a power of two <= kTopMaxBlocks = blockDim.x):
+// One block per window slot, one quad per block of k_reduce_scan (nblk a power of two <= kTopMaxBlocks):
 // window sum = sum_b W_b + 2^log_u * sum_b b S_b, the second term again as the sum of the suffix sums RS_b, b >= 1.
 // Bucket slice (MsmShape::slice_shift / slice_r): local bucket k stands for the digit magnitude (k << shift) + r + 1, so the
 // slot's sum is 2^shift * (Z1 - G) + (r + 1) G = 2^shift * Z1 - (2^shift - 1 - r) G with Z1 the 1-based sum and G = RS_0.
 template <class C>
-__global__ void __launch_bounds__(kTopMaxBlocks)
-k_reduce_top(const XYZZ<typename C::FC>* __restrict__ in_w, const XYZZ<typename C::FC>* __restrict__ in_s, uint32_t nblk,
-             uint32_t log_u, uint32_t slice_shift, uint32_t slice_r, XYZZ<typename C::FC>* __restrict__ wsum) {
-    using F = typename C::FC;
-    __shared__ XYZZ<F> sh[kTopMaxBlocks];
-    const uint32_t b = threadIdx.x;
+__global__ void __launch_bounds__(kQuadThreads)
+k_reduce_top(const XYZZ<typename C::F>* __restrict__ in_w, const XYZZ<typename C::F>* __restrict__ in_s, uint32_t nblk,
+             uint32_t log_u, uint32_t slice_shift, uint32_t slice_r, XYZZ<typename C::F>* __restrict__ wsum) {
+    using F = typename C::F;
+    using Q = QuadPoint<F>;
+    __shared__ XYZZ<F> sh[kQuadsPerBlock];
+    const uint32_t b = threadIdx.x >> 2;
     const size_t at = (size_t)blockIdx.x * nblk + b;
-    XYZZ<F> a = XYZZ<F>::inf();
-    if (b < nblk) a = ld16(in_s + at);
-    sh[b] = a;
+    const bool live = b < nblk;
+    Q a = Q::inf();
+    if (live) a = Q::load(in_s + at);
+    a = quad_suffix_scan(sh, b, b, nblk, a);                // quads >= nblk hold infinity and stay out of it
+    const Q g = quad_from_shared(&sh[0]);                   // RS_0: the plain sum of the slot's buckets
+    Q v = (b != 0 && live) ? a : Q::inf();
+    for (uint32_t d = 0; d < log_u; d++) v = quad_dbl_nl(v);
+    Q w = Q::inf();
+    if (live) w = Q::load(in_w + at);
+    v = quad_add_nl(v, w);
     __syncthreads();
-    for (uint32_t d = 1; d < nblk; d <<= 1) {
-        const bool has = b + d < nblk;
-        XYZZ<F> x;
-        if (has) x = sh[b + d];
-        __syncthreads();
-        if (has) {
-            a.add(x);
-            sh[b] = a;
-        }
-        __syncthreads();
-    }
-    XYZZ<F> g = sh[0];                                       // RS_0: the plain sum of the slot's buckets
-    XYZZ<F> v = XYZZ<F>::inf();
-    if (b != 0 && b < nblk) {
-        v = a;
-        for (uint32_t d = 0; d < log_u; d++) v = v.dbl();
-    }
-    if (b < nblk) v.add(ld16(in_w + at));
+    quad_to_shared(&sh[b], v);
     __syncthreads();
-    sh[b] = v;
-    __syncthreads();
-    for (uint32_t o = blockDim.x / 2; o > 0; o >>= 1) {
-        if (b < o) {
-            XYZZ<F> x = sh[b];
-            x.add(sh[b + o]);
-            sh[b] = x;
-        }
-        __syncthreads();
-    }
-    if (b == 0) {
-        XYZZ<F> z = sh[0];
+    quad_tree_sum(sh, b, b, nblk);
+    if (threadIdx.x < 32) {                                  // quad 0 finishes (its warp keeps it company)
+        Q z = quad_from_shared(&sh[0]);
         if (slice_shift != 0) {
-            for (uint32_t d = 0; d < slice_shift; d++) z = z.dbl();
-            XYZZ<F> w = mul_small(g, (1u << slice_shift) - 1u - slice_r);
-            z.add(w.neg());
+            for (uint32_t d = 0; d < slice_shift; d++) z = quad_dbl_nl(z);
+            const uint32_t k = (1u << slice_shift) - 1u - slice_r;       // < 2^slice_shift <= 8
+            Q t = Q::inf();
+            for (int bit = 3; bit >= 0; bit--) {
+                t = quad_dbl_nl(t);
+                t = quad_add_nl(t, ((k >> bit) & 1u) ? g : Q::inf());
+            }
+            if ((threadIdx.x & 3) == 1) t.c = t.c.neg();
+            z = quad_add_nl(z, t);
         }
-        st16(wsum + blockIdx.x, z);
+        if (b == 0) z.store(wsum + blockIdx.x);
     }
 }
 

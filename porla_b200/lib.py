@@ -38,7 +38,7 @@ NEW_SYMBOLS = [
     "porla_mtable_msm_host_scalars", "porla_mtable_msm_resident", "porla_mtable_scalars_upload", "porla_mtable_scalars_free",
     "porla_mtable_destroy", "porla_debug_copy_ring_bytes", "porla_msm_host_devices", "porla_debug_h2d_rate",
     "porla_mtable_create_replicated", "porla_mtable_slices", "porla_msm_max_slices", "porla_msm_slice_bucket_bytes",
-    "porla_msm_slice_window_sums_device",
+    "porla_msm_slice_window_sums_device", "porla_debug_quad_op",
 ]
 
 
@@ -134,6 +134,7 @@ def load() -> C.CDLL:
         "porla_secp256k1_inner_product_prove": (C.c_size_t, [P, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p]),
         "porla_secp256k1_inner_product_verify": (I, [P, C.c_size_t, C.POINTER(SecpGej), C.c_char_p]),
         "porla_debug_latency": (I, [I, I, I, I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "porla_debug_quad_op": (None, [I, I, P, P, C.c_int64, I, P]),
         "porla_debug_field_mul": (None, [I, P, P, C.c_int64, P]),
         "porla_debug_field_op": (None, [I, I, P, P, C.c_int64, P]),
         "porla_debug_point_add_host": (None, [I, P, P, C.c_int64, I, P]),

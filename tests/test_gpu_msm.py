@@ -158,7 +158,7 @@ def test_window_sizes_agree(window, monkeypatch):
     assert got == O.bn254_marshal(O.msm(BN, sc, pts))
 
 
-@pytest.mark.parametrize("switch", ["PORLA_REDUCE_SCAN", "PORLA_SORT_V2", "PORLA_ACC_AFFINE"])
+@pytest.mark.parametrize("switch", ["PORLA_REDUCE_V1", "PORLA_SORT_V2", "PORLA_ACC_AFFINE"])
 @pytest.mark.parametrize("n,window", [(600, 9), (5000, 0), (70001, 0), ((1 << 19) + 5, 0)])
 def test_opt_in_kernel_variants_agree(switch, n, window, monkeypatch):
     """The variants kept behind environment switches (measured slower, see profiles/r02*): the scan-form bucket reduction,

@@ -8,6 +8,7 @@ against the sort / accumulate / reduce pipeline, through the C-ABI.
 
 PORLA_NO_SMALL=1 forces the pipeline, so every case is computed twice and both must equal the oracle.
 """
+import ctypes as C
 import random
 
 import pytest
@@ -462,3 +463,47 @@ def test_data_butterfly_stage_matches_reference_arithmetic(lcm, n_blocks, chunks
         for p in range(chunks):
             off = 64 * (i * chunks + p)
             assert int.from_bytes(buf[off:off + 64], "little") == want[i][p], (i, p)
+
+
+# ---------------------------------------------------------------------------- four lanes per point operation (quad.cuh)
+@pytest.mark.parametrize("curve", [pb.CURVE_BN254, pb.CURVE_SECP256K1])
+def test_quad_point_operations_match_oracle(curve):
+    """quad_add / quad_dbl (one coordinate per lane, one field product per lane and level) against the oracle's affine
+    group law on random points, points at infinity on either side, equal points (P + P) and opposite points (P - P)."""
+    c = O.BN254 if curve == pb.CURVE_BN254 else O.SECP256K1
+    G = (c.gx, c.gy)
+    rnd = random.Random(77 + curve)
+    n = 61
+    A = [O.mul(c, rnd.randrange(1, c.n), G) for _ in range(n)]
+    B = [O.mul(c, rnd.randrange(1, c.n), G) for _ in range(n)]
+    for i in range(0, n, 7):
+        B[i] = A[i]                                    # P + P
+    for i in range(1, n, 7):
+        B[i] = (A[i][0], (c.p - A[i][1]) % c.p)        # P - P
+    for i in range(2, n, 7):
+        A[i] = None                                    # infinity + Q
+    for i in range(3, n, 7):
+        B[i] = None                                    # P + infinity
+    A[4] = B[4] = None
+    enc = lambda P: bytes(64) if P is None else P[0].to_bytes(32, "big") + P[1].to_bytes(32, "big")
+    ta = pb.Table.from_host(curve, b"".join(map(enc, A)))
+    tb = pb.Table.from_host(curve, b"".join(map(enc, B)))
+    add = lambda P, Q: O.add(c, P, Q)
+    neg = lambda P: None if P is None else (P[0], (c.p - P[1]) % c.p)
+    want = {
+        0: [add(a, b) for a, b in zip(A, B)],
+        1: [add(a, a) for a in A],
+        2: [add(add(a, a), add(a, b)) for a, b in zip(A, B)],
+        3: [O.mul(c, 32, a) if a is not None else None for a in A],
+        4: [add(add(a, b), neg(b)) for a, b in zip(A, B)],
+        5: [add(add(a, b), add(a, b)) for a, b in zip(A, B)],
+    }
+    out = (C.c_ubyte * (64 * n))()
+    bad = []
+    for op, exp in want.items():
+        pb.load().porla_debug_quad_op(curve, op, C.c_void_p(ta.handle), C.c_void_p(tb.handle), n, pb.POINT_BE64, out)
+        got = bytes(out)
+        bad += [(op, i) for i in range(n) if got[64 * i:64 * i + 64] != enc(exp[i])]
+    assert not bad, bad
+    ta.destroy()
+    tb.destroy()
