@@ -632,7 +632,14 @@ void butterfly_impl(PointTable* t, uint32_t m, const uint8_t* d_twiddles, int sc
     auto* pf = reinterpret_cast<Affine<typename C::F>*>(t->d_points);
     auto* pc = reinterpret_cast<Affine<typename C::FC>*>(t->d_points);
     const dim3 grid((nb + 127) / 128);
-    if (inlined && glv) k_butterfly<C, typename C::F, true><<<grid, 128, 0, stream>>>(pf, t->d_flags, t->n, m, d_twiddles, scalar_be);
+    // Few butterflies (at most two warps of quads per scheduler: 148 x 4 x 2 x 8 = 9472): four lanes per butterfly
+    // (k_butterfly_quad; PORLA_BUTTERFLY_QUAD=0 / 1 forces).  Measured per stage at n = 1024: see DESIGN.md section 4.
+    const char* fq = getenv("PORLA_BUTTERFLY_QUAD");
+    bool quad = false;
+    if constexpr (C::kGlv) quad = glv && (fq ? fq[0] == '1' : nb <= 9472u);
+    if (quad) {
+        if constexpr (C::kGlv) k_butterfly_quad<C><<<(nb * 4 + 127) / 128, 128, 0, stream>>>(pf, t->d_flags, t->n, m, d_twiddles, scalar_be);
+    } else if (inlined && glv) k_butterfly<C, typename C::F, true><<<grid, 128, 0, stream>>>(pf, t->d_flags, t->n, m, d_twiddles, scalar_be);
     else if (inlined) k_butterfly<C, typename C::F, false><<<grid, 128, 0, stream>>>(pf, t->d_flags, t->n, m, d_twiddles, scalar_be);
     else if (glv) k_butterfly<C, typename C::FC, true><<<grid, 128, 0, stream>>>(pc, t->d_flags, t->n, m, d_twiddles, scalar_be);
     else k_butterfly<C, typename C::FC, false><<<grid, 128, 0, stream>>>(pc, t->d_flags, t->n, m, d_twiddles, scalar_be);

@@ -1599,6 +1599,84 @@ k_butterfly(Affine<F>* __restrict__ pts, uint8_t* __restrict__ flags, uint32_t n
     }
 }
 
+// The same stage with FOUR lanes per butterfly (quad.cuh), for stages of few butterflies where the 127 dependent doublings and
+// additions are pure latency (Porla's rebuild of 1024 blocks: 512 butterflies per stage on a 148-SM part).  BN254 / GLV only.
+// Differences from k_butterfly besides the lane layout: the table entry P + phi(P) stays in XYZZ form (the four-lane addition
+// takes general operands, so its normalisation -- one inversion per butterfly -- disappears), and the loop bound is the
+// warp's largest bit length so that all lanes shuffle together.  The joint normalisation of the two outputs is done by the
+// quad's first lane on the gathered points.
+template <class C>
+__global__ void __launch_bounds__(128)
+k_butterfly_quad(Affine<typename C::F>* __restrict__ pts, uint8_t* __restrict__ flags, uint32_t n, uint32_t m,
+                 const uint8_t* __restrict__ twiddles, int big_endian) {
+    using F = typename C::F;
+    using Q = QuadPoint<F>;
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, role = threadIdx.x & 3;
+    const uint32_t m2 = m >> 1;
+    const bool live = b < n / 2;
+    const uint32_t bb = live ? b : 0u;
+    const uint32_t j = bb % m2, k = (bb / m2) * m + j;
+    uint32_t s[8], k1[4], k2[4], n1, n2;
+    load_u256(twiddles, j, big_endian, s);
+    reduce_scalar<C>(s);
+    glv_split<C>(s, k1, k2, n1, n2);
+    Q a1 = Q::load_affine(pts + k + m2, false);
+    if (!live) a1 = Q::inf();
+    Q tab0 = a1, tab1 = a1;
+    {
+        F beta;
+#pragma unroll
+        for (int q = 0; q < 8; q++) beta.v[q] = C::glv_beta_mont(q);
+        const F bx = a1.c * beta;
+        if (role == 0) tab1.c = bx;
+        if (role == 1) {
+            if (n1) tab0.c = tab0.c.neg();
+            if (n2) tab1.c = tab1.c.neg();
+        }
+    }
+    const Q tab2 = quad_add_nl(tab0, tab1);               // (+-1 +- lambda) P
+    int top = 127;
+    while (top >= 0 && !(((k1[top >> 5] | k2[top >> 5]) >> (top & 31)) & 1u)) top--;
+    if (!live) top = -1;
+    top = __reduce_max_sync(kFullMask, top);
+    Q t = Q::inf();
+#pragma unroll 1
+    for (int i = top; i >= 0; i--) {
+        t = quad_dbl_nl(t);
+        const uint32_t bits = ((k1[i >> 5] >> (i & 31)) & 1u) | (((k2[i >> 5] >> (i & 31)) & 1u) << 1);
+        Q q = Q::inf();
+        if (bits == 1) q = tab0;
+        else if (bits == 2) q = tab1;
+        else if (bits == 3) q = tab2;
+        t = quad_add_nl(t, q);
+    }
+    Q a0 = Q::load_affine(pts + k, false);
+    if (!live) a0 = Q::inf();
+    Q tn = t;
+    if (role == 1) tn.c = tn.c.neg();
+    const XYZZ<F> r0 = quad_add_nl(t, a0).gather(), r1 = quad_add_nl(tn, a0).gather();
+    if (!live || role != 0) return;
+    Affine<F> o0 = Affine<F>::inf(), o1 = Affine<F>::inf();
+    if (r0.is_inf() || r1.is_inf()) {
+        o0 = r0.to_affine();
+        o1 = r1.to_affine();
+    } else {
+        F inv = (r0.zzz * r1.zzz).inverse();
+        F i0 = inv * r1.zzz, i1 = inv * r0.zzz;
+        F t0 = r0.zz * i0, t1 = r1.zz * i1;   // 1/zz = (zz/zzz)^2
+        o0.x = r0.x * t0.sqr();
+        o0.y = r0.y * i0;
+        o1.x = r1.x * t1.sqr();
+        o1.y = r1.y * i1;
+    }
+    st16(pts + k, o0);
+    st16(pts + k + m2, o1);
+    if (flags) {
+        flags[k] = o0.is_inf() ? 1 : 0;
+        flags[k + m2] = o1.is_inf() ? 1 : 0;
+    }
+}
+
 // ---- Server::align_MAC scalar preparation (/root/reference/porla/Server/Server.hpp:531-540, KZG branch)
 // rem = a mod m for a 512-bit a (16 LE limbs) and a 256-bit m: restoring shift-subtract, one bit per step.
 // The values are touched once and the kernel is a few hundred kilobytes of traffic per launch; no attempt
