@@ -638,7 +638,7 @@ void butterfly_impl(PointTable* t, uint32_t m, const uint8_t* d_twiddles, int sc
     bool quad = false;
     if constexpr (C::kGlv) quad = glv && (fq ? fq[0] == '1' : nb <= 9472u);
     if (quad) {
-        if constexpr (C::kGlv) k_butterfly_quad<C><<<(nb * 4 + 127) / 128, 128, 0, stream>>>(pf, t->d_flags, t->n, m, d_twiddles, scalar_be);
+        if constexpr (C::kGlv) k_butterfly_quad<C><<<(nb * 4 + kBflyQuadThreads - 1) / kBflyQuadThreads, kBflyQuadThreads, 0, stream>>>(pf, t->d_flags, t->n, m, d_twiddles, scalar_be);
     } else if (inlined && glv) k_butterfly<C, typename C::F, true><<<grid, 128, 0, stream>>>(pf, t->d_flags, t->n, m, d_twiddles, scalar_be);
     else if (inlined) k_butterfly<C, typename C::F, false><<<grid, 128, 0, stream>>>(pf, t->d_flags, t->n, m, d_twiddles, scalar_be);
     else if (glv) k_butterfly<C, typename C::FC, true><<<grid, 128, 0, stream>>>(pc, t->d_flags, t->n, m, d_twiddles, scalar_be);

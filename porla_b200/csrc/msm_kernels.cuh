@@ -1601,17 +1601,22 @@ k_butterfly(Affine<F>* __restrict__ pts, uint8_t* __restrict__ flags, uint32_t n
 
 // The same stage with FOUR lanes per butterfly (quad.cuh), for stages of few butterflies where the 127 dependent doublings and
 // additions are pure latency (Porla's rebuild of 1024 blocks: 512 butterflies per stage on a 148-SM part).  BN254 / GLV only.
-// Differences from k_butterfly besides the lane layout: the table entry P + phi(P) stays in XYZZ form (the four-lane addition
-// takes general operands, so its normalisation -- one inversion per butterfly -- disappears), and the loop bound is the
-// warp's largest bit length so that all lanes shuffle together.  The joint normalisation of the two outputs is done by the
-// quad's first lane on the gathered points.
+// Differences from k_butterfly besides the lane layout:
+//   - joint 2-bit windows over the halves of w = k1 + k2 lambda: a table of the 15 combinations d1 (+-P) + d2 (+-phi(P)),
+//     0 <= d1, d2 <= 3, kept in shared memory in XYZZ form (the four-lane addition takes general operands, so nothing is
+//     normalised: A, 2A, 3A, their images under phi -- one product by beta each -- and nine additions), then 64 steps of two
+//     doublings and ONE addition instead of 127 steps of a doubling and an addition;
+//   - the loop bound is the warp's largest digit count, so that all lanes shuffle together;
+//   - the joint normalisation of the two outputs is done by the quad's first lane on the gathered points.
+constexpr int kBflyQuadThreads = 64;     // 16 quads x 16 table entries x 128 B = 32 KB of shared memory
 template <class C>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kBflyQuadThreads)
 k_butterfly_quad(Affine<typename C::F>* __restrict__ pts, uint8_t* __restrict__ flags, uint32_t n, uint32_t m,
                  const uint8_t* __restrict__ twiddles, int big_endian) {
     using F = typename C::F;
     using Q = QuadPoint<F>;
-    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, role = threadIdx.x & 3;
+    __shared__ F tab[kBflyQuadThreads / 4][16][4];
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, role = threadIdx.x & 3, ql = threadIdx.x >> 2;
     const uint32_t m2 = m >> 1;
     const bool live = b < n / 2;
     const uint32_t bb = live ? b : 0u;
@@ -1622,32 +1627,49 @@ k_butterfly_quad(Affine<typename C::F>* __restrict__ pts, uint8_t* __restrict__ 
     glv_split<C>(s, k1, k2, n1, n2);
     Q a1 = Q::load_affine(pts + k + m2, false);
     if (!live) a1 = Q::inf();
-    Q tab0 = a1, tab1 = a1;
     {
         F beta;
 #pragma unroll
         for (int q = 0; q < 8; q++) beta.v[q] = C::glv_beta_mont(q);
-        const F bx = a1.c * beta;
-        if (role == 0) tab1.c = bx;
-        if (role == 1) {
-            if (n1) tab0.c = tab0.c.neg();
-            if (n2) tab1.c = tab1.c.neg();
+        Q mult[3];
+        mult[0] = a1;
+        mult[1] = quad_dbl_nl(a1);
+        mult[2] = quad_add_nl(mult[1], a1);
+#pragma unroll 1
+        for (int d = 1; d <= 3; d++) {
+            Q e1 = mult[d - 1], e2 = mult[d - 1];
+            const F bx = e2.c * beta;                      // phi: X -> beta X (lane 0)
+            if (role == 0) e2.c = bx;
+            if (role == 1) {
+                if (n1) e1.c = e1.c.neg();
+                if (n2) e2.c = e2.c.neg();
+            }
+            tab[ql][d][role] = e1.c;                       // d (+-P)
+            tab[ql][4 * d][role] = e2.c;                   // d (+-phi(P))
         }
+        __syncwarp();
+#pragma unroll 1
+        for (int d2 = 1; d2 <= 3; d2++) {
+#pragma unroll 1
+            for (int d1 = 1; d1 <= 3; d1++) {
+                const Q x = quad_add_nl(Q{tab[ql][d1][role]}, Q{tab[ql][4 * d2][role]});
+                tab[ql][d1 + 4 * d2][role] = x.c;
+            }
+        }
+        __syncwarp();
     }
-    const Q tab2 = quad_add_nl(tab0, tab1);               // (+-1 +- lambda) P
-    int top = 127;
-    while (top >= 0 && !(((k1[top >> 5] | k2[top >> 5]) >> (top & 31)) & 1u)) top--;
+    int top = 63;                                          // digit positions: bits 2 i, 2 i + 1 of k1 and of k2
+    while (top >= 0 && !(((k1[top >> 4] | k2[top >> 4]) >> ((top & 15) * 2)) & 3u)) top--;
     if (!live) top = -1;
     top = __reduce_max_sync(kFullMask, top);
     Q t = Q::inf();
 #pragma unroll 1
     for (int i = top; i >= 0; i--) {
         t = quad_dbl_nl(t);
-        const uint32_t bits = ((k1[i >> 5] >> (i & 31)) & 1u) | (((k2[i >> 5] >> (i & 31)) & 1u) << 1);
+        t = quad_dbl_nl(t);
+        const uint32_t e = ((k1[i >> 4] >> ((i & 15) * 2)) & 3u) | (((k2[i >> 4] >> ((i & 15) * 2)) & 3u) << 2);
         Q q = Q::inf();
-        if (bits == 1) q = tab0;
-        else if (bits == 2) q = tab1;
-        else if (bits == 3) q = tab2;
+        if (e != 0) q.c = tab[ql][e][role];
         t = quad_add_nl(t, q);
     }
     Q a0 = Q::load_affine(pts + k, false);
