@@ -70,7 +70,7 @@ PORLA_D XYZZ<F> block_tree_sum(const XYZZ<F>& v, uint32_t count, XYZZ<F>* sh) {
                     a.c = reinterpret_cast<const F*>(&sh[i])[role];
                     b.c = reinterpret_cast<const F*>(&sh[i + o])[role];
                 }
-                a = quad_add(a, b);
+                a = quad_add_nl(a, b);                         // one outlined copy: the call is short, the code stays in the i-cache
                 if (act) reinterpret_cast<F*>(&sh[i])[role] = a.c;
             }
         }
