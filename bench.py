@@ -519,10 +519,29 @@ def strong_scaling(args, lib, pb, torch, dist, rank, world, dev, stream, barrier
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_n = float(t.item())
         got_sharded = res[0]
-        tab.destroy()
-        del ss
         entry["ms_sharded"] = ms_n
         entry["points_per_s_sharded"] = n / (ms_n * 1e-3)
+        # ---- the same sharded MSM with the table treated as a FIXED base (an SRS): every rank expands its range once
+        # (porla_table_precompute), all windows share one bucket set, a rank contributes one partial sum
+        fixed = None
+        got_fixed = None
+        if lg <= 24:
+            t0 = time.perf_counter()
+            c_fb = tab.precompute(0, hi - lo, 1, stream=stream)
+            torch.cuda.synchronize()
+            pre_ms = (time.perf_counter() - t0) * 1e3
+            eng_fb = ShardedMsm(pb.CURVE_BN254, n, world, rank, dist, dev, fixed_base_bits=c_fb)
+
+            def one_fixed():
+                res[0] = eng_fb.msm(tab, ss.data_ptr(), hi - lo, pb.SCALAR_LE32)
+            ms_fb = timed_ms(one_fixed)
+            t = torch.tensor([ms_fb], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            got_fixed = res[0]
+            fixed = {"window_bits": c_fb, "ms_sharded": float(t.item()), "precompute_ms_once_per_rank": pre_ms,
+                     "table_bytes_per_rank": (hi - lo) * 64 * ((254 + c_fb) // c_fb)}
+        tab.destroy()
+        del ss
         # ---- the same MSM on rank 0's GPU alone (the other ranks wait at the two barriers of timed_ms)
         if rank == 0:
             parts = [strong_shard_inputs(torch, lg, world, r, dev) for r in range(world)]
@@ -539,8 +558,6 @@ def strong_scaling(args, lib, pb, torch, dist, rank, world, dev, stream, barrier
             def one_single():
                 res1[0] = tab1.msm_resident(ss_all.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32, stream=stream)
             ms_1 = timed_ms(one_single)
-            tab1.destroy()
-            del ss_all
             if res1[0] != want:
                 raise SystemExit("bench self-check failed: single-GPU 2^%d MSM differs from the closed form" % lg)
             if got_sharded != want:
@@ -549,9 +566,22 @@ def strong_scaling(args, lib, pb, torch, dist, rank, world, dev, stream, barrier
             entry["points_per_s_n1"] = n / (ms_1 * 1e-3)
             entry["speedup_vs_n1"] = ms_1 / ms_n
             entry["checked"] = "sharded and single-GPU results equal the closed form [sum s_i (i+1) mod r] G, bit-exact"
+            if fixed is not None:
+                c1 = tab1.precompute(0, n, 1, stream=stream)
+                torch.cuda.synchronize()
+                ms_1f = timed_ms(one_single)          # msm_resident takes the expansion once it exists
+                if res1[0] != want or got_fixed != want:
+                    raise SystemExit("bench self-check failed: fixed-base 2^%d MSM differs from the closed form" % lg)
+                fixed.update({"window_bits_n1": c1, "ms_n1": ms_1f, "speedup_vs_n1_fixed_base": ms_1f / fixed["ms_sharded"],
+                              "speedup_vs_n1_general": ms_1 / fixed["ms_sharded"],
+                              "checked": "sharded and single-GPU fixed-base results equal the closed form, bit-exact"})
+            tab1.destroy()
+            del ss_all
         else:
-            barrier()
-            barrier()
+            for _ in range(4 if fixed is not None else 2):      # the barriers of rank 0's timed_ms calls
+                barrier()
+        if fixed is not None:
+            entry["fixed_base"] = fixed
         out["2^%d" % lg] = entry
     return out
 

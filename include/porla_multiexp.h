@@ -141,6 +141,10 @@ void porla_msm_table_host_scalars_batch(const porla_table* t, int64_t first, con
 #define PORLA_PLAN_WINDOW(code) ((code) & 0xff)
 #define PORLA_PLAN_GLV_ON 0x100
 #define PORLA_PLAN_GLV_OFF 0x200
+/* Fixed-base form of the sharded MSM: every part's table carries the window expansion of porla_table_precompute with the
+ * SAME window size PORLA_PLAN_WINDOW(code); all windows then share one bucket set and a part contributes ONE XYZZ sum
+ * (nwin = 1 in porla_msm_finalize_host).  An SRS is a fixed base, so the expansion is built once per table. */
+#define PORLA_PLAN_FIXED 0x400
 void porla_msm_plan(int curve, int64_t n, int64_t nbatch, int window_bits, int* c_out, int* nwin_out);
 void porla_msm_window_sums_device(const porla_table* t, const void* d_scalars, int64_t n, int scalar_fmt,
                                   int window_bits, void* d_window_sums, void* cuda_stream);

@@ -730,12 +730,20 @@ void porla_msm_window_sums_device(const porla_table* t, const void* d_scalars, i
     if (n > (int64_t)t->t.n) die("porla_msm_window_sums_device: table shorter than the MSM");
     MsmOptions opt;
     decode_plan(window_bits, &opt);
-    const MsmPlan plan = msm_plan(t->t.curve, (uint32_t)n, 1, opt.window_bits, opt.glv);
-    opt.window_bits = plan.c;
-    opt.glv = plan.glv;
+    if (window_bits & PORLA_PLAN_FIXED) {   // the parts agreed on the expansion's window size: one sum per part
+        if (t->t.fb_c <= 0 || t->t.fb_c != PORLA_PLAN_WINDOW(window_bits) || (int64_t)t->t.fb_n != (int64_t)t->t.n)
+            die("porla_msm_window_sums_device: PORLA_PLAN_FIXED needs porla_table_precompute with the plan's window size");
+        opt.window_bits = t->t.fb_c;
+        opt.glv = 0;
+        opt.no_small = 1;
+    } else {
+        const MsmPlan plan = msm_plan(t->t.curve, (uint32_t)n, 1, opt.window_bits, opt.glv);
+        opt.window_bits = plan.c;
+        opt.glv = plan.glv;
+        opt.no_fixed_base = 1;  // the sharded protocol exchanges nwin window sums per rank
+    }
     opt.scalar_be = scalar_fmt == PORLA_SCALAR_BE32;
     opt.shared_points = 1;
-    opt.no_fixed_base = 1;  // the sharded protocol exchanges nwin window sums per rank
     opt.d_window_sums = d_window_sums;
     msm_device(t->t.curve, t->t, (const uint8_t*)d_scalars, (uint32_t)n, 1, opt, nullptr, nullptr, (cudaStream_t)cuda_stream);
 }

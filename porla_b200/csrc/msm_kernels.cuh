@@ -1275,7 +1275,7 @@ k_reduce(const XYZZ<typename C::FC>* __restrict__ buckets, uint32_t nb, uint32_t
 // profiles/r02c_bucket_slices_and_scan_reduce.md.)
 constexpr int kQuadsPerBlock = 64;
 constexpr int kQuadThreads = 4 * kQuadsPerBlock;
-constexpr int kTopMaxBlocks = kQuadsPerBlock;     // blocks per slot k_reduce_top combines with one quad each
+constexpr int kTopMaxBlocks = kQuadsPerBlock * 64;  // blocks per slot k_reduce_top combines (up to 64 per quad)
 
 // ONE copy of the four-lane addition / doubling per kernel (seven inlined field products each time otherwise)
 template <class F>
@@ -1374,29 +1374,52 @@ k_reduce_scan(XYZZ<typename C::F>* __restrict__ buckets, uint32_t nb, uint32_t l
     if (l == 0 && live) quad_from_shared(&sh[q]).store(out_w + (size_t)slot * blocks_per_slot + blk);
 }
 
-// One block per window slot, one quad per block of k_reduce_scan (nblk a power of two <= kTopMaxBlocks):
-// window sum = sum_b W_b + 2^log_u * sum_b b S_b, the second term again as the sum of the suffix sums RS_b, b >= 1.
+// One block per window slot; quad b takes `per` = nblk / 64 consecutive blocks of k_reduce_scan (nblk a power of two; per = 1
+// up to 64 blocks) and folds them with running sums -- S' = sum S_j, W' = sum W_j + 2^log_u * sum_j j S_j -- after which the
+// quads are combined like the blocks themselves: window sum = sum_b W'_b + 2^(log_u + log2 per) * sum_b b S'_b, the second
+// term as the sum of the suffix sums RS_b, b >= 1.
 // Bucket slice (MsmShape::slice_shift / slice_r): local bucket k stands for the digit magnitude (k << shift) + r + 1, so the
 // slot's sum is 2^shift * (Z1 - G) + (r + 1) G = 2^shift * Z1 - (2^shift - 1 - r) G with Z1 the 1-based sum and G = RS_0.
 template <class C>
 __global__ void __launch_bounds__(kQuadThreads)
-k_reduce_top(const XYZZ<typename C::F>* __restrict__ in_w, const XYZZ<typename C::F>* __restrict__ in_s, uint32_t nblk,
+k_reduce_top(const XYZZ<typename C::F>* __restrict__ in_w, const XYZZ<typename C::F>* __restrict__ in_s, uint32_t nblk_in,
              uint32_t log_u, uint32_t slice_shift, uint32_t slice_r, XYZZ<typename C::F>* __restrict__ wsum) {
     using F = typename C::F;
     using Q = QuadPoint<F>;
     __shared__ XYZZ<F> sh[kQuadsPerBlock];
     const uint32_t b = threadIdx.x >> 2;
-    const size_t at = (size_t)blockIdx.x * nblk + b;
+    const uint32_t per = nblk_in > (uint32_t)kQuadsPerBlock ? nblk_in / kQuadsPerBlock : 1u;
+    const uint32_t nblk = nblk_in / per;                     // quads at work
     const bool live = b < nblk;
-    Q a = Q::inf();
-    if (live) a = Q::load(in_s + at);
+    const size_t at = (size_t)blockIdx.x * nblk_in + (size_t)b * per;
+    Q a = Q::inf();                                          // S' of this quad's blocks
+    Q wq = Q::inf();                                         // W' of this quad's blocks
+    if (per == 1) {
+        if (live) {
+            a = Q::load(in_s + at);
+            wq = Q::load(in_w + at);
+        }
+    } else {
+        Q z = Q::inf();                                      // sum_j j S_j over the quad's blocks (block units)
+        for (uint32_t j = per; j-- > 0;) {
+            Q s = Q::inf(), w = Q::inf();
+            if (live) {
+                s = Q::load(in_s + at + j);
+                w = Q::load(in_w + at + j);
+            }
+            a = quad_add_nl(a, s);
+            wq = quad_add_nl(wq, w);
+            if (j != 0) z = quad_add_nl(z, a);
+        }
+        for (uint32_t d = 0; d < log_u; d++) z = quad_dbl_nl(z);
+        wq = quad_add_nl(wq, z);
+        for (uint32_t q = per; q > 1; q >>= 1) log_u++;      // a quad now stands for `per` blocks
+    }
     a = quad_suffix_scan(sh, b, b, nblk, a);                // quads >= nblk hold infinity and stay out of it
     const Q g = quad_from_shared(&sh[0]);                   // RS_0: the plain sum of the slot's buckets
     Q v = (b != 0 && live) ? a : Q::inf();
     for (uint32_t d = 0; d < log_u; d++) v = quad_dbl_nl(v);
-    Q w = Q::inf();
-    if (live) w = Q::load(in_w + at);
-    v = quad_add_nl(v, w);
+    v = quad_add_nl(v, wq);
     __syncthreads();
     quad_to_shared(&sh[b], v);
     __syncthreads();

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("PORLA_LIB") or os.path.join(os.path.dirname(os.path.a
 CURVE_BN254, CURVE_SECP256K1 = 0, 1
 SCALAR_BE32, SCALAR_LE32 = 0, 1
 POINT_BE64, POINT_LE64 = 0, 1
+PLAN_GLV_ON, PLAN_GLV_OFF, PLAN_FIXED = 0x100, 0x200, 0x400     # plan-code flags of porla_msm_plan (include/porla_multiexp.h)
 
 # every symbol include/porla_multiexp.h declares (checked by tests/test_abi_symbols.py)
 LEGACY_SYMBOLS = [

@@ -41,7 +41,9 @@ class ShardedMsm:
     data-path collective) and combines on rank 0: parts added window by window, Horner over the windows, normalise.
     All ranks use the window layout planned for the LARGEST shard, so their window sums are addable."""
 
-    def __init__(self, curve: int, n_total: int, world: int, rank: int, dist, device):
+    def __init__(self, curve: int, n_total: int, world: int, rank: int, dist, device, fixed_base_bits: int = 0):
+        """fixed_base_bits = c > 0: the table is a fixed base (an SRS) and every rank has expanded its range with
+        table.precompute(c) -- all windows share one bucket set, a rank contributes ONE partial sum (PORLA_PLAN_FIXED)."""
         import ctypes as C
         import torch
         from . import lib as L
@@ -52,6 +54,8 @@ class ShardedMsm:
         c_, w_ = C.c_int(0), C.c_int(0)
         self.lib.porla_msm_plan(curve, largest, 1, 0, C.byref(c_), C.byref(w_))
         self.plan_code, self.nwin = c_.value, w_.value
+        if fixed_base_bits > 0:
+            self.plan_code, self.nwin = fixed_base_bits | L.PLAN_FIXED | L.PLAN_GLV_OFF, 1
         self.wsum = torch.zeros(self.nwin * 128, dtype=torch.uint8, device=device)
         self.host = torch.zeros(world * self.nwin * 128, dtype=torch.uint8).pin_memory()
         self.out = (C.c_ubyte * 64)()

@@ -370,3 +370,31 @@ def test_two_rank_nccl_sliced_msm_closed_form(two_part):
         assert p.exitcode == 0
     want = _closed_form_bytes(1 << log2n, a, b).hex()
     assert got == (want, want)
+
+
+def test_fixed_base_window_sums_add_up_on_one_device():
+    """PORLA_PLAN_FIXED: two range shards whose tables carry the fixed-base expansion with the same window size contribute
+    one XYZZ sum each; combined with nwin = 1 they give the MSM.  A table without the expansion is refused upstream
+    (the call aborts), so only the accepted form is exercised here."""
+    import torch
+    lib = pb.load()
+    n, c = 60000, 14
+    pts, sc = _inputs(n, 123)
+    want = loader.bn254_msm(sc, pts, n, 8)
+    half = n // 2
+    tabs = [pb.Table.from_host(pb.CURVE_BN254, pts[:64 * half]), pb.Table.from_host(pb.CURVE_BN254, pts[64 * half:])]
+    for t in tabs:
+        assert t.precompute(c, n, 1) == c
+    d_sc = torch.frombuffer(bytearray(sc), dtype=torch.uint8).cuda()
+    ws = torch.zeros(2 * 128, dtype=torch.uint8, device="cuda")
+    code = c | pb.lib.PLAN_FIXED | pb.lib.PLAN_GLV_OFF
+    lib.porla_msm_window_sums_device(C.c_void_p(tabs[0].handle), C.c_void_p(d_sc.data_ptr()), half, pb.SCALAR_BE32, code,
+                                     C.c_void_p(ws.data_ptr()), None)
+    lib.porla_msm_window_sums_device(C.c_void_p(tabs[1].handle), C.c_void_p(d_sc.data_ptr() + 32 * half), n - half, pb.SCALAR_BE32, code,
+                                     C.c_void_p(ws.data_ptr() + 128), None)
+    torch.cuda.synchronize()
+    out = (C.c_ubyte * 64)()
+    lib.porla_msm_finalize_host(pb.CURVE_BN254, ws.cpu().numpy().tobytes(), 2, 1, code, pb.POINT_BE64, C.cast(out, C.c_void_p))
+    assert bytes(out) == want
+    for t in tabs:
+        t.destroy()
