@@ -774,9 +774,10 @@ def run_ours(args):
                 allp = torch.zeros(64 * world, dtype=torch.uint8, device=dev)
                 dist.all_gather_into_tensor(allp, part)
                 if rank == 0:
-                    acc = bytearray(allp[:64].cpu().numpy().tobytes())
+                    host_parts = allp.cpu().numpy().tobytes()          # ONE device-to-host read of the world x 64 bytes
+                    acc = bytearray(host_parts[:64])
                     for r in range(1, world):
-                        pb.bn254_add(acc, allp[64 * r:64 * r + 64].cpu().numpy().tobytes())
+                        pb.bn254_add(acc, host_parts[64 * r:64 * r + 64])
         barrier()
         dt = (time.perf_counter() - t0) / e2e_steps
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -785,6 +786,14 @@ def run_ours(args):
         dt = float(t.item())
         e2e = {"value": world * n / dt, "unit": "points/s", "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": 64,
                "ms_per_step": dt * 1e3, "api": "compute_multi_exp(GoSlice*, GoSlice*, GoInt, GoSlice*) with pinned host buffers"}
+        # host-to-device rate of the library's copy path with ALL ranks copying at once (what bounds e2e weak scaling on
+        # a box whose GPUs share the host's memory fabric): the slowest rank's figure
+        barrier()
+        gbs = lib.porla_debug_h2d_rate(C.c_void_p(pts_host.data_ptr()), n * 64, 5)
+        t = torch.tensor([gbs], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        e2e["h2d_gbs_all_ranks_copying"] = float(t.item())
         if world == 1:
             # (a) the same call with PAGEABLE buffers -- ordinary heap memory, what the reference's callers pass (`new[]`
             # arrays, Client.hpp:124-127): the library moves them through its pinned-ring copy pool (multi.cu)
