@@ -521,8 +521,17 @@ k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ copy, uint32_t n,
 //           global atomic on the bucket cursor, groups the pairs by bucket in shared memory and writes them
 //           to their final place in `sorted` as coalesced runs.  Pairs whose bucket lies beyond the shared
 //           histogram (sparse inputs) take one global atomic each.
-constexpr int kPartThreads = 512;
-constexpr int kPartPerThread = 4;
+#ifndef PORLA_PART_THREADS
+#define PORLA_PART_THREADS 512
+#endif
+#ifndef PORLA_PART_PER_THREAD
+#define PORLA_PART_PER_THREAD 4
+#endif
+#ifndef PORLA_PART_MIN_BLOCKS
+#define PORLA_PART_MIN_BLOCKS 2
+#endif
+constexpr int kPartThreads = PORLA_PART_THREADS;
+constexpr int kPartPerThread = PORLA_PART_PER_THREAD;
 constexpr int kPartTile = kPartThreads * kPartPerThread;   // 2048 scalars: 64 KB of reduced words in smem
 constexpr int kPartMaxBins = 1024;                         // coarse bins per window
 constexpr int kFineThreads = 512;
@@ -538,7 +547,7 @@ static __global__ void k_init_coarse(const uint32_t* __restrict__ offsets, uint3
 }
 
 template <class C, bool GLV>
-__global__ void __launch_bounds__(kPartThreads, 2)
+__global__ void __launch_bounds__(kPartThreads, PORLA_PART_MIN_BLOCKS)
 k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const uint8_t* __restrict__ inf_flags,
                    MsmShape sh, int lb, uint32_t* __restrict__ coarse_cursor, uint2* __restrict__ part) {
     extern __shared__ uint32_t smem[];
@@ -643,7 +652,7 @@ k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const ui
         __syncthreads();
         // exclusive scan of the bin counts (local offsets), one global reservation per non-empty bin
         {
-            uint32_t v[2], sum = 0;
+            uint32_t v[(kPartMaxBins + kPartThreads - 1) / kPartThreads], sum = 0;
             const uint32_t b0 = threadIdx.x * ept;
             for (uint32_t k = 0; k < ept; k++) {
                 v[k] = b0 + k < ncw ? cnt[b0 + k] : 0u;

@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p build/variants/$name
-for f in msm msm_bn254 msm_secp abi abi_secp pint; do
+for f in msm msm_bn254 msm_secp abi abi_secp pint multi lat; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -diag-suppress 128 "$@" -c porla_b200/csrc/$f.cu -o build/variants/$name/$f.o 2>/dev/null &
 done
 wait
