@@ -1335,7 +1335,7 @@ PORLA_D QuadPoint<F> quad_suffix_scan(XYZZ<F>* sh, uint32_t q, uint32_t l, uint3
 
 template <class C>
 __global__ void __launch_bounds__(kQuadThreads)
-k_reduce_scan(XYZZ<typename C::F>* __restrict__ buckets, uint32_t nb, uint32_t log_m, uint32_t group, uint32_t total_slots,
+k_reduce_scan(XYZZ<typename C::F>* buckets, uint32_t nb, uint32_t log_m, uint32_t group, uint32_t total_slots,
               XYZZ<typename C::F>* __restrict__ out_w, XYZZ<typename C::F>* __restrict__ out_s) {
     using F = typename C::F;
     using Q = QuadPoint<F>;
@@ -1357,11 +1357,14 @@ k_reduce_scan(XYZZ<typename C::F>* __restrict__ buckets, uint32_t nb, uint32_t l
     XYZZ<F>* base = buckets + (size_t)slot * nb + (size_t)blk * ((size_t)group << log_m);
     // 1. local suffix sums of the chunk [l m, (l + 1) m), in place
     XYZZ<F>* p = base + ((size_t)l << log_m);
-    Q a = Q::inf();
-    if (live) a = Q::load(p + (m - 1));
+    Q a = Q::inf(), nxt = Q::inf();
+    if (live) {
+        a = Q::load_coherent(p + (m - 1));
+        if (m > 1) nxt = Q::load_coherent(p + (m - 2));
+    }
     for (uint32_t k = m - 1; k-- > 0;) {
-        Q b = Q::inf();
-        if (live) b = Q::load(p + k);
+        const Q b = nxt;
+        if (live && k > 0) nxt = Q::load_coherent(p + (k - 1));       // the next bucket travels while this addition runs
         a = quad_add_nl(a, b);
         if (live) a.store(p + k);
     }
@@ -1371,9 +1374,11 @@ k_reduce_scan(XYZZ<typename C::F>* __restrict__ buckets, uint32_t nb, uint32_t l
     // 3. m * RS_l (l >= 1) + the local suffix sums l, l + group, ...
     Q v = l != 0 ? a : Q::inf();
     for (uint32_t d = 0; d < log_m; d++) v = quad_dbl_nl(v);
+    nxt = Q::inf();
+    if (live) nxt = Q::load_coherent(base + l);
     for (uint32_t i = 0; i < m; i++) {
-        Q b = Q::inf();
-        if (live) b = Q::load(base + l + (size_t)i * group);
+        const Q b = nxt;
+        if (live && i + 1 < m) nxt = Q::load_coherent(base + l + (size_t)(i + 1) * group);
         v = quad_add_nl(v, b);
     }
     __syncthreads();

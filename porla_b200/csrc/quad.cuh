@@ -60,6 +60,17 @@ struct QuadPoint {
         const int role = threadIdx.x & 3;
         return QuadPoint{ld16(reinterpret_cast<const F*>(p) + role)};
     }
+    // the same through the coherent path: for records the running kernel itself has written (k_reduce_scan re-reads the suffix
+    // sums other quads of its block stored; the non-coherent path of ld16 is only for data that is read-only during the launch)
+    PORLA_D static QuadPoint load_coherent(const XYZZ<F>* p) {
+        const int role = threadIdx.x & 3;
+        const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const F*>(p) + role);
+        QuadPoint r;
+        uint4* d = reinterpret_cast<uint4*>(&r.c);
+        d[0] = s[0];
+        d[1] = s[1];
+        return r;
+    }
     PORLA_D void store(XYZZ<F>* p) const {
         const int role = threadIdx.x & 3;
         st16(reinterpret_cast<F*>(p) + role, c);
