@@ -57,7 +57,9 @@ class ShardedMsm:
         if fixed_base_bits > 0:
             self.plan_code, self.nwin = fixed_base_bits | L.PLAN_FIXED | L.PLAN_GLV_OFF, 1
         self.wsum = torch.zeros(self.nwin * 128, dtype=torch.uint8, device=device)
-        self.host = torch.zeros(world * self.nwin * 128, dtype=torch.uint8).pin_memory()
+        self.host = torch.zeros(world * self.nwin * 128, dtype=torch.uint8)
+        if torch.cuda.is_available():        # (the CPU tests build the engine for its plan only)
+            self.host = self.host.pin_memory()
         self.out = (C.c_ubyte * 64)()
 
     def msm(self, table, d_scalars: int, n_local: int, scalar_fmt: int, out_fmt: int = 0, stream: int = 0):
