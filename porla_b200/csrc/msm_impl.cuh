@@ -341,11 +341,14 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     const uint64_t total_scalars = (uint64_t)n * nbatch;
 
     g_stage_timer.mark(kStageCount, stream);
-    // radix path without the exact histogram (k_coarse_count ... k_fine_local, msm_kernels.cuh): opt-in (PORLA_SORT_V2=1).
-    // Measured on one B200 (profiles/r02b_sort_without_exact_histogram.txt): the coarse count is 2.2x faster than the exact
-    // one (2^24: 1.57 -> 0.71 ms) but one block per coarse bin scattering 8-byte pairs loses more than that to uncoalesced
-    // writes (scatter 3.67 -> 6.05 ms), so the default stays the exact histogram + tile-staged fine pass.
-    const bool sort_v2 = radix && slice_shift == 0 && lb <= 10 && (size_t)ncoarse * 4 <= (160u << 10) && getenv("PORLA_SORT_V2") != nullptr;
+    // Radix path without the exact histogram (k_coarse_count ... k_fine_smem, msm_kernels.cuh): a coarse count places the coarse
+    // bins, the coarse partition fills them, and ONE block per bin sorts it by bucket through shared memory.  Used when a bin is
+    // expected to fit the block's shared memory (pairs / bins <= 0.95 kBigBin; bins that overflow on skewed inputs take the
+    // tile-based route); PORLA_SORT_V2=0 / 1 forces.  Measured at 2^24 (ncu): exact count 1.55 -> coarse count 0.52 ms, fine pass
+    // 2.07 -> see profiles/r02b_sort_without_exact_histogram.txt.
+    const char* sv2 = getenv("PORLA_SORT_V2");
+    const bool v2_fits = ncoarse > 0 && pairs_cap / ncoarse <= (uint64_t)(kBigBin * 0.95);
+    const bool sort_v2 = radix && slice_shift == 0 && lb <= 10 && (size_t)ncoarse * 4 <= (160u << 10) && (sv2 ? sv2[0] == '1' : v2_fits);
     PORLA_CUDA(cudaMemsetAsync(counters, 0, (size_t)nbt * 4, stream));
     PORLA_CUDA(cudaMemsetAsync(grand, 0, 4, stream));
     PORLA_CUDA(cudaMemsetAsync(long_count, 0, 4, stream));
@@ -355,6 +358,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
         const size_t smem0 = (size_t)ncoarse * 4;
         const size_t smem1 = ((size_t)9 * kPartTile + 2 * kPartMaxBins) * 4 + (size_t)kPartTile * 8;
         const size_t smem2 = (size_t)2 * kFineHist * 4 + (size_t)kFineTile * 8;
+        const size_t smem3 = (size_t)kBigBin * 6 + (size_t)kFineLocalBuckets * 4;
         std::call_once(attr_once_dev2[current_device()], [=] {
             PORLA_CUDA(cudaFuncSetAttribute(k_coarse_count<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 << 10));
             PORLA_CUDA(cudaFuncSetAttribute(k_partition_coarse<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
@@ -363,6 +367,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
                 PORLA_CUDA(cudaFuncSetAttribute(k_partition_coarse<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
             }
             PORLA_CUDA(cudaFuncSetAttribute(k_partition_fine_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            PORLA_CUDA(cudaFuncSetAttribute(k_fine_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
         });
         uint32_t* coarse_count = offsets;                 // the exact-offset array is not needed on this path: reuse it
         uint32_t* coarse_off = offsets + ncoarse + 1;     // (nbt >= 2 * (ncoarse + 1): 2^lb >= 16 buckets per bin)
@@ -395,7 +400,7 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
             k_partition_coarse<C, false><<<(n + kPartTile - 1) / kPartTile, kPartThreads, smem1, stream>>>(
                 d_scalars, opt.scalar_be, table.d_flags, sh, lb, coarse_cursor, part);
         LAUNCHED();
-        k_fine_local<<<ncoarse, kFineLocalThreads, 0, stream>>>(part, coarse_off, lb, sorted);
+        k_fine_smem<<<ncoarse, kFineSmemThreads, smem3, stream>>>(part, coarse_off, lb, sorted);
         LAUNCHED();
         // bins too long for one block (skewed inputs): counted, scanned and scattered by tiles; no-ops otherwise
         const uint32_t tiles = (uint32_t)((pairs_cap + kFineTile - 1) / kFineTile);

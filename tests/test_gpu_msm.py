@@ -158,11 +158,11 @@ def test_window_sizes_agree(window, monkeypatch):
     assert got == O.bn254_marshal(O.msm(BN, sc, pts))
 
 
-@pytest.mark.parametrize("switch", ["PORLA_REDUCE_V1", "PORLA_SORT_V2", "PORLA_ACC_AFFINE"])
+@pytest.mark.parametrize("switch", ["PORLA_REDUCE_V1=1", "PORLA_SORT_V2=0", "PORLA_SORT_V2=1", "PORLA_ACC_AFFINE=1"])
 @pytest.mark.parametrize("n,window", [(600, 9), (5000, 0), (70001, 0), ((1 << 19) + 5, 0)])
 def test_opt_in_kernel_variants_agree(switch, n, window, monkeypatch):
-    """The variants kept behind environment switches (measured slower, see profiles/r02*): the scan-form bucket reduction,
-    the sort without the exact histogram, the affine bucket accumulation.  Same bytes as the default pipeline; the large
+    """The variants behind environment switches (profiles/r02*): the round-1 bucket reduction, the sort with / without the
+    exact histogram, the affine bucket accumulation.  Same bytes as the default pipeline; the large
     sizes go through the resident path with points k_i G and the closed form (sum s_i k_i) G."""
     import torch
     rnd = random.Random(n)
@@ -174,7 +174,7 @@ def test_opt_in_kernel_variants_agree(switch, n, window, monkeypatch):
         args = (enc_points(pts), b"".join(map(be, sc)), n)
         want = pb.bn254_multi_exp(*args)
         assert want == O.bn254_marshal(O.msm(BN, sc, pts))
-        monkeypatch.setenv(switch, "1")
+        monkeypatch.setenv(*switch.split("="))
         assert pb.bn254_multi_exp(*args) == want
         return
     g = torch.Generator(device="cuda")
@@ -188,7 +188,7 @@ def test_opt_in_kernel_variants_agree(switch, n, window, monkeypatch):
     total = sum(k * sum(int(v) << (32 * j) for j, v in enumerate(row)) for k, row in zip(kv, sv.tolist())) % BN.n
     want = O.bn254_marshal(O.mul(BN, total, (1, 2)))
     assert tab.msm_resident(ss.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32) == want
-    monkeypatch.setenv(switch, "1")
+    monkeypatch.setenv(*switch.split("="))
     assert tab.msm_resident(ss.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32) == want
     tab.destroy()
 
