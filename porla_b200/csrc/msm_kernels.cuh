@@ -6,16 +6,21 @@
 //   * secp256k1_ecmult_pippenger_wnaf, /root/reference/porla/Utils/secp256k1_lib/ecmult_impl.h:492-567.
 //
 // Pipeline (one or many MSMs per launch sequence; "window slot" = (msm, window)):
-//   k_digits<COUNT>   signed c-bit recoding of every scalar, histogram of bucket sizes
-//   k_scan_*          exclusive prefix sum -> bucket offsets
-//   k_digits<SCATTER> recode again, scatter (point index | sign) into bucket-sorted order
-//   k_accumulate      one thread per bucket: XYZZ += affine over the bucket's slice
-//   k_reduce          per window slot: chunked running-sum reduction -> a few partials
-//   k_finalize        per MSM: sum partials, Horner over windows, to affine, serialise
+//   sort, small / batched    k_digits<COUNT> (signed c-bit recoding of every scalar, histogram of bucket sizes), k_scan_*
+//                            (bucket offsets), k_digits<SCATTER> (recode again, one returning atomic per pair)
+//   sort, single MSM >= 2^19 k_coarse_count + k_coarse_scan + k_partition_coarse + k_fine_smem (coarse histogram, shared-memory
+//                            radix partition, one block per coarse bin sorting it in shared memory; k_big_* for oversized bins),
+//                            or the exact histogram + k_partition_coarse + k_partition_fine when a bin cannot fit shared memory
+//   k_accumulate             one thread per SLICE of the bucket-sorted pair list: XYZZ += affine, partial sums at the cuts
+//   k_stitch, k_stitch_long  the cut buckets' partial sums
+//   k_reduce / k_reduce_scan per window slot: sum_k (k+1) B_k by chunked running sums (one thread per chunk) or, up to 600 k
+//                            buckets, by suffix scans on quads (four lanes per point, quad.cuh); k_window_sums / k_reduce_top
+//   k_finalize               per MSM: Horner over windows, to affine, serialise (single MSMs finish on the host instead)
+//   k_butterfly(_quad), k_data_butterfly, k_audit_aggregate, k_align_scalars: the SURVEY 8(f) operations
 //
 // Data layout in HBM: points are 64-byte affine records (x,y as 8 LE 32-bit limbs in the
 // field's internal form, infinity = all zero) read with 128-bit loads; buckets are 128-byte
-// XYZZ records; the sorted index array is 4 B per (point, window) pair.
+// XYZZ records; the sorted list is 8 B per (point, window) pair: bucket id, point index | sign.
 #pragma once
 #include "ec.cuh"
 #include "quad.cuh"
