@@ -543,7 +543,7 @@ constexpr int kFineThreads = 512;
 constexpr int kFinePerThread = 8;
 constexpr int kFineTile = kFineThreads * kFinePerThread;   // 4096 pairs
 constexpr uint32_t kFineHist = 4096;                       // shared histogram entries of pass 2
-constexpr uint32_t kMetaSkip = 1u << 30, kMetaFlip = 1u << 31, kMetaFlip2 = 1u << 29;   // carry bits: 0 .. nwin-1 (<= 28)
+constexpr uint32_t kMetaSkip = 1u << 30, kMetaFlip = 1u << 31, kMetaFlip2 = 1u << 29;
 
 static __global__ void k_init_coarse(const uint32_t* __restrict__ offsets, uint32_t nbt, int lb, uint32_t ncoarse,
                                      uint32_t* __restrict__ coarse_cursor) {
@@ -596,27 +596,6 @@ k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const ui
                     }
                 }
             }
-            uint32_t carry = 0;
-            for (int w = 0; w < sh.nwin; w++) {
-                uint32_t lo, hi, sft;
-                if (GLV) {
-                    const int h = w >= sh.glv_wh ? 1 : 0;
-                    const int wl = w - h * sh.glv_wh;
-                    if (wl == 0) carry = 0;
-                    const uint32_t pos = (uint32_t)wl * sh.c, word = pos >> 5;   // word <= 3 inside a 128-bit half
-                    sft = pos & 31;
-                    lo = s[4 * h + word];
-                    hi = word < 3 ? s[4 * h + word + 1] : 0u;
-                } else {
-                    const uint32_t pos = (uint32_t)w * sh.c, word = pos >> 5;
-                    sft = pos & 31;
-                    lo = s[word < 8 ? word : 8];
-                    hi = s[word < 7 ? word + 1 : 8];
-                }
-                m |= carry << w;
-                uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry;
-                carry = d > half;
-            }
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) sw[k * kPartTile + p] = s[k];
@@ -624,6 +603,12 @@ k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const ui
     }
     // ---- one window at a time
     const uint32_t ept = (ncw + kPartThreads - 1) / kPartThreads;   // bins per thread in the scan (<= 2)
+    // The windows are visited in order and a thread meets the same kPartPerThread scalars in every window, so the carries of
+    // the signed recoding live in registers across the loop (round 1 precomputed them per scalar with a dynamically indexed
+    // limb array: ~600 instructions per scalar of compare / select chains, a quarter of this kernel).
+    uint32_t carry[kPartPerThread];
+#pragma unroll
+    for (int q = 0; q < kPartPerThread; q++) carry[q] = 0;
     for (int w = 0; w < sh.nwin; w++) {
         for (uint32_t b = threadIdx.x; b < ncw; b += kPartThreads) cnt[b] = 0;
         __syncthreads();
@@ -634,6 +619,10 @@ k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const ui
         const uint32_t word_end = GLV ? 4u * h + 4u : 8u;       // first limb past the value being recoded
         const uint32_t key0 = sh.fixed_n ? 0u : (uint32_t)wl * sh.nbuckets;
         const uint32_t flip_bit = h ? 29u : 31u;
+        if (GLV && wl == 0) {
+#pragma unroll
+            for (int q = 0; q < kPartPerThread; q++) carry[q] = 0;     // second half: a new value
+        }
         // packed per item: bucket (20 bits) | rank within (block, bin) (11 bits) | sign
         uint32_t item[kPartPerThread];
 #pragma unroll
@@ -644,8 +633,9 @@ k_partition_coarse(const uint8_t* __restrict__ scalars, int big_endian, const ui
             if (!(m & kMetaSkip)) {
                 uint32_t lo = word < word_end ? sw[word * kPartTile + p] : 0u;
                 uint32_t hi = word + 1 < word_end ? sw[(word + 1) * kPartTile + p] : 0u;
-                uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + ((m >> w) & 1u);
+                uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry[q];
                 uint32_t dneg = d > half;
+                carry[q] = dneg;
                 uint32_t mag = dneg ? ((1u << sh.c) - d) : d;
                 const uint32_t lbk = slice_bucket(sh, mag);
                 if (lbk != 0xffffffffu) {
@@ -801,31 +791,32 @@ k_coarse_count(const uint8_t* __restrict__ scalars, int big_endian, const uint8_
                 }
             }
         }
-        uint32_t carry = 0;
-        for (int w = 0; w < sh.nwin; w++) {
-            uint32_t lo, hi, sft;
-            int wl = w;
-            if (GLV) {
-                const int h = w >= sh.glv_wh ? 1 : 0;
-                wl = w - h * sh.glv_wh;
-                if (wl == 0) carry = 0;
-                const uint32_t pos = (uint32_t)wl * sh.c, word = pos >> 5;
-                sft = pos & 31;
-                lo = s[4 * h + word];
-                hi = word < 3 ? s[4 * h + word + 1] : 0u;
-            } else {
-                const uint32_t pos = (uint32_t)w * sh.c, word = pos >> 5;
-                sft = pos & 31;
-                lo = s[word < 8 ? word : 8];
-                hi = s[word < 7 ? word + 1 : 8];
-            }
-            const uint32_t d = (__funnelshift_r(lo, hi, sft) & mask) + carry;
-            const uint32_t dneg = d > half;
-            carry = dneg;
-            const uint32_t mag = dneg ? ((1u << sh.c) - d) : d;
-            if (mag != 0) {
-                const uint32_t key0 = sh.fixed_n ? 0u : (uint32_t)wl * sh.nbuckets;
-                atomicAdd(&smem[(key0 + (mag - 1)) >> lb], 1u);
+        // Walk the value word by word with a 64-bit shift register: the limbs are indexed statically (a dynamically indexed
+        // register array cost ~40 instructions of compare / select chains per window here), one c-bit digit per turn.
+        const int halves = GLV ? 2 : 1, words = GLV ? 4 : 8, wins = GLV ? sh.glv_wh : sh.nwin;
+#pragma unroll
+        for (int h = 0; h < halves; h++) {
+            uint64_t acc = 0;
+            int have = 0, wl = 0;
+            uint32_t carry = 0;
+#pragma unroll
+            for (int k = 0; k <= words; k++) {
+                const uint32_t limb = k < words ? s[h * 4 + k] : 0u;      // one zero word past the top: the last digits
+                acc |= (uint64_t)limb << have;
+                have += 32;
+                while (wl < wins && (have >= sh.c || k == words)) {
+                    const uint32_t d = ((uint32_t)acc & mask) + carry;
+                    acc >>= sh.c;
+                    have -= sh.c;
+                    const uint32_t dneg = d > half;
+                    carry = dneg;
+                    const uint32_t mag = dneg ? ((1u << sh.c) - d) : d;
+                    if (mag != 0) {
+                        const uint32_t key0 = sh.fixed_n ? 0u : (uint32_t)wl * sh.nbuckets;
+                        atomicAdd(&smem[(key0 + (mag - 1)) >> lb], 1u);
+                    }
+                    wl++;
+                }
             }
         }
     }
