@@ -244,11 +244,11 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     uint32_t blocks_per_slot = (threads_per_slot + kRedThreads - 1) / kRedThreads;
     // Scan form on quads (k_reduce_scan + k_reduce_top: four lanes per point, 2.35 us per dependent addition instead of 6.9):
     // used while the reduction is bound by the depth of its additions, i.e. up to PORLA_REDUCE_QUAD_MAX buckets in total
-    // (default 600 k; above that k_reduce is near the multiplier pipe's limit and the quads' extra pipe work loses).  m = 2^log_m
+    // (default C::kReduceQuadMax: 600 k for BN254, 300 k for secp256k1; above that k_reduce is near the multiplier pipe's limit and the quads' extra pipe work loses).  m = 2^log_m
     // buckets per quad: the smallest chunk that leaves at most PORLA_REDUCE_QUADS quads in flight (default 148 x 64: one block
     // of 64 quads, 8 warps, per SM), at most 64 and at least what keeps a slot within kTopMaxBlocks blocks.
     // PORLA_REDUCE_V1=1 keeps the round-1 kernel at every size.
-    static const uint64_t quad_max = [] { const char* e = getenv("PORLA_REDUCE_QUAD_MAX"); return e ? (uint64_t)atoll(e) : 600000ull; }();
+    static const uint64_t quad_max = [] { const char* e = getenv("PORLA_REDUCE_QUAD_MAX"); return e ? (uint64_t)atoll(e) : (uint64_t)C::kReduceQuadMax; }();
     static const uint64_t quad_target = [] { const char* e = getenv("PORLA_REDUCE_QUADS"); return e && atoll(e) > 0 ? (uint64_t)atoll(e) : 148ull * kQuadsPerBlock; }();
     const bool reduce_v1 = getenv("PORLA_REDUCE_V1") != nullptr || (uint64_t)nbt > quad_max;
     uint32_t log_m = 0;
