@@ -371,6 +371,44 @@ def test_radix_partition_sort_matches_atomic_scatter_and_closed_form(curve, c, k
     tab.destroy()
 
 
+@pytest.mark.parametrize("in_bin", [34816, 34817, 70000])
+def test_fine_sort_capacity_boundary(in_bin, monkeypatch):
+    """The sort without the exact histogram keeps one coarse bin per block in shared memory, up to 34 816 pairs; a bin with
+    exactly that many pairs still takes it, one pair more sends the bin (and only it) through the tile-based route.  secp256k1
+    with 16-bit windows (no GLV): the low 16 bits of a scalar are its window-0 digit, so `in_bin` scalars get a digit in
+    1 .. 256 (coarse bin 0 of window 0: buckets 0 .. 255) and the others a digit above it."""
+    import numpy as np
+    import torch
+    c = SE
+    n = (1 << 19) + 37
+    g = torch.Generator(device="cuda")
+    g.manual_seed(in_bin)
+    ks = torch.randint(-2**31, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda", generator=g)
+    ks[:, 2:] = 0
+    ss = torch.randint(0, 2**31 - 1, (n, 8), dtype=torch.int32, device="cuda", generator=g)
+    ss[:, 7] &= 0x3FFFFFFF                                      # below n / 2: no min(s, n - s) flip, digits as written
+    low = torch.randint(257, 32768, (n,), dtype=torch.int32, device="cuda", generator=g)
+    low[:in_bin] = torch.randint(1, 257, (in_bin,), dtype=torch.int32, device="cuda", generator=g)
+    ss[:, 0] = (ss[:, 0] & ~0xFFFF) | low
+    monkeypatch.setenv("PORLA_WINDOW_BITS", "16")
+    tab = pb.Table.multiples_of_generator(pb.CURVE_SECP256K1, ks.data_ptr(), n, pb.SCALAR_LE32, on_device=True)
+    got = tab.msm_resident(ss.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32)
+    monkeypatch.setenv("PORLA_SORT_V2", "0")
+    assert tab.msm_resident(ss.data_ptr(), n, scalar_fmt=pb.SCALAR_LE32) == got
+
+    def to_ints(t):
+        a = t.cpu().numpy().view(np.uint32).astype(object)
+        v = a[:, 0]
+        for j in range(1, 8):
+            v = v + (a[:, j] << (32 * j))
+        return v
+    kv, sv = to_ints(ks), to_ints(ss)
+    total = int(sum((int(x) % c.n) * int(k) for x, k in zip(sv, kv)) % c.n)
+    exp = O.mul(c, total, (c.gx, c.gy))
+    assert got == be(exp[0]) + be(exp[1])
+    tab.destroy()
+
+
 def test_host_buffer_msm_pipelined_halves_match_single_pass(monkeypatch):
     """compute_multi_exp from host buffers at 2^19 + 3 terms runs as two pipelined halves (copy of the
     second overlaps the MSM of the first); must equal the single-pass result and the closed form."""
