@@ -352,7 +352,11 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
     PORLA_CUDA(cudaMemsetAsync(counters, 0, (size_t)nbt * 4, stream));
     PORLA_CUDA(cudaMemsetAsync(grand, 0, 4, stream));
     PORLA_CUDA(cudaMemsetAsync(long_count, 0, 4, stream));
-    if (!into) PORLA_CUDA(cudaMemsetAsync(buckets, 0, (size_t)nbt * sizeof(XYZZ<F>), stream));  // empty bucket = infinity
+    // empty bucket = infinity: the whole array is cleared, except on the sort_v2 path, whose fine pass knows the empty buckets of
+    // every coarse bin and clears just those (k_fine_smem / k_big_scan)
+    static_assert(sizeof(XYZZ<F>) == 128, "k_fine_smem / k_big_scan clear 128-byte bucket records");
+    if (!into && !sort_v2) PORLA_CUDA(cudaMemsetAsync(buckets, 0, (size_t)nbt * sizeof(XYZZ<F>), stream));
+    uint4* zero_buckets = into ? nullptr : reinterpret_cast<uint4*>(buckets);
     if (total_scalars && sort_v2) {
         static std::once_flag attr_once_dev2[kMaxDevices];   // function attributes are per device
         const size_t smem0 = (size_t)ncoarse * 4;
@@ -400,13 +404,13 @@ void msm_impl(const PointTable& table, const uint8_t* d_scalars, uint32_t n, uin
             k_partition_coarse<C, false><<<(n + kPartTile - 1) / kPartTile, kPartThreads, smem1, stream>>>(
                 d_scalars, opt.scalar_be, table.d_flags, sh, lb, coarse_cursor, part);
         LAUNCHED();
-        k_fine_smem<<<ncoarse, kFineSmemThreads, smem3, stream>>>(part, coarse_off, lb, sorted);
+        k_fine_smem<<<ncoarse, kFineSmemThreads, smem3, stream>>>(part, coarse_off, lb, sorted, zero_buckets);
         LAUNCHED();
         // bins too long for one block (skewed inputs): counted, scanned and scattered by tiles; no-ops otherwise
         const uint32_t tiles = (uint32_t)((pairs_cap + kFineTile - 1) / kFineTile);
         k_big_count<<<tiles, kFineThreads, 0, stream>>>(part, grand, coarse_off, lb, counters);
         LAUNCHED();
-        k_big_scan<<<ncoarse, kFineLocalThreads, 0, stream>>>(coarse_off, lb, counters);
+        k_big_scan<<<ncoarse, kFineLocalThreads, 0, stream>>>(coarse_off, lb, counters, zero_buckets);
         LAUNCHED();
         k_partition_fine_big<<<tiles, kFineThreads, smem2, stream>>>(part, grand, coarse_off, lb, counters, sorted);
         LAUNCHED();

@@ -856,14 +856,23 @@ k_coarse_scan(const uint32_t* __restrict__ coarse_count, uint32_t ncoarse, uint3
 // profiles/r02b_sort_without_exact_histogram.txt).  Six bytes of shared memory per pair: bins of up to kBigBin pairs.
 constexpr int kFineSmemThreads = 1024;
 static __global__ void __launch_bounds__(kFineSmemThreads, 1)
-k_fine_smem(const uint2* __restrict__ part, const uint32_t* __restrict__ coarse_off, int lb, uint2* __restrict__ sorted) {
+k_fine_smem(const uint2* __restrict__ part, const uint32_t* __restrict__ coarse_off, int lb, uint2* __restrict__ sorted,
+            uint4* __restrict__ zero_buckets) {
     extern __shared__ uint32_t smem[];
     uint32_t* out_y = smem;                                              // [kBigBin] point word of the pair at each position
     uint16_t* out_b = reinterpret_cast<uint16_t*>(out_y + kBigBin);      // [kBigBin] its bucket within the bin
     uint32_t* hist = reinterpret_cast<uint32_t*>(out_b + kBigBin);       // [kFineLocalBuckets] counts, then cursors
     __shared__ uint32_t total;
     const uint32_t start = coarse_off[blockIdx.x], cnt = coarse_off[blockIdx.x + 1] - start;
-    if (cnt == 0 || cnt > kBigBin) return;
+    // zero_buckets != nullptr: this pass also writes the EMPTY buckets of its bin (128-byte records of zeros = infinity), which
+    // replaces the memset of the whole bucket array (872 MB at 2^24) by the few buckets that really are empty
+    uint4* zb = zero_buckets ? zero_buckets + ((size_t)blockIdx.x << lb) * 8 : nullptr;
+    if (cnt == 0) {
+        if (zb)
+            for (uint32_t j = threadIdx.x; j < (8u << lb); j += kFineSmemThreads) zb[j] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    if (cnt > kBigBin) return;                              // k_big_scan zeroes this bin's empty buckets
     const uint32_t bmask = (1u << lb) - 1u;
     const uint2* src = part + start;
     for (uint32_t b = threadIdx.x; b < kFineLocalBuckets; b += kFineSmemThreads) hist[b] = 0;
@@ -884,6 +893,10 @@ k_fine_smem(const uint2* __restrict__ part, const uint32_t* __restrict__ coarse_
     // 2. exclusive scan of the (at most 1024) bucket counts: cursors
     {
         const uint32_t v = threadIdx.x < kFineLocalBuckets ? hist[threadIdx.x] : 0u;
+        if (zb && v == 0 && threadIdx.x <= bmask) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) zb[(size_t)threadIdx.x * 8 + k] = make_uint4(0u, 0u, 0u, 0u);
+        }
         const uint32_t ex = block_exclusive_scan(v, &total);
         if (threadIdx.x < kFineLocalBuckets) hist[threadIdx.x] = ex;
     }
@@ -951,15 +964,20 @@ k_big_count(const uint2* __restrict__ part, const uint32_t* __restrict__ total_p
 
 // block b: if bin b is big, counters[b << lb ..] <- its output offsets (bin start + exclusive prefix of the counts)
 static __global__ void __launch_bounds__(kFineLocalThreads)
-k_big_scan(const uint32_t* __restrict__ coarse_off, int lb, uint32_t* __restrict__ counters) {
+k_big_scan(const uint32_t* __restrict__ coarse_off, int lb, uint32_t* __restrict__ counters, uint4* __restrict__ zero_buckets) {
     __shared__ uint32_t total;
     if (!bin_is_big(coarse_off, blockIdx.x)) return;
     const uint32_t nb = 1u << lb;
     uint32_t* c = counters + ((size_t)blockIdx.x << lb);
+    uint4* zb = zero_buckets ? zero_buckets + ((size_t)blockIdx.x << lb) * 8 : nullptr;     // see k_fine_smem
     uint32_t carry = coarse_off[blockIdx.x];
     for (uint32_t base = 0; base < nb; base += kFineLocalThreads) {
         const uint32_t i = base + threadIdx.x;
         const uint32_t v = i < nb ? c[i] : 0u;
+        if (zb && i < nb && v == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) zb[(size_t)i * 8 + k] = make_uint4(0u, 0u, 0u, 0u);
+        }
         const uint32_t ex = block_exclusive_scan(v, &total);
         if (i < nb) c[i] = carry + ex;
         carry += total;
