@@ -127,10 +127,6 @@ __global__ void k_quad_op(int op, const Affine<typename C::F>* __restrict__ a, c
         g = g.dbl();
         r = QuadPoint<F>::scatter(g, (int)((i + 1) & 3));                          // 2 (A + B)
     }
-    else if (op == 100) r = A;
-    else if (op == 101) r.c = A.c * quad_xor(B.c, 2);
-    else if (op == 102) r = quad_add(A, B);
-    else if (op == 103) r = quad_dbl(A);
     if (i < n) r.store(out + i);
 }
 
@@ -158,8 +154,7 @@ extern "C" void porla_debug_quad_op(int curve, int op, const porla_table* a, con
                                                                nullptr);
     }
     PORLA_CUDA(cudaGetLastError());
-    if (op >= 100) PORLA_CUDA(cudaMemcpy(out64, d_x, (size_t)n * 128, cudaMemcpyDeviceToHost));     // raw records (debugging)
-    else PORLA_CUDA(cudaMemcpy(out64, d_out, (size_t)n * 64, cudaMemcpyDeviceToHost));
+    PORLA_CUDA(cudaMemcpy(out64, d_out, (size_t)n * 64, cudaMemcpyDeviceToHost));
     PORLA_CUDA(cudaFree(d_x));
     PORLA_CUDA(cudaFree(d_out));
 }
